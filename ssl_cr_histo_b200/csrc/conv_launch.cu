@@ -1,0 +1,152 @@
+// Host launcher for the tcgen05 implicit-GEMM conv kernel (conv_igemm.cuh).
+#include <stdio.h>
+
+#include "conv_igemm.cuh"
+#include "launch.h"
+#include "tmap.h"
+
+namespace b2n {
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int BLOCK_N, int KBYTES, int STAGES>
+static int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p,
+                          int grid, cudaStream_t stream) {
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return set_error("conv: cudaFuncSetAttribute(%d B): %s", L::TOTAL,
+                                           cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, kConvThreads, L::TOTAL, stream>>>(ma, mb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("conv launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int launch_conv(const ConvArgs& a, cudaStream_t stream) {
+  if (a.Cout % 64 != 0) return set_error("conv: Cout=%d must be a multiple of 64", a.Cout);
+  int kbytes;
+  if (a.Cin % 32 == 0) kbytes = 128;
+  else if (a.Cin == 16) kbytes = 64;
+  else return set_error("conv: Cin=%d must be 16 or a multiple of 32", a.Cin);
+  const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
+  const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
+  if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("conv: empty output");
+  const long long M = 1ll * a.N * P * Q;
+  if (M > 2000000000ll) return set_error("conv: too many output pixels");
+  int block_n = a.Cout % 128 == 0 ? 128 : 64;
+  if (a.force_block_n) block_n = a.force_block_n;
+  if (a.Cout % block_n != 0) return set_error("conv: Cout %% BLOCK_N != 0");
+
+  ConvParams p;
+  p.M_total = (int)M;
+  p.P = P; p.Q = Q;
+  p.Cout = a.Cout; p.Cin = a.Cin; p.R = a.R; p.S = a.S;
+  p.stride = a.stride; p.pad_h = a.pad_h_lo; p.pad_w = a.pad_w_lo;
+  p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.num_n_tiles = a.Cout / block_n;
+  p.kslices = a.Cin / (kbytes / 4);
+  p.out = a.out; p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.mask = a.mask;
+  p.relu = a.relu; p.round_tf32 = a.round_tf32; p.stats = a.stats;
+
+  CUtensorMap ma, mb;
+  if (make_im2col_map(&ma, a.x, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi, a.pad_w_lo,
+                      a.pad_w_hi, a.stride, kbytes / 4, kBlockM, kbytes))
+    return set_error("conv: %s", tmap_last_error());
+  const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;
+  if (make_tiled_map_2d(&mb, a.w, a.Cout, ktot, ktot, block_n, kbytes / 4, kbytes))
+    return set_error("conv: %s", tmap_last_error());
+
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = device_sm_count();
+  if (tiles < grid) grid = tiles;
+
+  if (kbytes == 128) {
+    if (block_n == 64) return launch_variant<64, 128, 6>(ma, mb, p, grid, stream);
+    if (block_n == 128) return launch_variant<128, 128, 5>(ma, mb, p, grid, stream);
+    if (block_n == 256) return launch_variant<256, 128, 4>(ma, mb, p, grid, stream);
+  } else {
+    if (block_n == 64) return launch_variant<64, 64, 8>(ma, mb, p, grid, stream);
+  }
+  return set_error("conv: no kernel variant for BLOCK_N=%d KBYTES=%d", block_n, kbytes);
+}
+
+}  // namespace b2n
+
+// ------------------------------------------------------------------ wgrad
+#include "conv_wgrad.cuh"
+
+namespace b2n {
+
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad_variant(const CUtensorMap& mx, const CUtensorMap& mdy,
+                                const WgradParams& p, int grid, cudaStream_t stream) {
+  using L = WgradSmem<BLOCK_N, STAGES>;
+  auto kern = conv_wgrad_kernel<BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return set_error("wgrad: cudaFuncSetAttribute(%d B): %s", L::TOTAL,
+                                           cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, kWgradThreads, L::TOTAL, stream>>>(mx, mdy, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("wgrad launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
+  if (a.Cin % 32 != 0) return set_error("wgrad: Cin=%d must be a multiple of 32", a.Cin);
+  if (a.Cout % 64 != 0) return set_error("wgrad: Cout=%d must be a multiple of 64", a.Cout);
+  const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
+  const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
+  if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("wgrad: empty problem");
+  const long long M = 1ll * a.N * P * Q;
+  if (M > 2000000000ll) return set_error("wgrad: too many pixels");
+  const int block_n = a.Cout % 256 == 0 ? 256 : (a.Cout % 128 == 0 ? 128 : 64);
+
+  WgradParams p;
+  p.M_total = (int)M; p.P = P; p.Q = Q;
+  p.Cout = a.Cout; p.Cin = a.Cin; p.R = a.R; p.S = a.S; p.stride = a.stride;
+  p.pad_h = a.pad_h_lo; p.pad_w = a.pad_w_lo;
+  p.Ktot = a.R * a.S * a.Cin;
+  p.num_m_tiles = (p.Ktot + 127) / 128;
+  p.num_n_tiles = a.Cout / block_n;
+  p.slabs_total = (int)((M + kWgradPX - 1) / kWgradPX);
+  const int out_tiles = p.num_m_tiles * p.num_n_tiles;
+  int splits = a.force_splits > 0 ? a.force_splits : device_sm_count() / out_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.slabs_total) splits = p.slabs_total;
+  p.splits = splits;
+  p.dw = a.dw;
+
+  CUtensorMap mx, mdy;
+  if (make_im2col_map(&mx, a.x, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi, a.pad_w_lo,
+                      a.pad_w_hi, a.stride, 32, kWgradPX, kSwizzle128Atom32))
+    return set_error("wgrad: %s", tmap_last_error());
+  if (make_tiled_map_2d(&mdy, a.dy, (uint64_t)M, a.Cout, a.Cout, kWgradPX, 32, kSwizzle128Atom32))
+    return set_error("wgrad: %s", tmap_last_error());
+
+  const int grid = out_tiles * splits;
+  if (block_n == 64) return launch_wgrad_variant<64, 6>(mx, mdy, p, grid, stream);
+  if (block_n == 128) return launch_wgrad_variant<128, 5>(mx, mdy, p, grid, stream);
+  return launch_wgrad_variant<256, 4>(mx, mdy, p, grid, stream);
+}
+
+}  // namespace b2n

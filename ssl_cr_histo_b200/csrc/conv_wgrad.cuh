@@ -1,0 +1,187 @@
+// Weight-gradient implicit GEMM on tcgen05 (sm_100a), TF32 operands / FP32 accumulate.
+//
+//   dW[k][tap*Cin + c] = sum_{pixels m} X[pixel(m) + tap][c] * dY[m][k]
+//
+// GEMM view: D[row = (tap,c)][col = k], reduction over output pixels.  Both operands are
+// "MN-major" for the tensor core (the reduction index -- the pixel -- is the slow smem axis).
+// MN-major TF32 operands must use the 128B-span / 32B-atom swizzle (UMMA layout type
+// SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms are 32 channels x 4
+// pixels (512 B), one K=8 MMA consumes two of them.
+//   * A rows: im2col-mode TMA boxes of (32 channels x PX pixels), one per 32-channel group;
+//   * B cols: tiled-mode TMA boxes of (32 dY channels x PX pixels).
+// Split-K over pixel slabs across CTAs; partial tiles are accumulated into dW with coalesced
+// fp32 reductions (dW must be zeroed by the caller).  Replaces cudnnConvolutionBackwardFilter
+// reached from loss.backward() (pretrain_BreastPathQ.py:60).
+#pragma once
+#include "ptx.cuh"
+
+namespace b2n {
+
+struct WgradParams {
+  int M_total;      // N*P*Q pixels of dY
+  int P, Q;
+  int Cout, Cin, R, S, stride, pad_h, pad_w;
+  int Ktot;         // R*S*Cin rows of dW^T
+  int num_m_tiles;  // ceil(Ktot / 128)
+  int num_n_tiles;  // Cout / BLOCK_N
+  int splits;
+  int slabs_total;  // ceil(M_total / PX)
+  float* dw;        // [Cout][Ktot]
+};
+
+constexpr int kWgradThreads = 192;
+constexpr int kWgradPX = 32;  // pixels per pipeline stage
+
+template <int BLOCK_N, int STAGES>
+struct WgradSmem {
+  static constexpr int A_BYTES = 128 * kWgradPX * 4;
+  static constexpr int B_BYTES = BLOCK_N * kWgradPX * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = RING_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_dy, const WgradParams p) {
+  using L = WgradSmem<BLOCK_N, STAGES>;
+  constexpr int PX = kWgradPX;
+  constexpr int CB = 32;                         // channels per TMA box (128 B rows)
+  constexpr int A_BOXES = 128 / CB;              // boxes per 128-row tile
+  constexpr int BOX_BYTES = PX * 128;
+  constexpr int B_BOXES = BLOCK_N / 32;
+  constexpr uint32_t ATOM = 4 * 128;             // 4 pixel rows of one 128B/32B-atom swizzle atom
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int bid = blockIdx.x;
+  const int m_tile = bid % p.num_m_tiles; bid /= p.num_m_tiles;
+  const int n_tile = bid % p.num_n_tiles; bid /= p.num_n_tiles;
+  const int split = bid;
+  const int slabs_per = (p.slabs_total + p.splits - 1) / p.splits;
+  const int slab_lo = split * slabs_per;
+  int slab_hi = slab_lo + slabs_per;
+  if (slab_hi > p.slabs_total) slab_hi = p.slabs_total;
+  const int num_slabs = slab_hi - slab_lo;  // may be <= 0 for trailing splits
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (num_slabs > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // rows of this tile that exist (last tile of a 9*64-row problem is half empty)
+        int valid_boxes = (p.Ktot - m_tile * 128 + CB - 1) / CB;
+        if (valid_boxes > A_BOXES) valid_boxes = A_BOXES;
+        const uint32_t tx_bytes = valid_boxes * BOX_BYTES + L::B_BYTES;
+        const int PQ = p.P * p.Q;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int sl = slab_lo; sl < slab_hi; ++sl) {
+          const int m0 = sl * PX;
+          const int img = m0 / PQ;
+          const int rem = m0 - img * PQ;
+          const int op = rem / p.Q;
+          const int oq = rem - op * p.Q;
+          const int base_w = oq * p.stride - p.pad_w;
+          const int base_h = op * p.stride - p.pad_h;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          for (int b = 0; b < valid_boxes; ++b) {
+            const int row0 = m_tile * 128 + b * CB;
+            const int tap = row0 / p.Cin;
+            const int c0 = row0 - tap * p.Cin;
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            tma_load_im2col_4d(sa + b * BOX_BYTES, &map_x, &full_bar[stage], c0, base_w, base_h,
+                               img, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+          }
+#pragma unroll
+          for (int b = 0; b < B_BOXES; ++b)
+            tma_load_2d(sb + b * BOX_BYTES, &map_dy, &full_bar[stage],
+                        n_tile * BLOCK_N + b * 32, m0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < num_slabs; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < PX / 8; ++j) {
+            // MN-major: LBO = stride between 32-channel groups (one TMA box), SBO = stride
+            // between 4-pixel groups (one swizzle atom); a K=8 step spans two atoms.
+            const uint64_t da = make_smem_desc(a_addr + j * 2 * ATOM, BOX_BYTES, ATOM, kSwz128B32);
+            const uint64_t db = make_smem_desc(b_addr + j * 2 * ATOM, BOX_BYTES, ATOM, kSwz128B32);
+            umma_tf32(tmem_base, da, db, idesc, (it | j) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar);
+      }
+    } else {
+      const int quad = warp & 3;
+      const int grow = m_tile * 128 + quad * 32 + lane;  // row of dW^T = tap*Cin + c
+      const bool row_ok = grow < p.Ktot;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32(t_addr + ch * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = p.dw + static_cast<size_t>(n_tile * BLOCK_N + ch * 32) * p.Ktot + grow;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, v[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace b2n

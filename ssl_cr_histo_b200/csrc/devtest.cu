@@ -1,0 +1,246 @@
+// Stand-alone bring-up test for the tcgen05 conv kernels (no Python / torch needed).
+// Usage: devtest <case>     -- runs one case, prints PASS/FAIL and mismatch diagnostics.
+//        devtest list       -- prints the number of cases.
+// Inputs are small integers / dyadic fractions, so TF32 products and FP32 sums are exact and
+// any mismatch against the CPU loops below is a layout / indexing bug, not rounding.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "launch.h"
+
+using namespace b2n;
+
+#define CK(x)                                                                     \
+  do {                                                                            \
+    cudaError_t e_ = (x);                                                         \
+    if (e_ != cudaSuccess) {                                                      \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                    \
+    }                                                                             \
+  } while (0)
+
+struct Case {
+  const char* name;
+  int kind;  // 0 = conv fwd, 1 = wgrad
+  int N, H, W, Cin, Cout, R, S, stride, plo, phi;
+  int epi;      // conv: 0 plain+stats, 1 scale/shift/relu/round, 2 resid+mask
+  int force;    // conv: force BLOCK_N; wgrad: force splits
+};
+
+static const Case kCases[] = {
+    {"fwd 1x1 tiny (pure GEMM, 1 k-step)", 0, 1, 8, 16, 32, 64, 1, 1, 1, 0, 0, 0, 0},
+    {"fwd 1x1 C64 (2 k-slices)", 0, 1, 8, 16, 64, 64, 1, 1, 1, 0, 0, 0, 0},
+    {"fwd 3x3 s1 C32->64 one tile", 0, 1, 8, 16, 32, 64, 3, 3, 1, 1, 1, 0, 0},
+    {"fwd 3x3 s1 C64->64 56x56 N2 (layer1)", 0, 2, 56, 56, 64, 64, 3, 3, 1, 1, 1, 0, 0},
+    {"fwd 3x3 s1 ragged M (N3 7x7 C64->128)", 0, 3, 7, 7, 64, 128, 3, 3, 1, 1, 1, 0, 0},
+    {"fwd 3x3 s2 C64->128 56->28 (layer2.0)", 0, 2, 56, 56, 64, 128, 3, 3, 2, 1, 1, 0, 0},
+    {"fwd 1x1 s2 C64->128 downsample", 0, 2, 56, 56, 64, 128, 1, 1, 2, 0, 0, 0, 0},
+    {"fwd 3x3 s1 C128->256 BLOCK_N=256", 0, 2, 14, 14, 128, 256, 3, 3, 1, 1, 1, 0, 256},
+    {"fwd 3x3 s1 C512->512 7x7 N5 (layer4)", 0, 5, 7, 7, 512, 512, 3, 3, 1, 1, 1, 0, 0},
+    {"fwd epilogue scale/shift/relu/round", 0, 2, 14, 14, 64, 128, 3, 3, 1, 1, 1, 1, 0},
+    {"fwd epilogue resid+mask", 0, 2, 14, 14, 64, 64, 3, 3, 1, 1, 1, 2, 0},
+    {"fwd 4x4 s1 pad(2,1) C32->64 (s2d stem)", 0, 2, 20, 20, 32, 64, 4, 4, 1, 2, 1, 0, 0},
+    {"fwd many tiles persistent (N8 56x56)", 0, 8, 56, 56, 64, 64, 3, 3, 1, 1, 1, 0, 0},
+    {"wgrad 1x1 tiny one slab", 1, 1, 4, 8, 32, 64, 1, 1, 1, 0, 0, 0, 1},
+    {"wgrad 1x1 C128->128 splits=1", 1, 1, 8, 16, 128, 128, 1, 1, 1, 0, 0, 0, 1},
+    {"wgrad 3x3 s1 C64->64 N2 14x14 splits=1", 1, 2, 14, 14, 64, 64, 3, 3, 1, 1, 1, 0, 1},
+    {"wgrad 3x3 s1 C64->64 56x56 N2 auto split", 1, 2, 56, 56, 64, 64, 3, 3, 1, 1, 1, 0, 0},
+    {"wgrad 3x3 s2 C64->128 56->28", 1, 2, 56, 56, 64, 128, 3, 3, 2, 1, 1, 0, 0},
+    {"wgrad 1x1 s2 C64->128", 1, 2, 56, 56, 64, 128, 1, 1, 2, 0, 0, 0, 0},
+    {"wgrad 3x3 C256->512 7x7 N5 ragged", 1, 5, 14, 14, 256, 512, 3, 3, 2, 1, 1, 0, 0},
+    {"wgrad 4x4 pad(2,1) C32->64 (s2d stem)", 1, 2, 20, 20, 32, 64, 4, 4, 1, 2, 1, 0, 0},
+};
+static const int kNumCases = sizeof(kCases) / sizeof(kCases[0]);
+
+static uint32_t g_seed = 12345;
+static int rnd(int lo, int hi) {  // inclusive
+  g_seed = g_seed * 1664525u + 1013904223u;
+  return lo + (int)((g_seed >> 8) % (uint32_t)(hi - lo + 1));
+}
+
+static int report(const char* what, const std::vector<float>& got, const std::vector<double>& ref,
+                  int ld, double tol) {
+  size_t bad = 0;
+  double maxerr = 0;
+  for (size_t i = 0; i < got.size(); ++i) {
+    double e = fabs((double)got[i] - ref[i]);
+    if (!(e <= tol * (1.0 + fabs(ref[i])))) {
+      if (bad < 12)
+        printf("   mismatch %s[%zu][%zu]: got %.6f expected %.6f\n", what, i / ld, i % ld,
+               got[i], ref[i]);
+      ++bad;
+    }
+    if (e > maxerr || e != e) maxerr = e;
+  }
+  printf("   %s: %zu / %zu mismatches, max abs err %.3e\n", what, bad, got.size(), maxerr);
+  if (bad) {
+    // row / column histogram of the failures helps identify layout bugs
+    size_t rows = got.size() / ld;
+    size_t badrows = 0, badcols = 0;
+    std::vector<char> rb(rows, 0), cb(ld, 0);
+    for (size_t i = 0; i < got.size(); ++i) {
+      double e = fabs((double)got[i] - ref[i]);
+      if (!(e <= tol * (1.0 + fabs(ref[i])))) { rb[i / ld] = 1; cb[i % ld] = 1; }
+    }
+    for (size_t r = 0; r < rows; ++r) badrows += rb[r];
+    for (int c = 0; c < ld; ++c) badcols += cb[c];
+    printf("   bad rows %zu / %zu, bad cols %zu / %d; first bad rows:", badrows, rows, badcols, ld);
+    int shown = 0;
+    for (size_t r = 0; r < rows && shown < 16; ++r)
+      if (rb[r]) { printf(" %zu", r); ++shown; }
+    printf("\n");
+  }
+  return bad ? 1 : 0;
+}
+
+static int run_conv(const Case& c) {
+  const int P = (c.H + c.plo + c.phi - c.R) / c.stride + 1;
+  const int Q = (c.W + c.plo + c.phi - c.S) / c.stride + 1;
+  const size_t M = (size_t)c.N * P * Q;
+  const int Ktot = c.R * c.S * c.Cin;
+  std::vector<float> x((size_t)c.N * c.H * c.W * c.Cin), w((size_t)c.Cout * Ktot);
+  for (auto& v : x) v = (float)rnd(-4, 4);
+  for (auto& v : w) v = (float)rnd(-2, 2) * 0.25f;
+  std::vector<float> scale(c.Cout), shift(c.Cout), resid(M * c.Cout), mask(M * c.Cout);
+  for (auto& v : scale) v = (float)rnd(1, 4) * 0.5f;
+  for (auto& v : shift) v = (float)rnd(-8, 8);
+  for (auto& v : resid) v = (float)rnd(-16, 16);
+  for (auto& v : mask) v = (float)rnd(-1, 1);
+
+  std::vector<double> ref(M * c.Cout, 0.0), ssum(c.Cout, 0.0), ssq(c.Cout, 0.0);
+  for (int n = 0; n < c.N; ++n)
+    for (int p = 0; p < P; ++p)
+      for (int q = 0; q < Q; ++q) {
+        const size_t m = ((size_t)n * P + p) * Q + q;
+        for (int k = 0; k < c.Cout; ++k) {
+          double acc = 0;
+          for (int r = 0; r < c.R; ++r) {
+            const int h = p * c.stride - c.plo + r;
+            if (h < 0 || h >= c.H) continue;
+            for (int s = 0; s < c.S; ++s) {
+              const int ww = q * c.stride - c.plo + s;
+              if (ww < 0 || ww >= c.W) continue;
+              const float* xp = &x[(((size_t)n * c.H + h) * c.W + ww) * c.Cin];
+              const float* wp = &w[(size_t)k * Ktot + (r * c.S + s) * c.Cin];
+              for (int ci = 0; ci < c.Cin; ++ci) acc += (double)xp[ci] * wp[ci];
+            }
+          }
+          ssum[k] += acc;
+          ssq[k] += acc * acc;
+          double o = acc;
+          if (c.epi == 1) { o = o * scale[k] + shift[k]; o = o > 0 ? o : 0; }
+          if (c.epi == 2) o += mask[m * c.Cout + k] > 0 ? resid[m * c.Cout + k] : 0.0;
+          ref[m * c.Cout + k] = o;
+        }
+      }
+
+  float *dx, *dw, *dout, *dscale, *dshift, *dresid, *dmask;
+  double* dstats;
+  CK(cudaMalloc(&dx, x.size() * 4));
+  CK(cudaMalloc(&dw, w.size() * 4));
+  CK(cudaMalloc(&dout, M * c.Cout * 4));
+  CK(cudaMalloc(&dscale, c.Cout * 4));
+  CK(cudaMalloc(&dshift, c.Cout * 4));
+  CK(cudaMalloc(&dresid, M * c.Cout * 4));
+  CK(cudaMalloc(&dmask, M * c.Cout * 4));
+  CK(cudaMalloc(&dstats, 2 * c.Cout * 8));
+  CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dscale, scale.data(), c.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dshift, shift.data(), c.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dresid, resid.data(), M * c.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dmask, mask.data(), M * c.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xFF, M * c.Cout * 4));
+  CK(cudaMemset(dstats, 0, 2 * c.Cout * 8));
+
+  ConvArgs a;
+  a.x = dx; a.w = dw; a.out = dout;
+  a.N = c.N; a.H = c.H; a.W = c.W; a.Cin = c.Cin; a.Cout = c.Cout; a.R = c.R; a.S = c.S;
+  a.stride = c.stride;
+  a.pad_h_lo = a.pad_w_lo = c.plo; a.pad_h_hi = a.pad_w_hi = c.phi;
+  a.force_block_n = c.force;
+  if (c.epi == 0) a.stats = dstats;
+  if (c.epi == 1) { a.scale = dscale; a.shift = dshift; a.relu = 1; a.round_tf32 = 1; }
+  if (c.epi == 2) { a.resid = dresid; a.mask = dmask; }
+  if (launch_conv(a, 0)) { printf("   launch_conv error: %s\n", last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("   kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+
+  std::vector<float> got(M * c.Cout);
+  CK(cudaMemcpy(got.data(), dout, got.size() * 4, cudaMemcpyDeviceToHost));
+  int fail = report("out", got, ref, c.Cout, 1e-5);
+  if (c.epi == 0) {
+    std::vector<double> st(2 * c.Cout);
+    CK(cudaMemcpy(st.data(), dstats, st.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<float> g1(c.Cout), g2(c.Cout);
+    for (int k = 0; k < c.Cout; ++k) { g1[k] = (float)st[k]; g2[k] = (float)st[c.Cout + k]; }
+    fail |= report("sum", g1, ssum, c.Cout, 1e-5);
+    fail |= report("sumsq", g2, ssq, c.Cout, 1e-5);
+  }
+  return fail;
+}
+
+static int run_wgrad(const Case& c) {
+  const int P = (c.H + c.plo + c.phi - c.R) / c.stride + 1;
+  const int Q = (c.W + c.plo + c.phi - c.S) / c.stride + 1;
+  const size_t M = (size_t)c.N * P * Q;
+  const int Ktot = c.R * c.S * c.Cin;
+  std::vector<float> x((size_t)c.N * c.H * c.W * c.Cin), dy(M * c.Cout);
+  for (auto& v : x) v = (float)rnd(-2, 2);
+  for (auto& v : dy) v = (float)rnd(-2, 2) * 0.5f;
+  std::vector<double> ref((size_t)c.Cout * Ktot, 0.0);
+  for (int n = 0; n < c.N; ++n)
+    for (int p = 0; p < P; ++p)
+      for (int q = 0; q < Q; ++q) {
+        const size_t m = ((size_t)n * P + p) * Q + q;
+        for (int r = 0; r < c.R; ++r) {
+          const int h = p * c.stride - c.plo + r;
+          if (h < 0 || h >= c.H) continue;
+          for (int s = 0; s < c.S; ++s) {
+            const int ww = q * c.stride - c.plo + s;
+            if (ww < 0 || ww >= c.W) continue;
+            const float* xp = &x[(((size_t)n * c.H + h) * c.W + ww) * c.Cin];
+            for (int k = 0; k < c.Cout; ++k) {
+              const double g = dy[m * c.Cout + k];
+              if (g == 0) continue;
+              double* rp = &ref[(size_t)k * Ktot + (r * c.S + s) * c.Cin];
+              for (int ci = 0; ci < c.Cin; ++ci) rp[ci] += g * xp[ci];
+            }
+          }
+        }
+      }
+  float *dx, *ddy, *ddw;
+  CK(cudaMalloc(&dx, x.size() * 4));
+  CK(cudaMalloc(&ddy, dy.size() * 4));
+  CK(cudaMalloc(&ddw, ref.size() * 4));
+  CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ddy, dy.data(), dy.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(ddw, 0, ref.size() * 4));
+  WgradArgs a;
+  a.x = dx; a.dy = ddy; a.dw = ddw;
+  a.N = c.N; a.H = c.H; a.W = c.W; a.Cin = c.Cin; a.Cout = c.Cout; a.R = c.R; a.S = c.S;
+  a.stride = c.stride;
+  a.pad_h_lo = a.pad_w_lo = c.plo; a.pad_h_hi = a.pad_w_hi = c.phi;
+  a.force_splits = c.force;
+  if (launch_wgrad(a, 0)) { printf("   launch_wgrad error: %s\n", last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("   kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<float> got(ref.size());
+  CK(cudaMemcpy(got.data(), ddw, got.size() * 4, cudaMemcpyDeviceToHost));
+  return report("dw", got, ref, Ktot, 1e-5);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2 || !strcmp(argv[1], "list")) { printf("%d\n", kNumCases); return 0; }
+  const int id = atoi(argv[1]);
+  if (id < 0 || id >= kNumCases) return 3;
+  const Case& c = kCases[id];
+  printf("[case %d] %s\n", id, c.name);
+  const int fail = c.kind == 0 ? run_conv(c) : run_wgrad(c);
+  printf("[case %d] %s\n", id, fail ? "FAIL" : "PASS");
+  return fail;
+}
