@@ -1,0 +1,147 @@
+/* b2n.h -- C ABI of libb2n.so: the B200-native (sm_100a) kernels behind the ResNet18
+ * RSP-pretext / consistency-training hot path of srinidhiPY/SSL_CR_Histo.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer owned by the caller (PyTorch's caching allocator
+ *     in the Python binding); the library allocates nothing and keeps no hidden stream:
+ *     `stream` is the caller's cudaStream_t (0 = legacy default stream); calls are async.
+ *   - activations are NHWC fp32; tensors that feed a tensor-core conv hold TF32-representable
+ *     values (the producing kernel rounds to nearest).  Parameters keep PyTorch layouts.
+ *   - return 0 on success, non-zero on error; b2n_last_error() gives the message (thread-local).
+ *     No exceptions cross the ABI.  The Python binding raises RuntimeError.
+ *   - re-entrant; the only process-wide state is cached function attributes / SM count.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository; "tv:" = site-packages/torchvision/models/resnet.py, the third-party module that
+ * models/net.py:32 instantiates).
+ */
+#ifndef B2N_H_
+#define B2N_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2N_ABI_VERSION 1
+
+int b2n_version(void);
+const char* b2n_last_error(void);
+/* 1 when the current device is compute capability 10.x, 0 otherwise, <0 when no device. */
+int b2n_device_ok(void);
+
+/* ---- tensor-core convolutions ---------------------------------------------------------- */
+
+/* Implicit-GEMM convolution, tcgen05 TF32 / FP32 accumulate.
+ *   y[n,p,q,k] = sum_{r,s,c} x[n, p*stride - pad_h_lo + r, q*stride - pad_w_lo + s, c]
+ *                             * w_packed[k][(r*S+s)*Cin + c]
+ * epilogue: v = acc; v = v*scale[k] (if scale); v += shift[k] (if shift);
+ *           v += resid[..] (if resid; only where mask[..] > 0 if mask); relu; TF32 round.
+ * stats (optional, [2][Cout] doubles, caller-zeroed): += per-channel sum / sum of squares of
+ * the raw accumulator -- the BatchNorm batch statistics.
+ * Requires Cin % 32 == 0, Cout % 64 == 0.  Used for the forward pass AND (with a
+ * b2n_pack_weight_dgrad pack) for the data gradient.
+ * Replaces: tv:92,96,100 (conv3x3 / downsample conv in BasicBlock.forward), tv:268 (stem, via
+ * the space-to-depth view), and the conv dgrad reached from loss.backward()
+ * (pretrain_BreastPathQ.py:60, eval_BreastPathQ_SSL_CR.py:99). */
+int b2n_conv_fwd(const float* x, const float* w_packed, float* y, int N, int H, int W, int Cin,
+                 int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
+                 int pad_w_hi, const float* scale, const float* shift, const float* resid,
+                 const float* mask, int relu, int round_tf32, double* stats, void* stream);
+
+/* Weight gradient, split-K over pixels, accumulated atomically:
+ *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
+ * dw_packed must be zeroed by the caller.  Replaces cudnnConvolutionBackwardFilter reached from
+ * loss.backward() (pretrain_BreastPathQ.py:60). */
+int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
+                   int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
+                   int pad_w_hi, void* stream);
+
+/* (K,C,R,S) parameter -> forward pack [K][(r*S+s)*C + c], data-gradient pack
+ * [C][((R-1-r)*S+(S-1-s))*K + k] (both TF32-rounded); packed weight gradient -> (K,C,R,S). */
+int b2n_pack_weight_fwd(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
+int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
+int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, void* stream);
+
+/* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
+/* x NCHW fp32 (N,3,H,W), H and W even -> xs NHWC (N,H/2,W/2,32) (12 real channels). */
+int b2n_stem_pack_input(const float* x_nchw, float* xs, int N, int H, int W, void* stream);
+/* w (K,3,7,7) -> ws [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
+int b2n_stem_pack_weight(const float* w, float* ws, int K, void* stream);
+int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream);
+
+/* ---- BatchNorm / ReLU / residual (tv:93-103,269-270; nn.BatchNorm2d train + eval) -------- */
+/* Batch statistics -> per-channel affine (scale = gamma*invstd, shift = beta - mean*scale),
+ * saves mean / invstd for backward, and applies `n_updates` running-stat updates in closed form
+ * (momentum, unbiased variance).  running_* may be null (no update). */
+int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                    int C, double count, float momentum, float eps, int n_updates, void* stream);
+/* eval mode: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean*scale */
+int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                     const float* running_var, float* scale, float* shift, int C, float eps,
+                     void* stream);
+/* out = [relu](scale*y + shift + residual); residual = res, or res_scale*res + res_shift when
+ * res_scale is given (downsample-branch BN); optional TF32 rounding.  [rows][C] row-major. */
+int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
+                 const float* res_scale, const float* res_shift, float* out, long long rows, int C,
+                 int relu, int round_tf32, void* stream);
+/* BatchNorm backward, two passes.  g' = g * [mask > 0] (mask = post-ReLU block output or null).
+ *   reduce: sums[0][c] += sum g', sums[1][c] += sum g' * xhat        (sums caller-zeroed)
+ *   apply : dy = gamma*invstd*(g' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0 */
+int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
+                      const float* invstd, double* sums, long long rows, int C, void* stream);
+int b2n_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
+                     const float* invstd, const float* gamma, const double* sums, float* dy,
+                     float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
+                     void* stream);
+/* up[n,2p,2q,:] = dy[n,p,q,:], zero elsewhere: stride-2 data gradient as a stride-1 conv. */
+int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
+                      void* stream);
+
+/* ---- pooling (tv:271 MaxPool2d(3,2,1) fused with bn1+relu; tv:278-279 avgpool+flatten) --- */
+int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
+                        unsigned char* argmax_idx /* may be null */, int N, int H, int W, int C,
+                        void* stream);
+int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* argmax_idx, const float* y,
+                         const float* scale, const float* shift, float* gz, int N, int H, int W,
+                         int C, void* stream);
+int b2n_avgpool_fwd(const float* a, float* e, int N, int HW, int C, void* stream);
+int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream);
+
+/* ---- fully-connected heads, exact FP32 (models/net.py:12-15,36-37,60-62,110) ------------- */
+int b2n_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,
+                   float* y, long long ldy, int rows, int in_f, int out_f, int relu, int accumulate,
+                   void* stream);
+int b2n_linear_bwd_data(const float* dy, long long lddy, const float* w, long long ldw, float* dx,
+                        long long lddx, const float* relu_mask, int rows, int in_f, int out_f,
+                        int accumulate, void* stream);
+int b2n_linear_bwd_weight(const float* dy, long long lddy, const float* x, long long ldx, float* dw,
+                          long long lddw, float* db /* may be null */, int rows, int in_f,
+                          int out_f, int accumulate, void* stream);
+
+/* ---- fused losses ------------------------------------------------------------------------
+ * mode 0: mean softmax-CE of logits_x vs targets_i + argmax (pretrain_BreastPathQ.py:56,66)
+ * mode 1: sup = MSE(logits_x, targets_f), cons = MSE(logits_u_w, logits_u_s)
+ *         (eval_BreastPathQ_SSL_CR.py:92-95)
+ * mode 2: sup = CE(logits_x, targets_i), cons = CE(logits_u_s, argmax logits_u_w)
+ *         (eval_Kather_SSL_CR.py:87-93)
+ * losses[3] = {sup, cons, sup + lambda_u*cons}; dlogits_* = d(total)/d(logits) (may be null). */
+int b2n_fused_loss(int mode, const float* logits_x, const long long* targets_i,
+                   const float* targets_f, const float* logits_u_w, const float* logits_u_s,
+                   int rows_x, int rows_u, int C, float lambda_u, float* losses, float* dlogits_x,
+                   float* dlogits_u, long long* argmax_x, long long* pseudo_labels, void* stream);
+
+/* ---- multi-tensor weight lerp ("EMA") -----------------------------------------------------
+ * dst[i] <- alpha*src[i] + (1-alpha)*dst[i]; write_back also stores the result into src[i].
+ * dst/src/numel are HOST arrays of n device pointers / element counts.
+ * alpha=1: teacher<-student hand-off (eval_BreastPathQ_SSL_CR.py:515-516);
+ * alpha=1-la_alpha, write_back=1: Lookahead pull (models/optimiser/RAdam/lookahead.py:96-97). */
+int b2n_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
+                   float alpha, int write_back, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2N_H_ */

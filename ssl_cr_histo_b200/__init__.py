@@ -1,0 +1,12 @@
+"""ssl_cr_histo_b200 -- B200-native (sm_100a) hot path of srinidhiPY/SSL_CR_Histo.
+
+Public surface (mirrors the reference's operator interface for this path):
+  net.Classifier / TripletNet / TripletNet_Finetune / FinetuneResNet   (models/net.py)
+  losses.cross_entropy / consistency_mse / consistency_ce               (fused loss kernels)
+  weights.lerp_ / teacher_handoff_ / lookahead_pull_                    (multi-tensor lerp)
+  ddp.GradAllReducer                                                    (one NCCL all-reduce / step)
+"""
+from . import net  # noqa: F401
+from . import losses, weights, ddp  # noqa: F401
+
+__all__ = ["net", "losses", "weights", "ddp"]

@@ -1,0 +1,97 @@
+"""ctypes binding of libb2n.so (the C ABI declared in include/b2n.h).
+
+There is no CPU fallback: if the library cannot be loaded, or an entry point reports an
+error, a RuntimeError is raised.  Tensors are passed as raw device pointers; every call is
+enqueued on ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2n.so")
+
+P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
+
+# name -> argument ctypes (the trailing stream argument is appended automatically)
+_SIGNATURES = {
+    "b2n_conv_fwd": [P, P, P] + [I] * 12 + [P, P, P, P, I, I, P],
+    "b2n_conv_wgrad": [P, P, P] + [I] * 12,
+    "b2n_pack_weight_fwd": [P, P, I, I, I, I],
+    "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
+    "b2n_unpack_wgrad": [P, P, I, I, I, I],
+    "b2n_stem_pack_input": [P, P, I, I, I],
+    "b2n_stem_pack_weight": [P, P, I],
+    "b2n_stem_unpack_wgrad": [P, P, I],
+    "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],
+    "b2n_bn_fold_eval": [P] * 6 + [I, F],
+    "b2n_bn_apply": [P] * 7 + [LL, I, I, I],
+    "b2n_bn_bwd_reduce": [P] * 6 + [LL, I],
+    "b2n_bn_bwd_apply": [P] * 10 + [LL, I, I],
+    "b2n_upsample_zero": [P, P] + [I] * 6,
+    "b2n_bn_relu_maxpool": [P] * 5 + [I] * 4,
+    "b2n_maxpool_relu_bwd": [P] * 6 + [I] * 4,
+    "b2n_avgpool_fwd": [P, P, I, I, I],
+    "b2n_avgpool_bwd": [P, P, I, I, I],
+    "b2n_linear_fwd": [P, LL, P, LL, P, P, LL, I, I, I, I, I],
+    "b2n_linear_bwd_data": [P, LL, P, LL, P, LL, P, I, I, I, I],
+    "b2n_linear_bwd_weight": [P, LL, P, LL, P, LL, P, I, I, I, I],
+    "b2n_fused_loss": [I, P, P, P, P, P, I, I, I, F, P, P, P, P, P],
+    "b2n_lerp_multi": [P, P, P, I, F, I],
+}
+EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok"] + list(_SIGNATURES)
+
+_lib = None
+# bumped whenever a kernel writes parameters behind autograd's back (lerp), so that cached
+# weight packs keyed on tensor._version are invalidated
+WEIGHT_EPOCH = 0
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError("libb2n.so is missing (%s); run __graft_entry__.build()" % LIB_PATH)
+        from . import build as _build
+
+        _build.build_lib()
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.b2n_version.restype = c_int
+    lib.b2n_last_error.restype = c_char_p
+    lib.b2n_device_ok.restype = c_int
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = list(sig) + [c_void_p]
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def _conv(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point on the current CUDA stream; raise on a non-zero return code."""
+    lib = load()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(lib, name)(*[_conv(a) for a in args], stream)
+    if rc != 0:
+        raise RuntimeError("%s failed: %s" % (name, lib.b2n_last_error().decode()))
+
+
+def require_device(t: torch.Tensor, what: str = "input") -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            "ssl_cr_histo_b200 runs only on CUDA (sm_100a) tensors; got a %s %s -- there is no "
+            "CPU fallback" % (t.device.type, what))

@@ -42,4 +42,58 @@ struct WgradArgs {
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t stream);
 
+
+// ---- element-wise / small kernels (bn.cu, stem_pool.cu, pack.cu, linear.cu, loss_lerp.cu) ----
+int launch_bn_finalize(const double* stats, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float* scale, float* shift,
+                       float* mean, float* invstd, int C, double count, float momentum, float eps,
+                       int n_updates, cudaStream_t stream);
+int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                        float* scale, float* shift, int C, float eps, cudaStream_t stream);
+int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
+                    const float* res_scale, const float* res_shift, float* out, long long rows,
+                    int C, int relu, int round_tf32, cudaStream_t stream);
+int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
+                         const float* invstd, double* sums, long long rows, int C,
+                         cudaStream_t stream);
+int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
+                        const float* invstd, const float* gamma, const double* sums, float* dy,
+                        float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
+                        cudaStream_t stream);
+int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
+                         cudaStream_t stream);
+int launch_stem_pack_input(const float* x, float* xs, int N, int H, int W, cudaStream_t stream);
+int launch_stem_pack_weight(const float* w, float* ws, int K, cudaStream_t stream);
+int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream);
+int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
+                           unsigned char* idx, int N, int H, int W, int C, cudaStream_t stream);
+int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
+                            const float* scale, const float* shift, float* gz, int N, int H, int W,
+                            int C, cudaStream_t stream);
+int launch_avgpool_fwd(const float* a, float* e, int N, int HW, int C, cudaStream_t stream);
+int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream);
+int launch_pack_fwd(const float* src, float* dst, int K, int C, int R, int S, cudaStream_t stream);
+int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
+                      cudaStream_t stream);
+int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S,
+                        cudaStream_t stream);
+int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,
+                      float* y, long long ldy, int rows, int in_f, int out_f, int relu,
+                      int accumulate, cudaStream_t stream);
+int launch_linear_bwd_data(const float* dy, long long lddy, const float* w, long long ldw,
+                           float* dx, long long lddx, const float* mask, int rows, int in_f,
+                           int out_f, int accumulate, cudaStream_t stream);
+int launch_linear_bwd_weight(const float* dy, long long lddy, const float* x, long long ldx,
+                             float* dw, long long lddw, int rows, int in_f, int out_f,
+                             int accumulate, cudaStream_t stream);
+int launch_colsum(const float* dy, long long lddy, float* db, int rows, int out_f, int accumulate,
+                  cudaStream_t stream);
+int launch_fused_loss(int mode, const float* logits_x, const long long* targets_i,
+                      const float* targets_f, const float* logits_u_w, const float* logits_u_s,
+                      int rows_x, int rows_u, int C, float lambda_u, float* losses,
+                      float* dlogits_x, float* dlogits_u, long long* argmax_x,
+                      long long* pseudo_out, cudaStream_t stream);
+int launch_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
+                      float alpha, int write_back, cudaStream_t stream);
+
 }  // namespace b2n

@@ -1,0 +1,133 @@
+// FP32 SIMT GEMM for the small fully-connected heads: the pair-MLP Linear(1024,512)+ReLU+
+// Linear(512,256) (models/net.py:36-37,60-62), Classifier Linear(768,128)+ReLU+Linear(128,C)
+// (models/net.py:12-15) and FinetuneResNet Linear(768,C) (models/net.py:110).  These are
+// < 0.1 % of the step's FLOPs, so they stay in exact FP32 FMA arithmetic (no TF32 rounding in
+// front of the logits) -- 64x64x16 tiles, 4x4 outputs per thread.
+#include "launch.h"
+
+namespace b2n {
+
+// C[m][n] = sum_k A(m,k) * B(k,n)  (+ bias[n]) (relu) (* [mask[m][n] > 0]) (+= when accumulate)
+// A(m,k) = a[m*sam + k*sak], B(k,n) = b[k*sbk + n*sbn], C row-major with pitch ldc.
+struct GemmArgs {
+  const float* a; long long sam, sak;
+  const float* b; long long sbk, sbn;
+  float* c; long long ldc;
+  const float* bias;   // [N] or null
+  const float* mask;   // [M][ldc] or null
+  int M, N, K;
+  int relu;
+  int accumulate;
+};
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  __shared__ float As[TK][TM + 1];
+  __shared__ float Bs[TK][TN + 1];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a 4 x 4 micro-tile
+  float acc[4][4] = {};
+  const bool a_kfast = g.sak == 1;  // choose the smem fill order that keeps gmem reads coalesced
+  const bool b_kfast = g.sbk == 1;
+  for (int k0 = 0; k0 < g.K; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < (TM * TK) / 256; ++i) {
+      const int e = tid + i * 256;
+      const int mm = a_kfast ? e / TK : e % TM;
+      const int kk = a_kfast ? e % TK : e / TM;
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < g.K) ? g.a[m * g.sam + k * g.sak] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < (TN * TK) / 256; ++i) {
+      const int e = tid + i * 256;
+      const int nn = b_kfast ? e / TK : e % TN;
+      const int kk = b_kfast ? e % TK : e / TN;
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < g.N && k < g.K) ? g.b[k * g.sbk + n * g.sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias != nullptr) v += g.bias[n];
+      if (g.relu) v = fmaxf(v, 0.f);
+      const size_t o = static_cast<size_t>(m) * g.ldc + n;
+      if (g.mask != nullptr && !(g.mask[o] > 0.f)) v = 0.f;
+      if (g.accumulate) v += g.c[o];
+      g.c[o] = v;
+    }
+  }
+}
+
+static int run_gemm(const GemmArgs& g, cudaStream_t stream, const char* who) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM);
+  sgemm_kernel<<<grid, 256, 0, stream>>>(g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("%s: %s", who, cudaGetErrorString(e));
+  return 0;
+}
+
+// y[n][o] = act(x[n][:] . w[o][:] + b[o]);  x pitch ldx, y pitch ldy, w pitch ldw
+int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,
+                      float* y, long long ldy, int rows, int in_f, int out_f, int relu,
+                      int accumulate, cudaStream_t stream) {
+  GemmArgs g{x, ldx, 1, w, 1, ldw, y, ldy, b, nullptr, rows, out_f, in_f, relu, accumulate};
+  return run_gemm(g, stream, "linear_fwd");
+}
+// dx[n][i] = sum_o dy[n][o] * w[o][i]   (optionally gated by mask > 0, optionally accumulated)
+int launch_linear_bwd_data(const float* dy, long long lddy, const float* w, long long ldw,
+                           float* dx, long long lddx, const float* mask, int rows, int in_f,
+                           int out_f, int accumulate, cudaStream_t stream) {
+  GemmArgs g{dy, lddy, 1, w, ldw, 1, dx, lddx, nullptr, mask, rows, in_f, out_f, 0, accumulate};
+  return run_gemm(g, stream, "linear_bwd_data");
+}
+// dw[o][i] (+)= sum_n dy[n][o] * x[n][i]
+int launch_linear_bwd_weight(const float* dy, long long lddy, const float* x, long long ldx,
+                             float* dw, long long lddw, int rows, int in_f, int out_f,
+                             int accumulate, cudaStream_t stream) {
+  GemmArgs g{dy, 1, lddy, x, ldx, 1, dw, lddw, nullptr, nullptr, out_f, in_f, rows, 0, accumulate};
+  return run_gemm(g, stream, "linear_bwd_weight");
+}
+
+// db[o] (+)= sum_n dy[n][o]
+__global__ void colsum_kernel(const float* __restrict__ dy, long long lddy, float* __restrict__ db,
+                              int rows, int out_f, int accumulate) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out_f) return;
+  float acc = 0.f;
+  for (int n = 0; n < rows; ++n) acc += dy[static_cast<size_t>(n) * lddy + o];
+  db[o] = accumulate ? db[o] + acc : acc;
+}
+int launch_colsum(const float* dy, long long lddy, float* db, int rows, int out_f, int accumulate,
+                  cudaStream_t stream) {
+  colsum_kernel<<<(out_f + 127) / 128, 128, 0, stream>>>(dy, lddy, db, rows, out_f, accumulate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("colsum: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace b2n

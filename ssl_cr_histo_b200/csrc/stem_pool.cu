@@ -1,0 +1,254 @@
+// Stem re-layout, max-pool and average-pool kernels (HBM-bound).
+//
+// The 7x7/stride-2 stem convolution (torchvision resnet.py:197, applied :268) is run on the
+// tensor cores as a 4x4/stride-1 convolution over a 2x2 space-to-depth view of the input:
+//   xs[n, i, j, (dy*2+dx)*3 + c] = x[n, c, 2i+dy, 2j+dx]         (12 real + 20 zero channels)
+//   ws[k, tr, ts, (dy*2+dx)*3 + c] = w[k, c, 2tr+dy-1, 2ts+dx-1] (zero when out of the 7x7 window)
+//   out[p, q] = sum xs[p-2+tr, q-2+ts, :] . ws[:, tr, ts, :]      (padding 2 low / 1 high)
+// The channel count is padded to 32 so that the same 128-byte-row TMA boxes / UMMA layouts as
+// every other conv (forward and weight-gradient) apply.
+#include <float.h>
+
+#include "launch.h"
+#include "ptx.cuh"
+
+namespace b2n {
+
+constexpr int kStemC = 32;
+
+// x: NCHW fp32 (N,3,H,W), H and W even.  xs: NHWC (N,H/2,W/2,32), TF32-rounded.
+__global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __restrict__ xs, int N,
+                                       int H, int W) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const size_t total = static_cast<size_t>(N) * H2 * W2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += stride) {
+    const int j = static_cast<int>(t % W2);
+    const int i = static_cast<int>((t / W2) % H2);
+    const int n = static_cast<int>(t / (static_cast<size_t>(W2) * H2));
+    float v[12];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* plane = x + (static_cast<size_t>(n) * 3 + c) * H * W;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float2 p = *reinterpret_cast<const float2*>(plane + static_cast<size_t>(2 * i + dy) * W + 2 * j);
+        v[(dy * 2 + 0) * 3 + c] = tf32_rn(p.x);
+        v[(dy * 2 + 1) * 3 + c] = tf32_rn(p.y);
+      }
+    }
+    float4* dst = xs + t * (kStemC / 4);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+#pragma unroll
+    for (int k = 3; k < kStemC / 4; ++k) dst[k] = make_float4(0, 0, 0, 0);
+  }
+}
+
+// w: (K,3,7,7) -> ws: [K][16 taps][32], TF32-rounded.  unpack = the transpose map for grads.
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, float* __restrict__ ws, int K) {
+  const int total = K * 16 * kStemC;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int ch = t % kStemC;
+    const int tap = (t / kStemC) % 16;
+    const int k = t / (kStemC * 16);
+    float v = 0.f;
+    if (ch < 12) {
+      const int c = ch % 3, dd = ch / 3, dy = dd >> 1, dx = dd & 1;
+      const int r = 2 * (tap >> 2) + dy - 1, s = 2 * (tap & 3) + dx - 1;
+      if (r >= 0 && r < 7 && s >= 0 && s < 7) v = tf32_rn(w[((k * 3 + c) * 7 + r) * 7 + s]);
+    }
+    ws[t] = v;
+  }
+}
+__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw,
+                                         int K) {
+  const int total = K * 3 * 49;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int s = t % 7, r = (t / 7) % 7, c = (t / 49) % 3, k = t / 147;
+    const int tr = (r + 1) >> 1, dy = (r + 1) & 1, ts = (s + 1) >> 1, dx = (s + 1) & 1;
+    dw[t] = dws[(k * 16 + tr * 4 + ts) * kStemC + (dy * 2 + dx) * 3 + c];
+  }
+}
+
+int launch_stem_pack_input(const float* x, float* xs, int N, int H, int W, cudaStream_t stream) {
+  if ((H | W) & 1) return set_error("stem_pack_input: H and W must be even (got %dx%d)", H, W);
+  const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2);
+  size_t blocks = (total + 127) / 128;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  stem_pack_input_kernel<<<(unsigned)blocks, 128, 0, stream>>>(x, reinterpret_cast<float4*>(xs), N,
+                                                              H, W);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("stem_pack_input: %s", cudaGetErrorString(e));
+  return 0;
+}
+int launch_stem_pack_weight(const float* w, float* ws, int K, cudaStream_t stream) {
+  stem_pack_weight_kernel<<<64, 256, 0, stream>>>(w, ws, K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("stem_pack_weight: %s", cudaGetErrorString(e));
+  return 0;
+}
+int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream) {
+  stem_unpack_wgrad_kernel<<<37, 256, 0, stream>>>(dws, dw, K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("stem_unpack_wgrad: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------- BN + ReLU + maxpool 3x3/s2/p1
+// a[n,p,q,c] = max_{3x3 window} relu(scale*y + shift); idx = r*3+s of the first maximum
+// (same tie rule as ATen's max_pool2d, torchvision resnet.py:271).  idx may be null (eval).
+__global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, float4* __restrict__ a,
+                                       uchar4* __restrict__ idx, int N, int H, int W, int P, int Q,
+                                       int C4) {
+  const size_t total = static_cast<size_t>(N) * P * Q * C4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += stride) {
+    const int c4 = static_cast<int>(t % C4);
+    size_t u = t / C4;
+    const int q = static_cast<int>(u % Q); u /= Q;
+    const int p = static_cast<int>(u % P);
+    const int n = static_cast<int>(u / P);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
+    float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    unsigned char bi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * p - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * q - 1 + s;
+        if (w < 0 || w >= W) continue;
+        const float4 v = y[((static_cast<size_t>(n) * H + h) * W + w) * C4 + c4];
+        const float z[4] = {fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), fmaxf(fmaf(v.y, sc.y, sh.y), 0.f),
+                            fmaxf(fmaf(v.z, sc.z, sh.z), 0.f), fmaxf(fmaf(v.w, sc.w, sh.w), 0.f)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (z[k] > best[k]) { best[k] = z[k]; bi[k] = static_cast<unsigned char>(r * 3 + s); }
+      }
+    }
+    a[t] = make_float4(tf32_rn(best[0]), tf32_rn(best[1]), tf32_rn(best[2]), tf32_rn(best[3]));
+    if (idx != nullptr) idx[t] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+
+// Gradient of maxpool + ReLU w.r.t. the BN output: gz[n,h,w,c] = [scale*y+shift > 0] *
+// sum over the (<= 4) windows whose recorded argmax is (h,w) of ga.
+__global__ void maxpool_relu_bwd_kernel(const float4* __restrict__ ga, const uchar4* __restrict__ idx,
+                                        const float4* __restrict__ y, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, float4* __restrict__ gz,
+                                        int N, int H, int W, int P, int Q, int C4) {
+  const size_t total = static_cast<size_t>(N) * H * W * C4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += stride) {
+    const int c4 = static_cast<int>(t % C4);
+    size_t u = t / C4;
+    const int w = static_cast<int>(u % W); u /= W;
+    const int h = static_cast<int>(u % H);
+    const int n = static_cast<int>(u / H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;  // windows with 2p-1 <= h <= 2p+1
+    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      if (p >= P) continue;
+      const int r = h - (2 * p - 1);
+      for (int q = q_lo; q <= q_hi; ++q) {
+        if (q >= Q) continue;
+        const int s = w - (2 * q - 1);
+        const unsigned char code = static_cast<unsigned char>(r * 3 + s);
+        const size_t o = ((static_cast<size_t>(n) * P + p) * Q + q) * C4 + c4;
+        const uchar4 id = idx[o];
+        const float4 g = ga[o];
+        if (id.x == code) acc[0] += g.x;
+        if (id.y == code) acc[1] += g.y;
+        if (id.z == code) acc[2] += g.z;
+        if (id.w == code) acc[3] += g.w;
+      }
+    }
+    const float4 v = y[t];
+    const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
+    float4 o;
+    o.x = fmaf(v.x, sc.x, sh.x) > 0.f ? acc[0] : 0.f;
+    o.y = fmaf(v.y, sc.y, sh.y) > 0.f ? acc[1] : 0.f;
+    o.z = fmaf(v.z, sc.z, sh.z) > 0.f ? acc[2] : 0.f;
+    o.w = fmaf(v.w, sc.w, sh.w) > 0.f ? acc[3] : 0.f;
+    gz[t] = o;
+  }
+}
+
+static unsigned grid_for(size_t total, int threads) {
+  size_t blocks = (total + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
+                           unsigned char* idx, int N, int H, int W, int C, cudaStream_t stream) {
+  if (C % 4 != 0) return set_error("bn_relu_maxpool: C %% 4 != 0");
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const size_t total = static_cast<size_t>(N) * P * Q * (C / 4);
+  bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a),
+      reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C / 4);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("bn_relu_maxpool: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
+                            const float* scale, const float* shift, float* gz, int N, int H, int W,
+                            int C, cudaStream_t stream) {
+  if (C % 4 != 0) return set_error("maxpool_relu_bwd: C %% 4 != 0");
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const size_t total = static_cast<size_t>(N) * H * W * (C / 4);
+  maxpool_relu_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(ga), reinterpret_cast<const uchar4*>(idx),
+      reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(gz), N, H, W, P, Q,
+      C / 4);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("maxpool_relu_bwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------ global avg-pool
+// a: [N][HW][C] -> e: [N][C]  (AdaptiveAvgPool2d(1) + flatten, torchvision resnet.py:278-279)
+__global__ void avgpool_fwd_kernel(const float* __restrict__ a, float* __restrict__ e, int HW, int C) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < HW; ++i) acc += a[(static_cast<size_t>(n) * HW + i) * C + c];
+    e[static_cast<size_t>(n) * C + c] = acc / static_cast<float>(HW);
+  }
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ ge, float* __restrict__ g, int HW, int C) {
+  const int n = blockIdx.x;
+  const float inv = 1.f / static_cast<float>(HW);
+  for (int t = threadIdx.x; t < HW * C; t += blockDim.x)
+    g[static_cast<size_t>(n) * HW * C + t] = ge[static_cast<size_t>(n) * C + (t % C)] * inv;
+}
+int launch_avgpool_fwd(const float* a, float* e, int N, int HW, int C, cudaStream_t stream) {
+  avgpool_fwd_kernel<<<N, 256, 0, stream>>>(a, e, HW, C);
+  cudaError_t er = cudaGetLastError();
+  if (er != cudaSuccess) return set_error("avgpool_fwd: %s", cudaGetErrorString(er));
+  return 0;
+}
+int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream) {
+  avgpool_bwd_kernel<<<N, 256, 0, stream>>>(ge, g, HW, C);
+  cudaError_t er = cudaGetLastError();
+  if (er != cudaSuccess) return set_error("avgpool_bwd: %s", cudaGetErrorString(er));
+  return 0;
+}
+
+}  // namespace b2n

@@ -1,0 +1,383 @@
+"""ResNet18 trunk (fc removed) executed by the libb2n CUDA kernels.
+
+Drop-in for the ``torchvision.models.resnet18(pretrained=False)`` + ``model.fc = Sequential()``
+object that models/net.py:32-34 builds: same parameter / buffer names, order, shapes and
+initialisation, same train / eval BatchNorm semantics, autograd-visible.
+``nn.Conv2d`` / ``nn.BatchNorm2d`` objects are used only as parameter containers -- their
+``forward`` is never called; all arithmetic goes through ``_lib.call``.
+
+Layout: activations NHWC fp32 in HBM.  Per conv+BN unit the raw conv output ``y`` (FP32
+accumulators), and the normalised / activated tensor ``a`` (TF32-rounded, because it is the
+next conv's tensor-core operand) are kept for the backward pass.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import call
+
+_LAYER_CFG = [(64, 1), (128, 2), (256, 2), (512, 2)]  # (planes, stride of first block)
+STEM_C = 32  # channels of the space-to-depth stem input (12 real)
+
+
+class BasicBlock(nn.Module):
+    """Parameter container with torchvision's attribute names (conv1, bn1, conv2, bn2,
+    downsample.0/.1).  Registration order follows torchvision's BasicBlock.__init__ so that
+    ``named_parameters()`` enumerates identically (index-based freezing relies on it)."""
+
+    def __init__(self, inplanes: int, planes: int, stride: int, downsample: Optional[nn.Module]):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class _PackCache:
+    """Packed (K-major, TF32-rounded) copies of conv weights, refreshed when a parameter's
+    version counter, storage or the global weight epoch changes.  Never copied or saved."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def __deepcopy__(self, memo):
+        return _PackCache()
+
+    def get(self, key: str, param: torch.Tensor, maker):
+        tag = (param.data_ptr(), param._version, _lib.WEIGHT_EPOCH, param.device)
+        hit = self.entries.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        packed = maker(param.detach())
+        self.entries[key] = (tag, packed)
+        return packed
+
+
+def _pack_fwd(w):
+    K, C, R, S = w.shape
+    out = torch.empty(K, R * S * C, device=w.device, dtype=torch.float32)
+    call("b2n_pack_weight_fwd", w, out, K, C, R, S)
+    return out
+
+
+def _pack_dgrad(w):
+    K, C, R, S = w.shape
+    out = torch.empty(C, R * S * K, device=w.device, dtype=torch.float32)
+    call("b2n_pack_weight_dgrad", w, out, K, C, R, S)
+    return out
+
+
+def _pack_stem(w):
+    out = torch.empty(w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float32)
+    call("b2n_stem_pack_weight", w, out, w.shape[0])
+    return out
+
+
+class ResNet18Trunk(nn.Module):
+    """(N,3,H,W) fp32 NCHW in [0,255] -> (N,512) features.  H and W must be even."""
+
+    def __init__(self):
+        super().__init__()
+        # Construction order and RNG consumption mirror torchvision.models.resnet.ResNet.__init__
+        # (resnet.py:197-213) so that the same torch seed yields the same initial weights.
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inplanes = 64
+        for li, (planes, stride) in enumerate(_LAYER_CFG, start=1):
+            blocks = []
+            for bi in range(2):
+                s = stride if bi == 0 else 1
+                down = None
+                if s != 1 or inplanes != planes:
+                    down = nn.Sequential(nn.Conv2d(inplanes, planes, 1, s, bias=False),
+                                         nn.BatchNorm2d(planes))
+                blocks.append(BasicBlock(inplanes, planes, s, down))
+                inplanes = planes
+            setattr(self, "layer%d" % li, nn.Sequential(*blocks))
+        nn.Linear(512, 1000)  # torchvision builds (and the reference then discards) this fc
+        self.fc = nn.Sequential()
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        self._packs = _PackCache()
+
+    # ------------------------------------------------------------------ plumbing
+    def blocks(self) -> List[BasicBlock]:
+        return [b for li in (1, 2, 3, 4) for b in getattr(self, "layer%d" % li)]
+
+    def bn_layers(self) -> List[nn.BatchNorm2d]:
+        out = [self.bn1]
+        for b in self.blocks():
+            out += [b.bn1, b.bn2]
+            if b.downsample is not None:
+                out.append(b.downsample[1])
+        return out
+
+    def forward(self, x: torch.Tensor, n_updates: int = 1) -> torch.Tensor:
+        """``n_updates`` > 1 applies that many identical BN running-stat updates in closed form
+        (TripletNet_Finetune runs the same input through the trunk three times)."""
+        _lib.require_device(x)
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError("expected (N,3,H,W) input, got %s" % (tuple(x.shape),))
+        params = [p for p in self.parameters()]
+        return _TrunkFn.apply(x, self, n_updates, *params)
+
+
+# ====================================================================== execution
+
+
+class _BNState:
+    __slots__ = ("scale", "shift", "mean", "invstd")
+
+
+def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs, slot):
+    """Per-channel affine for one BN layer; in training mode also the running-stat update."""
+    C = bn.num_features
+    st = _BNState()
+    st.scale, st.shift, st.mean, st.invstd = (bufs[i][slot:slot + C] for i in range(4))
+    if training:
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        call("b2n_bn_finalize", stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+             st.scale, st.shift, st.mean, st.invstd, C, float(count), momentum, bn.eps, n_updates)
+        bn.num_batches_tracked += n_updates
+    else:
+        call("b2n_bn_fold_eval", bn.weight, bn.bias, bn.running_mean, bn.running_var, st.scale,
+             st.shift, C, bn.eps)
+    return st
+
+
+def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
+          resid=None, mask=None, relu=0, rnd=0, stats=None, out=None):
+    P = (H + pad_lo + pad_hi - R) // stride + 1
+    Q = (W + pad_lo + pad_hi - R) // stride + 1
+    if out is None:
+        out = torch.empty(N, P, Q, Cout, device=x.device, dtype=torch.float32)
+    call("b2n_conv_fwd", x, wp, out, N, H, W, Cin, Cout, R, R, stride, pad_lo, pad_hi, pad_lo,
+         pad_hi, scale, shift, resid, mask, relu, rnd, stats)
+    return out
+
+
+class _TrunkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, trunk: ResNet18Trunk, n_updates: int, *params):
+        training = trunk.training
+        # (grad mode is always off inside Function.forward; needs_input_grad already folds in
+        # torch.no_grad() and requires_grad of every parameter)
+        any_grad = any(ctx.needs_input_grad[3:])
+        if any_grad and not training:
+            raise NotImplementedError(
+                "eval-mode BatchNorm with trainable trunk parameters is not on the reference's "
+                "path (teacher / validation run under no_grad); call .train() or no_grad()")
+        save = any_grad
+        dev = x.device
+        x = x.contiguous().float()
+        N, _, H, W = x.shape
+        if (H | W) & 1:
+            raise RuntimeError("H and W must be even (got %dx%d)" % (H, W))
+        packs = trunk._packs
+        bns = trunk.bn_layers()
+        total_c = sum(b.num_features for b in bns)
+        stats_all = torch.zeros(2 * total_c, device=dev, dtype=torch.float64) if training else None
+        bufs = torch.empty(4, total_c, device=dev, dtype=torch.float32)
+        slot = [0]
+
+        def next_bn(bn, count):
+            C = bn.num_features
+            s = slot[0]
+            slot[0] += C
+            stats = stats_all[2 * s:2 * s + 2 * C] if training else None
+            return s, stats
+
+        saved = {"N": N, "H": H, "W": W, "blocks": []}
+
+        # ---- stem: s2d pack -> 4x4 tensor-core conv -> BN+ReLU+maxpool
+        H2, W2 = H // 2, W // 2
+        xs = torch.empty(N, H2, W2, STEM_C, device=dev, dtype=torch.float32)
+        call("b2n_stem_pack_input", x, xs, N, H, W)
+        ws = packs.get("stem", trunk.conv1.weight, _pack_stem)
+        s0, stats0 = next_bn(trunk.bn1, N * H2 * W2)
+        PH, PW = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
+        a = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.float32)
+        if training:
+            y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0)
+            bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0)
+            idx = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.uint8) if save else None
+            call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a, idx, N, H2, W2, 64)
+            if save:
+                saved.update(xs=xs, y0=y0, bn0=bn0, idx=idx)
+        else:
+            bn0 = _bn_affine(trunk.bn1, False, None, 0, 0, bufs, s0)
+            z0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, scale=bn0.scale, shift=bn0.shift,
+                       relu=1)
+            ones = torch.ones(64, device=dev)
+            zeros = torch.zeros(64, device=dev)
+            call("b2n_bn_relu_maxpool", z0, ones, zeros, a, None, N, H2, W2, 64)
+        h, w = PH, PW
+
+        # ---- eight basic blocks
+        for bi, blk in enumerate(trunk.blocks()):
+            cin, cout, s = blk.conv1.in_channels, blk.conv1.out_channels, blk.stride
+            ph, pw = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+            w1 = packs.get("b%d.w1" % bi, blk.conv1.weight, _pack_fwd)
+            w2 = packs.get("b%d.w2" % bi, blk.conv2.weight, _pack_fwd)
+            rows = N * ph * pw
+            rec = {"a_in": a, "h": h, "w": w, "ph": ph, "pw": pw}
+            s1, st1 = next_bn(blk.bn1, rows)
+            s2, st2 = next_bn(blk.bn2, rows)
+            if blk.downsample is not None:
+                wd = packs.get("b%d.wd" % bi, blk.downsample[0].weight, _pack_fwd)
+                sd, std = next_bn(blk.downsample[1], rows)
+            if training:
+                y1 = _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, stats=st1)
+                b1 = _bn_affine(blk.bn1, True, st1, rows, n_updates, bufs, s1)
+                a1 = torch.empty_like(y1)
+                call("b2n_bn_apply", y1, b1.scale, b1.shift, None, None, None, a1, rows, cout, 1, 1)
+                y2 = _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, stats=st2)
+                b2 = _bn_affine(blk.bn2, True, st2, rows, n_updates, bufs, s2)
+                a_out = torch.empty_like(y2)
+                if blk.downsample is not None:
+                    yd = _conv(a, wd, N, h, w, cin, cout, 1, s, 0, 0, stats=std)
+                    bd = _bn_affine(blk.downsample[1], True, std, rows, n_updates, bufs, sd)
+                    call("b2n_bn_apply", y2, b2.scale, b2.shift, yd, bd.scale, bd.shift, a_out, rows,
+                         cout, 1, 1)
+                    rec.update(yd=yd, bd=bd)
+                else:
+                    call("b2n_bn_apply", y2, b2.scale, b2.shift, a, None, None, a_out, rows, cout,
+                         1, 1)
+                rec.update(y1=y1, a1=a1, y2=y2, a_out=a_out, b1=b1, b2=b2)
+            else:
+                # eval: BN folded into the conv epilogue, no intermediate tensors
+                b1 = _bn_affine(blk.bn1, False, None, 0, 0, bufs, s1)
+                b2 = _bn_affine(blk.bn2, False, None, 0, 0, bufs, s2)
+                a1 = _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, scale=b1.scale, shift=b1.shift,
+                           relu=1, rnd=1)
+                if blk.downsample is not None:
+                    bd = _bn_affine(blk.downsample[1], False, None, 0, 0, bufs, sd)
+                    idn = _conv(a, wd, N, h, w, cin, cout, 1, s, 0, 0, scale=bd.scale,
+                                shift=bd.shift)
+                else:
+                    idn = a
+                a_out = _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, scale=b2.scale,
+                              shift=b2.shift, resid=idn, relu=1, rnd=1)
+            if save:
+                saved["blocks"].append(rec)
+            a, h, w = a_out, ph, pw
+
+        e = torch.empty(N, 512, device=dev, dtype=torch.float32)
+        call("b2n_avgpool_fwd", a, e, N, h * w, 512)
+        ctx.trunk = trunk
+        ctx.saved = saved if save else None
+        ctx.bufs = bufs
+        return e
+
+    @staticmethod
+    def backward(ctx, ge):
+        trunk, sv = ctx.trunk, ctx.saved
+        if sv is None:
+            raise RuntimeError("trunk backward called without saved activations")
+        ctx.saved = None  # free activations as early as possible
+        params = list(trunk.parameters())
+        needs = ctx.needs_input_grad[3:]
+        grads = {id(p): None for p in params}
+        need = {id(p): n for p, n in zip(params, needs)}
+        dev = ge.device
+        N = sv["N"]
+        packs = trunk._packs
+        blocks = trunk.blocks()
+
+        def unit_needs(mods):
+            return any(need[id(p)] for m in mods for p in m.parameters())
+
+        unit_need = [unit_needs([trunk.conv1, trunk.bn1])] + [unit_needs([b]) for b in blocks]
+        if not any(unit_need):
+            return (None, None, None) + tuple(None for _ in params)
+        min_unit = min(i for i, n in enumerate(unit_need) if n)
+
+        def bn_backward(g, mask, y, st, bn, rows, C):
+            sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+            call("b2n_bn_bwd_reduce", g, mask, y, st.mean, st.invstd, sums, rows, C)
+            dy = torch.empty_like(y)
+            dgamma = torch.empty(C, device=dev)
+            dbeta = torch.empty(C, device=dev)
+            call("b2n_bn_bwd_apply", g, mask, y, st.mean, st.invstd, bn.weight, sums, dy, dgamma,
+                 dbeta, rows, C, 1)
+            if need[id(bn.weight)]:
+                grads[id(bn.weight)] = dgamma
+            if need[id(bn.bias)]:
+                grads[id(bn.bias)] = dbeta
+            return dy
+
+        def wgrad(conv, x_in, dy, H, W, stride, pad):
+            if not need[id(conv.weight)]:
+                return
+            K, C, R, S = conv.weight.shape
+            dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
+            call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad)
+            dw = torch.empty_like(conv.weight)
+            call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
+            grads[id(conv.weight)] = dw
+
+        last = sv["blocks"][-1]
+        hw = last["ph"] * last["pw"]
+        g = torch.empty(N, last["ph"], last["pw"], 512, device=dev, dtype=torch.float32)
+        call("b2n_avgpool_bwd", ge.contiguous().float(), g, N, hw, 512)
+
+        for bi in range(len(blocks) - 1, -1, -1):
+            unit = bi + 1
+            if unit < min_unit:
+                break
+            blk, rec = blocks[bi], sv["blocks"][bi]
+            cin, cout, s = blk.conv1.in_channels, blk.conv1.out_channels, blk.stride
+            h, w, ph, pw = rec["h"], rec["w"], rec["ph"], rec["pw"]
+            rows = N * ph * pw
+            need_in = unit > min_unit
+            # main branch: bn2 <- conv2 <- relu/bn1 <- conv1
+            dy2 = bn_backward(g, rec["a_out"], rec["y2"], rec["b2"], blk.bn2, rows, cout)
+            wgrad(blk.conv2, rec["a1"], dy2, ph, pw, 1, 1)
+            wd2 = packs.get("b%d.w2d" % bi, blk.conv2.weight, _pack_dgrad)
+            da1 = _conv(dy2, wd2, N, ph, pw, cout, cout, 3, 1, 1, 1)
+            dy1 = bn_backward(da1, rec["a1"], rec["y1"], rec["b1"], blk.bn1, rows, cout)
+            wgrad(blk.conv1, rec["a_in"], dy1, h, w, s, 1)
+            g_in = None
+            if blk.downsample is not None:
+                dconv, dbn = blk.downsample[0], blk.downsample[1]
+                dyd = bn_backward(g, rec["a_out"], rec["yd"], rec["bd"], dbn, rows, cout)
+                wgrad(dconv, rec["a_in"], dyd, h, w, s, 0)
+                if need_in:
+                    up = torch.empty(N, h, w, cout, device=dev, dtype=torch.float32)
+                    call("b2n_upsample_zero", dyd, up, N, ph, pw, h, w, cout)
+                    wdd = packs.get("b%d.wdd" % bi, dconv.weight, _pack_dgrad)
+                    g_in = _conv(up, wdd, N, h, w, cout, cin, 1, 1, 0, 0)
+                    call("b2n_upsample_zero", dy1, up, N, ph, pw, h, w, cout)
+                    wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
+                    _conv(up, wd1, N, h, w, cout, cin, 3, 1, 1, 1, resid=g_in, out=g_in)
+            elif need_in:
+                wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
+                # identity shortcut: add the ReLU-gated upstream gradient in the epilogue
+                g_in = _conv(dy1, wd1, N, ph, pw, cout, cin, 3, 1, 1, 1, resid=g, mask=rec["a_out"])
+            g = g_in
+
+        if min_unit == 0:
+            H2, W2 = sv["H"] // 2, sv["W"] // 2
+            bn0 = sv["bn0"]
+            gz = torch.empty_like(sv["y0"])
+            call("b2n_maxpool_relu_bwd", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, gz, N, H2, W2,
+                 64)
+            dy0 = bn_backward(gz, None, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
+            if need[id(trunk.conv1.weight)]:
+                dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
+                call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1)
+                dw = torch.empty_like(trunk.conv1.weight)
+                call("b2n_stem_unpack_wgrad", dws, dw, 64)
+                grads[id(trunk.conv1.weight)] = dw
+
+        return (None, None, None) + tuple(grads[id(p)] for p in params)
