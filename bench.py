@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Headline benchmark: 224x224 histo patches/sec of the SSL_CR teacher-student consistency step.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1, one rank per GPU)
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "cfg3"; per rank, weak scaling -- 8 ranks
+are configs[3]): eval_BreastPathQ_SSL_CR.py:76-100 with --batch_size 64 --mu 8 --lambda_u 1
+--modules_student 0: labeled inputs_x (192,3,224,224), weak / strong unlabeled (512,3,224,224)
+each; frozen teacher (eval, no_grad) + FinetuneResNet(1) on the weak view, student (train) on
+cat(labeled, strong), MSE/MSE consistency loss, full backward, Adam(lr 1e-4, wd 1e-4).
+One step = 704 unique patches per rank.  Synthetic uint8-valued patches, seeded random-init
+weights (the reference's constructors under torch.manual_seed(42)).
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: same step through the
+public modules with per-step pinned-host -> device input copies and a loss read-back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_FWD, FLOP_BWD = 3.627e9, 7.018e9   # per patch per trunk pass at 224^2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-size", type=int, default=64, help="labeled items per rank (x3 views)")
+    ap.add_argument("--mu", type=int, default=8)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_step_rate(steps, warmup, b=2, mu=7, size=224):
+    """The reference's consistency step on the host cores: the oracle port of models/net.py
+    driven by the restated loop body (eval_BreastPathQ_SSL_CR.py:76-100).  Bounded sample:
+    b labeled items x 3 views + b*mu weak + b*mu strong patches."""
+    from oracle import ref_net as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    student, cls_s = O.TripletNet_Finetune("resnet18"), O.FinetuneResNet(1)
+    teacher, cls_t = O.teacher_handoff(student), O.teacher_handoff(cls_s)
+    O.freeze_by_index(teacher, 64)
+    for p in cls_t.parameters():
+        p.requires_grad = False
+    teacher.eval(); cls_t.eval(); student.train(); cls_s.train()
+    opt = O.make_cr_optimizer(list(student.parameters()) + list(cls_s.parameters()))
+    ix = O.synthetic_patches(3 * b, size, seed=0)
+    iw, is_ = O.synthetic_patches(b * mu, size, seed=1), O.synthetic_patches(b * mu, size, seed=2)
+    tx = torch.rand(3 * b, generator=torch.Generator().manual_seed(3))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.consistency_step(teacher, student, cls_t, cls_s, opt, ix, tx, iw, is_, 1.0, "mse")
+        float(out["loss"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    patches = 3 * b + b * mu
+    return {"value": patches * len(times) / total, "ms_per_step": 1e3 * total / len(times),
+            "cores": cores, "patches_per_step": patches,
+            "sample": "b=%d labeled items x3 views + %d weak + %d strong %dx%d patches per step, "
+                      "%d timed steps after %d warm-up" % (b, b * mu, b * mu, size, size, len(times), warmup)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_step_rate(args.steps, args.warmup, size=args.size)
+    line = {
+        "impl": "reference", "metric": "224x224 histo patches/sec (consistency step)",
+        "value": r["value"], "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SSL_CR consistency step (eval_BreastPathQ_SSL_CR.py), MSE/MSE, "
+                               "modules_student=0, CPU sample of cfg3", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"],
+                         "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------- CUDA arm
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import ssl_cr_histo_b200.net as net
+    from ssl_cr_histo_b200 import _lib, ddp, losses
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if _lib.load().b2n_device_ok() != 1:
+        raise SystemExit("bench needs a compute-capability 10.x GPU (no fallback path exists)")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    b, mu, S = args.batch_size, args.mu, args.size
+    nx, nu = 3 * b, b * mu
+    torch.manual_seed(42)
+    student, cls_s = net.TripletNet_Finetune("resnet18"), net.FinetuneResNet(1)
+    import copy
+    teacher, cls_t = copy.deepcopy(student), copy.deepcopy(cls_s)
+    for p in list(teacher.parameters()) + list(cls_t.parameters()):   # --modules_teacher 64 (:414-427)
+        p.requires_grad = False
+    student, cls_s, teacher, cls_t = (m.to(dev) for m in (student, cls_s, teacher, cls_t))
+    teacher.eval(); cls_t.eval(); student.train(); cls_s.train()
+    params = list(student.parameters()) + list(cls_s.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4)       # :481
+    reducer = ddp.GradAllReducer(params) if world > 1 else None
+
+    # synthetic inputs: host copies in pinned memory (e2e) and resident device copies (value)
+    seed = 1000 * rank
+    def patches_u8(n, sd):   # uint8-valued floats, un-normalised (dataset.py:65-67)
+        g = torch.Generator().manual_seed(sd)
+        return torch.randint(0, 256, (n, 3, S, S), dtype=torch.uint8, generator=g).float()
+
+    host = [patches_u8(n, seed + i).pin_memory() for i, n in enumerate((nx, nu, nu))]
+    host_t = torch.rand(nx, generator=torch.Generator().manual_seed(seed + 7)).pin_memory()
+    resident = [h.to(dev) for h in host] + [host_t.to(dev)]
+    h2d_bytes = sum(h.numel() * 4 for h in host) + host_t.numel() * 4
+
+    def step(ix, iw, is_, tx):
+        with torch.no_grad():
+            logits_u_w = cls_t(teacher(iw))
+        logits = cls_s(student(torch.cat((ix, is_))))
+        loss, parts = losses.consistency_mse(logits[:nx], tx, logits_u_w, logits[nx:], 1.0)
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if reducer is not None:
+            reducer.all_reduce()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        dev_in = [h.to(dev, non_blocking=True) for h in host] + [host_t.to(dev, non_blocking=True)]
+        return float(step(*dev_in))       # .item(): the loop's loss read-back (:103)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), _lib.launch_count() - n0
+
+    for _ in range(max(args.warmup, 3)):
+        step(*resident)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(lambda: step(*resident), args.steps)
+    sampler.stop_flag = True
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # per-kernel roofline of the dominant kernels, CUDA events on the launching stream
+    roof = None
+    if not args.no_profile:
+        _lib.PROFILE = {"b2n_conv_fwd": [], "b2n_conv_wgrad": []}
+        t_ms, _ = timed(lambda: step(*resident), 2)
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        torch.cuda.synchronize()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16 = peaks.get("bf16_tflops_sustained")
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 issues at half the bf16 rate)"
+        if bf16 is None:
+            bf16, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) / 2"
+        peak = bf16 / 2.0
+        kern = {}
+        for name, ev in prof.items():
+            t = sum(a.elapsed_time(c) for a, c, _ in ev)
+            w = sum(x for _, _, x in ev)
+            kern[name] = {"launches_per_step": len(ev) / 2, "ms_per_step": t / 2,
+                          "tflops": w / (t * 1e-3) / 1e12 if t > 0 else None}
+        dom = kern["b2n_conv_fwd"]
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
+                "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
+                "frac": dom["tflops"] / peak if dom["tflops"] else None, "traffic": None,
+                "peak_source": peak_src, "share_of_step": dom["ms_per_step"] / (t_ms / 2),
+                "launches_per_step": dom["launches_per_step"],
+                "wgrad": {"tflops": kern["b2n_conv_wgrad"]["tflops"],
+                          "frac": (kern["b2n_conv_wgrad"]["tflops"] or 0) / peak,
+                          "share_of_step": kern["b2n_conv_wgrad"]["ms_per_step"] / (t_ms / 2)}}
+
+    patches = (nx + nu) * world
+    alg_flops = world * (nu * FLOP_FWD + (nx + nu) * (FLOP_FWD + FLOP_BWD))
+    line = {
+        "metric": "224x224 histo patches/sec (consistency step)", "unit": "patches/s",
+        "value": patches * args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage and accumulate)",
+        "data": "synthetic",
+        "config": {"workload": "SSL_CR consistency step (eval_BreastPathQ_SSL_CR.py:76-100), MSE/MSE, "
+                               "modules_student=0, BASELINE configs[2] per rank",
+                   "labeled": nx, "unlabeled_weak": nu, "unlabeled_strong": nu, "image": S,
+                   "unique_patches_per_step_per_rank": nx + nu, "optimizer": "Adam(1e-4, wd 1e-4)",
+                   "parallelism": "dp%d, one NCCL all-reduce of %.1f MB grads/step" % (
+                       world, reducer.nbytes / 1e6) if reducer else "single GPU",
+                   "l2": "inputs (%.0f MB/step) larger than the 126 MB L2" % (h2d_bytes / 1e6)},
+        "algorithmic_tflops": alg_flops * args.steps / (ms * 1e-3) / 1e12,
+        "e2e": {"value": patches * args.steps / (ms_e2e * 1e-3), "unit": "patches/s",
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+    }
+    if roof is not None:
+        line["roofline"] = roof
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_step_rate(3, 1, size=S)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"],
+                                "kind": "port", "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -28,6 +28,8 @@ extern "C" {
 
 int b2n_version(void);
 const char* b2n_last_error(void);
+/* kernels enqueued through this library since it was loaded (monotonic, process-wide). */
+unsigned long long b2n_launch_count(void);
 /* 1 when the current device is compute capability 10.x, 0 otherwise, <0 when no device. */
 int b2n_device_ok(void);
 
@@ -36,8 +38,13 @@ int b2n_device_ok(void);
 /* Implicit-GEMM convolution, tcgen05 TF32 / FP32 accumulate.
  *   y[n,p,q,k] = sum_{r,s,c} x[n, p*stride - pad_h_lo + r, q*stride - pad_w_lo + s, c]
  *                             * w_packed[k][(r*S+s)*Cin + c]
+ * Error-compensated mode ("3xTF32", used by every forward conv): when x_lo and w_packed_lo are
+ * given, both operands are (hi, lo) pairs of TF32 tensors (hi + lo = the FP32 value) and the
+ * kernel accumulates hi*hi + lo*hi + hi*lo -- FP32-grade results from TF32 tensor cores.
+ * With x_lo = w_packed_lo = NULL a single TF32 pass is issued (data-gradient launches).
  * epilogue: v = acc; v = v*scale[k] (if scale); v += shift[k] (if shift);
- *           v += resid[..] (if resid; only where mask[..] > 0 if mask); relu; TF32 round.
+ *           v += resid[..] (+ resid_lo[..]) (if resid; only where mask[..] > 0 if mask); relu;
+ *           store v, or TF32-rounded v (round_tf32), or the (hi, lo) pair into y / y_lo (y_lo).
  * stats (optional, [2][Cout] doubles, caller-zeroed): += per-channel sum / sum of squares of
  * the raw accumulator -- the BatchNorm batch statistics.
  * Requires Cin % 32 == 0, Cout % 64 == 0.  Used for the forward pass AND (with a
@@ -45,10 +52,12 @@ int b2n_device_ok(void);
  * Replaces: tv:92,96,100 (conv3x3 / downsample conv in BasicBlock.forward), tv:268 (stem, via
  * the space-to-depth view), and the conv dgrad reached from loss.backward()
  * (pretrain_BreastPathQ.py:60, eval_BreastPathQ_SSL_CR.py:99). */
-int b2n_conv_fwd(const float* x, const float* w_packed, float* y, int N, int H, int W, int Cin,
+int b2n_conv_fwd(const float* x, const float* x_lo, const float* w_packed,
+                 const float* w_packed_lo, float* y, float* y_lo, int N, int H, int W, int Cin,
                  int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
                  int pad_w_hi, const float* scale, const float* shift, const float* resid,
-                 const float* mask, int relu, int round_tf32, double* stats, void* stream);
+                 const float* resid_lo, const float* mask, int relu, int round_tf32, double* stats,
+                 void* stream);
 
 /* Weight gradient, split-K over pixels, accumulated atomically:
  *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
@@ -58,17 +67,21 @@ int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int
                    int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
                    int pad_w_hi, void* stream);
 
-/* (K,C,R,S) parameter -> forward pack [K][(r*S+s)*C + c], data-gradient pack
- * [C][((R-1-r)*S+(S-1-s))*K + k] (both TF32-rounded); packed weight gradient -> (K,C,R,S). */
-int b2n_pack_weight_fwd(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
+/* (K,C,R,S) parameter -> forward pack [K][(r*S+s)*C + c] as a (hi, lo) TF32 pair (w_packed_lo
+ * may be NULL), data-gradient pack [C][((R-1-r)*S+(S-1-s))*K + k] (TF32-rounded); packed weight
+ * gradient -> (K,C,R,S). */
+int b2n_pack_weight_fwd(const float* w, float* w_packed, float* w_packed_lo, int K, int C, int R,
+                        int S, void* stream);
 int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, void* stream);
 
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
-/* x NCHW fp32 (N,3,H,W), H and W even -> xs NHWC (N,H/2,W/2,32) (12 real channels). */
-int b2n_stem_pack_input(const float* x_nchw, float* xs, int N, int H, int W, void* stream);
-/* w (K,3,7,7) -> ws [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
-int b2n_stem_pack_weight(const float* w, float* ws, int K, void* stream);
+/* x NCHW fp32 (N,3,H,W), H and W even -> xs (+ xs_lo, may be NULL) NHWC (N,H/2,W/2,32)
+ * (12 real channels), as a (hi, lo) TF32 pair. */
+int b2n_stem_pack_input(const float* x_nchw, float* xs, float* xs_lo, int N, int H, int W,
+                        void* stream);
+/* w (K,3,7,7) -> ws (+ ws_lo) [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
+int b2n_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, void* stream);
 int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream);
 
 /* ---- BatchNorm / ReLU / residual (tv:93-103,269-270; nn.BatchNorm2d train + eval) -------- */
@@ -82,11 +95,13 @@ int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, 
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                      const float* running_var, float* scale, float* shift, int C, float eps,
                      void* stream);
-/* out = [relu](scale*y + shift + residual); residual = res, or res_scale*res + res_shift when
- * res_scale is given (downsample-branch BN); optional TF32 rounding.  [rows][C] row-major. */
+/* out = [relu](scale*y + shift + residual); residual = res (+ res_lo when the shortcut is a
+ * (hi, lo) pair), or res_scale*res + res_shift when res_scale is given (downsample-branch BN).
+ * Output: fp32, TF32-rounded (round_tf32), or a (hi, lo) TF32 pair when out_lo is given.
+ * [rows][C] row-major. */
 int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                 const float* res_scale, const float* res_shift, float* out, long long rows, int C,
-                 int relu, int round_tf32, void* stream);
+                 const float* res_lo, const float* res_scale, const float* res_shift, float* out,
+                 float* out_lo, long long rows, int C, int relu, int round_tf32, void* stream);
 /* BatchNorm backward, two passes.  g' = g * [mask > 0] (mask = post-ReLU block output or null).
  *   reduce: sums[0][c] += sum g', sums[1][c] += sum g' * xhat        (sums caller-zeroed)
  *   apply : dy = gamma*invstd*(g' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0 */
@@ -102,12 +117,13 @@ int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, in
 
 /* ---- pooling (tv:271 MaxPool2d(3,2,1) fused with bn1+relu; tv:278-279 avgpool+flatten) --- */
 int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                        unsigned char* argmax_idx /* may be null */, int N, int H, int W, int C,
-                        void* stream);
+                        float* a_lo /* may be null */, unsigned char* argmax_idx /* may be null */,
+                        int N, int H, int W, int C, void* stream);
 int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* argmax_idx, const float* y,
                          const float* scale, const float* shift, float* gz, int N, int H, int W,
                          int C, void* stream);
-int b2n_avgpool_fwd(const float* a, float* e, int N, int HW, int C, void* stream);
+int b2n_avgpool_fwd(const float* a, const float* a_lo /* may be null */, float* e, int N, int HW,
+                    int C, void* stream);
 int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream);
 
 /* ---- fully-connected heads, exact FP32 (models/net.py:12-15,36-37,60-62,110) ------------- */

@@ -19,23 +19,23 @@ P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 
 # name -> argument ctypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
-    "b2n_conv_fwd": [P, P, P] + [I] * 12 + [P, P, P, P, I, I, P],
+    "b2n_conv_fwd": [P] * 6 + [I] * 12 + [P, P, P, P, P, I, I, P],
     "b2n_conv_wgrad": [P, P, P] + [I] * 12,
-    "b2n_pack_weight_fwd": [P, P, I, I, I, I],
+    "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
     "b2n_unpack_wgrad": [P, P, I, I, I, I],
-    "b2n_stem_pack_input": [P, P, I, I, I],
-    "b2n_stem_pack_weight": [P, P, I],
+    "b2n_stem_pack_input": [P, P, P, I, I, I],
+    "b2n_stem_pack_weight": [P, P, P, I],
     "b2n_stem_unpack_wgrad": [P, P, I],
     "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
-    "b2n_bn_apply": [P] * 7 + [LL, I, I, I],
+    "b2n_bn_apply": [P] * 9 + [LL, I, I, I],
     "b2n_bn_bwd_reduce": [P] * 6 + [LL, I],
     "b2n_bn_bwd_apply": [P] * 10 + [LL, I, I],
     "b2n_upsample_zero": [P, P] + [I] * 6,
-    "b2n_bn_relu_maxpool": [P] * 5 + [I] * 4,
+    "b2n_bn_relu_maxpool": [P] * 6 + [I] * 4,
     "b2n_maxpool_relu_bwd": [P] * 6 + [I] * 4,
-    "b2n_avgpool_fwd": [P, P, I, I, I],
+    "b2n_avgpool_fwd": [P, P, P, I, I, I],
     "b2n_avgpool_bwd": [P, P, I, I, I],
     "b2n_linear_fwd": [P, LL, P, LL, P, P, LL, I, I, I, I, I],
     "b2n_linear_bwd_data": [P, LL, P, LL, P, LL, P, I, I, I, I],
@@ -43,7 +43,7 @@ _SIGNATURES = {
     "b2n_fused_loss": [I, P, P, P, P, P, I, I, I, F, P, P, P, P, P],
     "b2n_lerp_multi": [P, P, P, I, F, I],
 }
-EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok"] + list(_SIGNATURES)
+EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok", "b2n_launch_count"] + list(_SIGNATURES)
 
 _lib = None
 # bumped whenever a kernel writes parameters behind autograd's back (lerp), so that cached
@@ -65,6 +65,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.b2n_version.restype = c_int
     lib.b2n_last_error.restype = c_char_p
     lib.b2n_device_ok.restype = c_int
+    lib.b2n_launch_count.restype = ctypes.c_ulonglong
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = list(sig) + [c_void_p]
@@ -81,13 +82,31 @@ def _conv(a):
     return a
 
 
-def call(name: str, *args) -> None:
+# Optional per-kernel timing (bench.py): when PROFILE is a dict, calls whose entry-point name
+# is a key get bracketed by CUDA events on the launching stream; `work` (algorithmic FLOPs or
+# bytes of that launch, supplied by the caller) is accumulated next to them.
+PROFILE = None
+
+
+def call(name: str, *args, work: float = 0.0) -> None:
     """Invoke an entry point on the current CUDA stream; raise on a non-zero return code."""
     lib = load()
     stream = torch.cuda.current_stream().cuda_stream
+    prof = PROFILE.get(name) if PROFILE is not None else None
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*[_conv(a) for a in args], stream)
     if rc != 0:
         raise RuntimeError("%s failed: %s" % (name, lib.b2n_last_error().decode()))
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, work))
+
+
+def launch_count() -> int:
+    return int(load().b2n_launch_count())
 
 
 def require_device(t: torch.Tensor, what: str = "input") -> None:

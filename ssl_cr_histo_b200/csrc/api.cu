@@ -7,9 +7,17 @@ using namespace b2n;
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// number of kernels enqueued through this library since load (bench.py's gpu_launches)
+static unsigned long long g_launches = 0;
+static inline int counted(int rc, int kernels = 1) {
+  if (rc == 0) __atomic_fetch_add(&g_launches, (unsigned long long)kernels, __ATOMIC_RELAXED);
+  return rc;
+}
+
 extern "C" {
 
 int b2n_version(void) { return B2N_ABI_VERSION; }
+unsigned long long b2n_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* b2n_last_error(void) { return last_error(); }
 
 int b2n_device_ok(void) {
@@ -23,18 +31,21 @@ int b2n_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
-int b2n_conv_fwd(const float* x, const float* w_packed, float* y, int N, int H, int W, int Cin,
+int b2n_conv_fwd(const float* x, const float* x_lo, const float* w_packed,
+                 const float* w_packed_lo, float* y, float* y_lo, int N, int H, int W, int Cin,
                  int Cout, int R, int Sf, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
                  int pad_w_hi, const float* scale, const float* shift, const float* resid,
-                 const float* mask, int relu, int round_tf32, double* stats, void* stream) {
+                 const float* resid_lo, const float* mask, int relu, int round_tf32, double* stats,
+                 void* stream) {
   if (!x || !w_packed || !y) return set_error("b2n_conv_fwd: null tensor");
   ConvArgs a;
-  a.x = x; a.w = w_packed; a.out = y;
+  a.x = x; a.x_lo = x_lo; a.w = w_packed; a.w_lo = w_packed_lo; a.out = y; a.out_lo = y_lo;
+  a.resid_lo = resid_lo;
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.R = R; a.S = Sf; a.stride = stride;
   a.pad_h_lo = pad_h_lo; a.pad_h_hi = pad_h_hi; a.pad_w_lo = pad_w_lo; a.pad_w_hi = pad_w_hi;
   a.scale = scale; a.shift = shift; a.resid = resid; a.mask = mask;
   a.relu = relu; a.round_tf32 = round_tf32; a.stats = stats;
-  return launch_conv(a, S(stream));
+  return counted(launch_conv(a, S(stream)));
 }
 
 int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
@@ -45,95 +56,99 @@ int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int
   a.x = x; a.dy = dy; a.dw = dw_packed;
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.R = R; a.S = Sf; a.stride = stride;
   a.pad_h_lo = pad_h_lo; a.pad_h_hi = pad_h_hi; a.pad_w_lo = pad_w_lo; a.pad_w_hi = pad_w_hi;
-  return launch_wgrad(a, S(stream));
+  return counted(launch_wgrad(a, S(stream)));
 }
 
-int b2n_pack_weight_fwd(const float* w, float* wp, int K, int C, int R, int Sf, void* stream) {
-  return launch_pack_fwd(w, wp, K, C, R, Sf, S(stream));
+int b2n_pack_weight_fwd(const float* w, float* wp, float* wp_lo, int K, int C, int R, int Sf,
+                        void* stream) {
+  return counted(launch_pack_fwd(w, wp, wp_lo, K, C, R, Sf, S(stream)));
 }
 int b2n_pack_weight_dgrad(const float* w, float* wp, int K, int C, int R, int Sf, void* stream) {
-  return launch_pack_dgrad(w, wp, K, C, R, Sf, S(stream));
+  return counted(launch_pack_dgrad(w, wp, K, C, R, Sf, S(stream)));
 }
 int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, void* stream) {
-  return launch_unpack_wgrad(dwp, dw, K, C, R, Sf, S(stream));
+  return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, S(stream)));
 }
 
-int b2n_stem_pack_input(const float* x, float* xs, int N, int H, int W, void* stream) {
-  return launch_stem_pack_input(x, xs, N, H, W, S(stream));
+int b2n_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H, int W,
+                        void* stream) {
+  return counted(launch_stem_pack_input(x, xs, xs_lo, N, H, W, S(stream)));
 }
-int b2n_stem_pack_weight(const float* w, float* ws, int K, void* stream) {
-  return launch_stem_pack_weight(w, ws, K, S(stream));
+int b2n_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, void* stream) {
+  return counted(launch_stem_pack_weight(w, ws, ws_lo, K, S(stream)));
 }
 int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream) {
-  return launch_stem_unpack_wgrad(dws, dw, K, S(stream));
+  return counted(launch_stem_unpack_wgrad(dws, dw, K, S(stream)));
 }
 
 int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float* scale, float* shift, float* mean, float* invstd,
                     int C, double count, float momentum, float eps, int n_updates, void* stream) {
-  return launch_bn_finalize(stats, gamma, beta, running_mean, running_var, scale, shift, mean,
-                            invstd, C, count, momentum, eps, n_updates, S(stream));
+  return counted(launch_bn_finalize(stats, gamma, beta, running_mean, running_var, scale, shift, mean,
+                            invstd, C, count, momentum, eps, n_updates, S(stream)));
 }
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                      float* scale, float* shift, int C, float eps, void* stream) {
-  return launch_bn_fold_eval(gamma, beta, rm, rv, scale, shift, C, eps, S(stream));
+  return counted(launch_bn_fold_eval(gamma, beta, rm, rv, scale, shift, C, eps, S(stream)));
 }
 int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                 const float* res_scale, const float* res_shift, float* out, long long rows, int C,
-                 int relu, int round_tf32, void* stream) {
-  return launch_bn_apply(y, scale, shift, res, res_scale, res_shift, out, rows, C, relu,
-                         round_tf32, S(stream));
+                 const float* res_lo, const float* res_scale, const float* res_shift, float* out,
+                 float* out_lo, long long rows, int C, int relu, int round_tf32, void* stream) {
+  return counted(launch_bn_apply(y, scale, shift, res, res_lo, res_scale, res_shift, out, out_lo,
+                                 rows, C, relu, round_tf32, S(stream)));
 }
 int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
                       const float* invstd, double* sums, long long rows, int C, void* stream) {
-  return launch_bn_bwd_reduce(g, mask, y, mean, invstd, sums, rows, C, S(stream));
+  return counted(launch_bn_bwd_reduce(g, mask, y, mean, invstd, sums, rows, C, S(stream)));
 }
 int b2n_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
                      const float* invstd, const float* gamma, const double* sums, float* dy,
                      float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
                      void* stream) {
-  return launch_bn_bwd_apply(g, mask, y, mean, invstd, gamma, sums, dy, dgamma, dbeta, rows, C,
-                             round_tf32, S(stream));
+  return counted(launch_bn_bwd_apply(g, mask, y, mean, invstd, gamma, sums, dy, dgamma, dbeta, rows, C,
+                             round_tf32, S(stream)));
 }
 int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                       void* stream) {
-  return launch_upsample_zero(dy, up, N, P, Q, H, W, C, S(stream));
+  return counted(launch_upsample_zero(dy, up, N, P, Q, H, W, C, S(stream)));
 }
 
 int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                        unsigned char* idx, int N, int H, int W, int C, void* stream) {
-  return launch_bn_relu_maxpool(y, scale, shift, a, idx, N, H, W, C, S(stream));
+                        float* a_lo, unsigned char* idx, int N, int H, int W, int C, void* stream) {
+  return counted(launch_bn_relu_maxpool(y, scale, shift, a, a_lo, idx, N, H, W, C, S(stream)));
 }
 int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
                          const float* scale, const float* shift, float* gz, int N, int H, int W,
                          int C, void* stream) {
-  return launch_maxpool_relu_bwd(ga, idx, y, scale, shift, gz, N, H, W, C, S(stream));
+  return counted(launch_maxpool_relu_bwd(ga, idx, y, scale, shift, gz, N, H, W, C, S(stream)));
 }
-int b2n_avgpool_fwd(const float* a, float* e, int N, int HW, int C, void* stream) {
-  return launch_avgpool_fwd(a, e, N, HW, C, S(stream));
+int b2n_avgpool_fwd(const float* a, const float* a_lo, float* e, int N, int HW, int C,
+                    void* stream) {
+  return counted(launch_avgpool_fwd(a, a_lo, e, N, HW, C, S(stream)));
 }
 int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream) {
-  return launch_avgpool_bwd(ge, g, N, HW, C, S(stream));
+  return counted(launch_avgpool_bwd(ge, g, N, HW, C, S(stream)));
 }
 
 int b2n_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,
                    float* y, long long ldy, int rows, int in_f, int out_f, int relu, int accumulate,
                    void* stream) {
-  return launch_linear_fwd(x, ldx, w, ldw, b, y, ldy, rows, in_f, out_f, relu, accumulate,
-                           S(stream));
+  return counted(launch_linear_fwd(x, ldx, w, ldw, b, y, ldy, rows, in_f, out_f, relu, accumulate,
+                           S(stream)));
 }
 int b2n_linear_bwd_data(const float* dy, long long lddy, const float* w, long long ldw, float* dx,
                         long long lddx, const float* relu_mask, int rows, int in_f, int out_f,
                         int accumulate, void* stream) {
-  return launch_linear_bwd_data(dy, lddy, w, ldw, dx, lddx, relu_mask, rows, in_f, out_f,
-                                accumulate, S(stream));
+  return counted(launch_linear_bwd_data(dy, lddy, w, ldw, dx, lddx, relu_mask, rows, in_f, out_f,
+                                accumulate, S(stream)));
 }
 int b2n_linear_bwd_weight(const float* dy, long long lddy, const float* x, long long ldx, float* dw,
                           long long lddw, float* db, int rows, int in_f, int out_f, int accumulate,
                           void* stream) {
-  int rc = launch_linear_bwd_weight(dy, lddy, x, ldx, dw, lddw, rows, in_f, out_f, accumulate,
-                                    S(stream));
-  if (rc == 0 && db != nullptr) rc = launch_colsum(dy, lddy, db, rows, out_f, accumulate, S(stream));
+  int rc = counted(launch_linear_bwd_weight(dy, lddy, x, ldx, dw, lddw, rows, in_f, out_f,
+                                            accumulate, S(stream)));
+  if (rc == 0 && db != nullptr)
+    rc = counted(launch_colsum(dy, lddy, db, rows, out_f, accumulate, S(stream)));
   return rc;
 }
 
@@ -141,15 +156,16 @@ int b2n_fused_loss(int mode, const float* logits_x, const long long* targets_i,
                    const float* targets_f, const float* logits_u_w, const float* logits_u_s,
                    int rows_x, int rows_u, int C, float lambda_u, float* losses, float* dlogits_x,
                    float* dlogits_u, long long* argmax_x, long long* pseudo_labels, void* stream) {
-  return launch_fused_loss(mode, logits_x, targets_i, targets_f, logits_u_w, logits_u_s, rows_x,
+  return counted(launch_fused_loss(mode, logits_x, targets_i, targets_f, logits_u_w, logits_u_s, rows_x,
                            rows_u, C, lambda_u, losses, dlogits_x, dlogits_u, argmax_x,
-                           pseudo_labels, S(stream));
+                           pseudo_labels, S(stream)));
 }
 
 int b2n_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
                    float alpha, int write_back, void* stream) {
   if (n < 0 || (n > 0 && (!dst || !src || !numel))) return set_error("b2n_lerp_multi: bad args");
-  return launch_lerp_multi(dst, src, numel, n, alpha, write_back, S(stream));
+  return counted(launch_lerp_multi(dst, src, numel, n, alpha, write_back, S(stream)),
+                 (n + 95) / 96);
 }
 
 }  // extern "C"

@@ -53,12 +53,15 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
 // --------------------------------------------------------------------- apply
 // out = act(scale*y + shift + residual), residual = res (identity) or res_scale*res + res_shift
 // (the downsample branch's BN), optionally rounded to TF32 because `out` feeds the next conv.
-template <bool RELU, bool ROUND>
+// OUT_MODE: 0 = plain fp32, 1 = TF32-rounded, 2 = (hi, lo) TF32 pair into out / out_lo.
+// res_lo: low part when the residual is itself a (hi, lo) pair (identity shortcut).
+template <bool RELU, int OUT_MODE>
 __global__ void bn_apply_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const float4* __restrict__ res,
+                                const float4* __restrict__ res_lo,
                                 const float* __restrict__ res_scale,
                                 const float* __restrict__ res_shift, float4* __restrict__ out,
-                                size_t n4, int C) {
+                                float4* __restrict__ out_lo, size_t n4, int C) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const int c = static_cast<int>((i * 4) % C);
@@ -69,6 +72,10 @@ __global__ void bn_apply_kernel(const float4* __restrict__ y, const float* __res
                            fmaf(v.w, sc.w, sh.w));
     if (res != nullptr) {
       float4 r = res[i];
+      if (res_lo != nullptr) {
+        const float4 rl = res_lo[i];
+        r.x += rl.x; r.y += rl.y; r.z += rl.z; r.w += rl.w;
+      }
       if (res_scale != nullptr) {
         const float4 rs = *reinterpret_cast<const float4*>(res_scale + c);
         const float4 rh = *reinterpret_cast<const float4*>(res_shift + c);
@@ -80,16 +87,24 @@ __global__ void bn_apply_kernel(const float4* __restrict__ y, const float* __res
     if (RELU) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
-    if (ROUND) {
-      o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+    if (OUT_MODE == 2) {
+      const float4 h = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
+      out[i] = h;
+      out_lo[i] = make_float4(tf32_rn(o.x - h.x), tf32_rn(o.y - h.y), tf32_rn(o.z - h.z),
+                              tf32_rn(o.w - h.w));
+    } else {
+      if (OUT_MODE == 1) {
+        o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+      }
+      out[i] = o;
     }
-    out[i] = o;
   }
 }
 
 int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                    const float* res_scale, const float* res_shift, float* out, long long rows,
-                    int C, int relu, int round_tf32, cudaStream_t stream) {
+                    const float* res_lo, const float* res_scale, const float* res_shift,
+                    float* out, float* out_lo, long long rows, int C, int relu, int round_tf32,
+                    cudaStream_t stream) {
   if (C % 4 != 0) return set_error("bn_apply: C %% 4 != 0");
   const size_t n4 = static_cast<size_t>(rows) * C / 4;
   if (n4 == 0) return 0;
@@ -99,14 +114,22 @@ int launch_bn_apply(const float* y, const float* scale, const float* shift, cons
   if (blocks > cap) blocks = cap;
   auto y4 = reinterpret_cast<const float4*>(y);
   auto r4 = reinterpret_cast<const float4*>(res);
+  auto rl4 = reinterpret_cast<const float4*>(res_lo);
   auto o4 = reinterpret_cast<float4*>(out);
-#define B2N_LAUNCH(R, T)                                                                       \
-  bn_apply_kernel<R, T><<<(unsigned)blocks, threads, 0, stream>>>(y4, scale, shift, r4, res_scale, \
-                                                                 res_shift, o4, n4, C)
-  if (relu && round_tf32) B2N_LAUNCH(true, true);
-  else if (relu) B2N_LAUNCH(true, false);
-  else if (round_tf32) B2N_LAUNCH(false, true);
-  else B2N_LAUNCH(false, false);
+  auto ol4 = reinterpret_cast<float4*>(out_lo);
+  const int mode = out_lo != nullptr ? 2 : (round_tf32 ? 1 : 0);
+#define B2N_LAUNCH(R, T)                                                                     \
+  bn_apply_kernel<R, T><<<(unsigned)blocks, threads, 0, stream>>>(y4, scale, shift, r4, rl4, \
+                                                                 res_scale, res_shift, o4, ol4, n4, C)
+  if (relu) {
+    if (mode == 2) B2N_LAUNCH(true, 2);
+    else if (mode == 1) B2N_LAUNCH(true, 1);
+    else B2N_LAUNCH(true, 0);
+  } else {
+    if (mode == 2) B2N_LAUNCH(false, 2);
+    else if (mode == 1) B2N_LAUNCH(false, 1);
+    else B2N_LAUNCH(false, 0);
+  }
 #undef B2N_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_apply: %s", cudaGetErrorString(e));

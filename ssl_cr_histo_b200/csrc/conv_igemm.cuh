@@ -10,6 +10,13 @@
 //     two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 //
+// SPLIT = true is the error-compensated forward mode ("3xTF32"): both operands arrive as a
+// (hi, lo) pair of TF32 tensors with hi + lo == the FP32 value to ~2^-22, and each K step
+// issues hi*hi + lo*hi + hi*lo into the same accumulator.  A single TF32 pass is only good to
+// ~1e-3 on the logits of this network (and flips ~0.3 % of the ReLU gates, which the gradients
+// then inherit); the split restores FP32-grade forward results.  Data-gradient launches
+// (SPLIT = false) multiply plain TF32 operands.
+//
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
 // torchvision BasicBlock.forward (site-packages/torchvision/models/resnet.py:92-100).
@@ -29,10 +36,12 @@ struct ConvParams {
   int num_m_tiles, num_n_tiles;
   int kslices;  // Cin / KELEMS
   float* out;
-  const float* scale;  // per-channel multiplier (eval-mode BN fold) or null
-  const float* shift;  // per-channel bias or null
-  const float* resid;  // tensor added in the epilogue or null
-  const float* mask;   // when set, resid is only added where mask > 0 (ReLU gate)
+  float* out_lo;          // when set the result is stored as a (hi, lo) TF32 pair
+  const float* scale;     // per-channel multiplier (eval-mode BN fold) or null
+  const float* shift;     // per-channel bias or null
+  const float* resid;     // tensor added in the epilogue or null
+  const float* resid_lo;  // low part of a split residual or null
+  const float* mask;      // when set, resid is only added where mask > 0 (ReLU gate)
   int relu;
   int round_tf32;
   double* stats;  // [2][Cout] per-channel sum / sum of squares of the raw accumulator, or null
@@ -41,27 +50,33 @@ struct ConvParams {
 constexpr int kConvThreads = 192;
 constexpr int kBlockM = 128;
 
-template <int BLOCK_N, int KBYTES, int STAGES>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT>
 struct ConvSmem {
   static constexpr int A_BYTES = kBlockM * KBYTES;
   static constexpr int B_BYTES = BLOCK_N * KBYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STATS_FLOATS = 2 * 512;
   // ring | stats accumulators | barriers | tmem ptr   (+1024 slack for manual alignment)
   static constexpr int TOTAL = RING_BYTES + STATS_FLOATS * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int KBYTES, int STAGES>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                  const __grid_constant__ CUtensorMap map_b, const ConvParams p) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES>;
+                  const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT>;
   constexpr int KELEMS = KBYTES / 4;
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // tf32: K = 8 elements = 32 bytes per MMA
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
   constexpr uint32_t SBO = 8 * KBYTES;  // 8 rows of one swizzle atom
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // stage layout: A_hi | B_hi | A_lo | B_lo
+  constexpr int OFF_B = L::A_BYTES;
+  constexpr int OFF_A_LO = L::A_BYTES + L::B_BYTES;
+  constexpr int OFF_B_LO = 2 * L::A_BYTES + L::B_BYTES;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
 
@@ -83,6 +98,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (SPLIT) {
+      tma_prefetch_desc(&map_a_lo);
+      tma_prefetch_desc(&map_b_lo);
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -125,12 +144,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           const int r = tap / p.S;
           const int s = tap - r * p.S;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
+          uint8_t* st = smem + stage * L::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_im2col_4d(sa, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
+          const int kcoord = tap * p.Cin + cs * KELEMS;
+          tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
                              static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin + cs * KELEMS, n_tile * BLOCK_N);
+          tma_load_2d(st + OFF_B, &map_b, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+          if (SPLIT) {
+            tma_load_im2col_4d(st + OFF_A_LO, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w,
+                               base_h, img, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+            tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -151,12 +175,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
           for (int j = 0; j < MMAS_PER_STAGE; ++j) {
             const uint64_t da = make_smem_desc(a_addr + j * 32, 16, SBO, SWZ);
-            const uint64_t db = make_smem_desc(b_addr + j * 32, 16, SBO, SWZ);
+            const uint64_t db = make_smem_desc(a_addr + OFF_B + j * 32, 16, SBO, SWZ);
             umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
+            if (SPLIT) {
+              const uint64_t dal = make_smem_desc(a_addr + OFF_A_LO + j * 32, 16, SBO, SWZ);
+              const uint64_t dbl = make_smem_desc(a_addr + OFF_B_LO + j * 32, 16, SBO, SWZ);
+              umma_tf32(d_tmem, dal, db, idesc, 1u);
+              umma_tf32(d_tmem, da, dbl, idesc, 1u);
+            }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -222,6 +251,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             }
             if (p.resid != nullptr) {
               float4 rr = *reinterpret_cast<const float4*>(p.resid + off + 4 * i);
+              if (p.resid_lo != nullptr) {
+                const float4 rl = *reinterpret_cast<const float4*>(p.resid_lo + off + 4 * i);
+                rr.x += rl.x; rr.y += rl.y; rr.z += rl.z; rr.w += rl.w;
+              }
               if (p.mask != nullptr) {
                 const float4 mk = *reinterpret_cast<const float4*>(p.mask + off + 4 * i);
                 rr.x = mk.x > 0.f ? rr.x : 0.f; rr.y = mk.y > 0.f ? rr.y : 0.f;
@@ -233,10 +266,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f);
               o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
             }
-            if (p.round_tf32) {
-              o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+            if (p.out_lo != nullptr) {
+              const float4 h = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
+              dst[i] = h;
+              reinterpret_cast<float4*>(p.out_lo + off)[i] = make_float4(
+                  tf32_rn(o.x - h.x), tf32_rn(o.y - h.y), tf32_rn(o.z - h.z), tf32_rn(o.w - h.w));
+            } else {
+              if (p.round_tf32) {
+                o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+              }
+              dst[i] = o;
             }
-            dst[i] = o;
           }
         }
       }

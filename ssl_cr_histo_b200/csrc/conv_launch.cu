@@ -18,11 +18,14 @@ int device_sm_count() {
   return sms;
 }
 
-template <int BLOCK_N, int KBYTES, int STAGES>
-static int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p,
-                          int grid, cudaStream_t stream) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES>;
+struct ConvMaps {
+  CUtensorMap a, b, a_lo, b_lo;
+};
+
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT>
+static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -31,7 +34,7 @@ static int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const Co
                                            cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, kConvThreads, L::TOTAL, stream>>>(ma, mb, p);
+  kern<<<grid, kConvThreads, L::TOTAL, stream>>>(m.a, m.b, m.a_lo, m.b_lo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv launch: %s", cudaGetErrorString(e));
   return 0;
@@ -39,10 +42,11 @@ static int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const Co
 
 int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (a.Cout % 64 != 0) return set_error("conv: Cout=%d must be a multiple of 64", a.Cout);
-  int kbytes;
-  if (a.Cin % 32 == 0) kbytes = 128;
-  else if (a.Cin == 16) kbytes = 64;
-  else return set_error("conv: Cin=%d must be 16 or a multiple of 32", a.Cin);
+  if (a.Cin % 32 != 0) return set_error("conv: Cin=%d must be a multiple of 32", a.Cin);
+  const bool split = a.x_lo != nullptr;
+  if (split != (a.w_lo != nullptr))
+    return set_error("conv: split mode needs both x_lo and w_lo");
+  const int kbytes = 128;
   const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
   const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
   if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("conv: empty output");
@@ -60,29 +64,41 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
   p.num_n_tiles = a.Cout / block_n;
   p.kslices = a.Cin / (kbytes / 4);
-  p.out = a.out; p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.mask = a.mask;
-  p.relu = a.relu; p.round_tf32 = a.round_tf32; p.stats = a.stats;
+  p.out = a.out; p.out_lo = a.out_lo;
+  p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.resid_lo = a.resid_lo;
+  p.mask = a.mask; p.relu = a.relu; p.round_tf32 = a.round_tf32; p.stats = a.stats;
 
-  CUtensorMap ma, mb;
-  if (make_im2col_map(&ma, a.x, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi, a.pad_w_lo,
-                      a.pad_w_hi, a.stride, kbytes / 4, kBlockM, kbytes))
-    return set_error("conv: %s", tmap_last_error());
+  ConvMaps m;
   const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;
-  if (make_tiled_map_2d(&mb, a.w, a.Cout, ktot, ktot, block_n, kbytes / 4, kbytes))
+  if (make_im2col_map(&m.a, a.x, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
+                      a.pad_w_lo, a.pad_w_hi, a.stride, kbytes / 4, kBlockM, kbytes))
     return set_error("conv: %s", tmap_last_error());
+  if (make_tiled_map_2d(&m.b, a.w, a.Cout, ktot, ktot, block_n, kbytes / 4, kbytes))
+    return set_error("conv: %s", tmap_last_error());
+  if (split) {
+    if (make_im2col_map(&m.a_lo, a.x_lo, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
+                        a.pad_w_lo, a.pad_w_hi, a.stride, kbytes / 4, kBlockM, kbytes))
+      return set_error("conv: %s", tmap_last_error());
+    if (make_tiled_map_2d(&m.b_lo, a.w_lo, a.Cout, ktot, ktot, block_n, kbytes / 4, kbytes))
+      return set_error("conv: %s", tmap_last_error());
+  } else {
+    m.a_lo = m.a;
+    m.b_lo = m.b;
+  }
 
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
 
-  if (kbytes == 128) {
-    if (block_n == 64) return launch_variant<64, 128, 6>(ma, mb, p, grid, stream);
-    if (block_n == 128) return launch_variant<128, 128, 5>(ma, mb, p, grid, stream);
-    if (block_n == 256) return launch_variant<256, 128, 4>(ma, mb, p, grid, stream);
+  if (split) {
+    if (block_n == 64) return launch_variant<64, 128, 4, true>(m, p, grid, stream);
+    if (block_n == 128) return launch_variant<128, 128, 3, true>(m, p, grid, stream);
   } else {
-    if (block_n == 64) return launch_variant<64, 64, 8>(ma, mb, p, grid, stream);
+    if (block_n == 64) return launch_variant<64, 128, 6, false>(m, p, grid, stream);
+    if (block_n == 128) return launch_variant<128, 128, 5, false>(m, p, grid, stream);
+    if (block_n == 256) return launch_variant<256, 128, 4, false>(m, p, grid, stream);
   }
-  return set_error("conv: no kernel variant for BLOCK_N=%d KBYTES=%d", block_n, kbytes);
+  return set_error("conv: no kernel variant for BLOCK_N=%d split=%d", block_n, (int)split);
 }
 
 }  // namespace b2n

@@ -15,13 +15,17 @@ int device_sm_count();
 // x is NHWC fp32 [N,H,W,Cin]; w is packed K-major [Cout][R*S*Cin]; out is NHWC [N,P,Q,Cout].
 struct ConvArgs {
   const float* x = nullptr;
+  const float* x_lo = nullptr;  // with w_lo: error-compensated (hi, lo) TF32 operands
   const float* w = nullptr;
+  const float* w_lo = nullptr;
   float* out = nullptr;
+  float* out_lo = nullptr;      // store the result as a (hi, lo) TF32 pair
   int N = 0, H = 0, W = 0, Cin = 0, Cout = 0, R = 0, S = 0, stride = 1;
   int pad_h_lo = 0, pad_h_hi = 0, pad_w_lo = 0, pad_w_hi = 0;
   const float* scale = nullptr;
   const float* shift = nullptr;
   const float* resid = nullptr;
+  const float* resid_lo = nullptr;
   const float* mask = nullptr;
   int relu = 0;
   int round_tf32 = 0;
@@ -51,8 +55,9 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
 int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                         float* scale, float* shift, int C, float eps, cudaStream_t stream);
 int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                    const float* res_scale, const float* res_shift, float* out, long long rows,
-                    int C, int relu, int round_tf32, cudaStream_t stream);
+                    const float* res_lo, const float* res_scale, const float* res_shift,
+                    float* out, float* out_lo, long long rows, int C, int relu, int round_tf32,
+                    cudaStream_t stream);
 int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
                          const float* invstd, double* sums, long long rows, int C,
                          cudaStream_t stream);
@@ -62,17 +67,21 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
                         cudaStream_t stream);
 int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                          cudaStream_t stream);
-int launch_stem_pack_input(const float* x, float* xs, int N, int H, int W, cudaStream_t stream);
-int launch_stem_pack_weight(const float* w, float* ws, int K, cudaStream_t stream);
+int launch_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H, int W,
+                           cudaStream_t stream);
+int launch_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, cudaStream_t stream);
 int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream);
 int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                           unsigned char* idx, int N, int H, int W, int C, cudaStream_t stream);
+                           float* a_lo, unsigned char* idx, int N, int H, int W, int C,
+                           cudaStream_t stream);
 int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
                             const float* scale, const float* shift, float* gz, int N, int H, int W,
                             int C, cudaStream_t stream);
-int launch_avgpool_fwd(const float* a, float* e, int N, int HW, int C, cudaStream_t stream);
+int launch_avgpool_fwd(const float* a, const float* a_lo, float* e, int N, int HW, int C,
+                       cudaStream_t stream);
 int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream);
-int launch_pack_fwd(const float* src, float* dst, int K, int C, int R, int S, cudaStream_t stream);
+int launch_pack_fwd(const float* src, float* dst, float* dst_lo, int K, int C, int R, int S,
+                    cudaStream_t stream);
 int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
                       cudaStream_t stream);
 int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S,

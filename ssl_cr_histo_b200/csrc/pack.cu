@@ -7,8 +7,8 @@
 namespace b2n {
 
 // forward operand:  wf[k][(r*S+s)*C + c] = w[k][c][r][s]
-__global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__ wf, int K, int C,
-                                int R, int S) {
+__global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__ wf,
+                                float* __restrict__ wf_lo, int K, int C, int R, int S) {
   const size_t total = static_cast<size_t>(K) * C * R * S;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -17,7 +17,10 @@ __global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__
     const int s = static_cast<int>(u % S); u /= S;
     const int r = static_cast<int>(u % R);
     const int k = static_cast<int>(u / R);
-    wf[t] = tf32_rn(w[((static_cast<size_t>(k) * C + c) * R + r) * S + s]);
+    const float v = w[((static_cast<size_t>(k) * C + c) * R + r) * S + s];
+    const float h = tf32_rn(v);
+    wf[t] = h;
+    if (wf_lo != nullptr) wf_lo[t] = tf32_rn(v - h);  // hi + lo == v to ~2^-22
   }
 }
 // data-gradient operand (flipped taps, in/out channels swapped):
@@ -64,7 +67,14 @@ static unsigned pack_grid(size_t total) {
     if (e != cudaSuccess) return set_error(#NAME ": %s", cudaGetErrorString(e));            \
     return 0;                                                                               \
   }
-B2N_PACK_LAUNCH(launch_pack_fwd, pack_fwd_kernel)
+int launch_pack_fwd(const float* src, float* dst, float* dst_lo, int K, int C, int R, int S,
+                    cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(K) * C * R * S;
+  pack_fwd_kernel<<<pack_grid(total), 256, 0, stream>>>(src, dst, dst_lo, K, C, R, S);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("launch_pack_fwd: %s", cudaGetErrorString(e));
+  return 0;
+}
 B2N_PACK_LAUNCH(launch_pack_dgrad, pack_dgrad_kernel)
 B2N_PACK_LAUNCH(launch_unpack_wgrad, unpack_wgrad_kernel)
 #undef B2N_PACK_LAUNCH

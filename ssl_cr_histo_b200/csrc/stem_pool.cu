@@ -17,8 +17,8 @@ namespace b2n {
 constexpr int kStemC = 32;
 
 // x: NCHW fp32 (N,3,H,W), H and W even.  xs: NHWC (N,H/2,W/2,32), TF32-rounded.
-__global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __restrict__ xs, int N,
-                                       int H, int W) {
+__global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __restrict__ xs,
+                                       float4* __restrict__ xs_lo, int N, int H, int W) {
   const int H2 = H >> 1, W2 = W >> 1;
   const size_t total = static_cast<size_t>(N) * H2 * W2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -27,15 +27,16 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __re
     const int j = static_cast<int>(t % W2);
     const int i = static_cast<int>((t / W2) % H2);
     const int n = static_cast<int>(t / (static_cast<size_t>(W2) * H2));
-    float v[12];
+    float v[12], l[12];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* plane = x + (static_cast<size_t>(n) * 3 + c) * H * W;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
         const float2 p = *reinterpret_cast<const float2*>(plane + static_cast<size_t>(2 * i + dy) * W + 2 * j);
-        v[(dy * 2 + 0) * 3 + c] = tf32_rn(p.x);
-        v[(dy * 2 + 1) * 3 + c] = tf32_rn(p.y);
+        const int e0 = (dy * 2 + 0) * 3 + c, e1 = (dy * 2 + 1) * 3 + c;
+        v[e0] = tf32_rn(p.x); l[e0] = tf32_rn(p.x - v[e0]);
+        v[e1] = tf32_rn(p.y); l[e1] = tf32_rn(p.y - v[e1]);
       }
     }
     float4* dst = xs + t * (kStemC / 4);
@@ -44,11 +45,20 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __re
     dst[2] = make_float4(v[8], v[9], v[10], v[11]);
 #pragma unroll
     for (int k = 3; k < kStemC / 4; ++k) dst[k] = make_float4(0, 0, 0, 0);
+    if (xs_lo != nullptr) {
+      float4* dl = xs_lo + t * (kStemC / 4);
+      dl[0] = make_float4(l[0], l[1], l[2], l[3]);
+      dl[1] = make_float4(l[4], l[5], l[6], l[7]);
+      dl[2] = make_float4(l[8], l[9], l[10], l[11]);
+#pragma unroll
+      for (int k = 3; k < kStemC / 4; ++k) dl[k] = make_float4(0, 0, 0, 0);
+    }
   }
 }
 
 // w: (K,3,7,7) -> ws: [K][16 taps][32], TF32-rounded.  unpack = the transpose map for grads.
-__global__ void stem_pack_weight_kernel(const float* __restrict__ w, float* __restrict__ ws, int K) {
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, float* __restrict__ ws,
+                                        float* __restrict__ ws_lo, int K) {
   const int total = K * 16 * kStemC;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int ch = t % kStemC;
@@ -58,9 +68,11 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, float* __re
     if (ch < 12) {
       const int c = ch % 3, dd = ch / 3, dy = dd >> 1, dx = dd & 1;
       const int r = 2 * (tap >> 2) + dy - 1, s = 2 * (tap & 3) + dx - 1;
-      if (r >= 0 && r < 7 && s >= 0 && s < 7) v = tf32_rn(w[((k * 3 + c) * 7 + r) * 7 + s]);
+      if (r >= 0 && r < 7 && s >= 0 && s < 7) v = w[((k * 3 + c) * 7 + r) * 7 + s];
     }
-    ws[t] = v;
+    const float h = tf32_rn(v);
+    ws[t] = h;
+    if (ws_lo != nullptr) ws_lo[t] = tf32_rn(v - h);
   }
 }
 __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw,
@@ -73,21 +85,22 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* _
   }
 }
 
-int launch_stem_pack_input(const float* x, float* xs, int N, int H, int W, cudaStream_t stream) {
+int launch_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H, int W,
+                           cudaStream_t stream) {
   if ((H | W) & 1) return set_error("stem_pack_input: H and W must be even (got %dx%d)", H, W);
   const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2);
   size_t blocks = (total + 127) / 128;
   const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  stem_pack_input_kernel<<<(unsigned)blocks, 128, 0, stream>>>(x, reinterpret_cast<float4*>(xs), N,
-                                                              H, W);
+  stem_pack_input_kernel<<<(unsigned)blocks, 128, 0, stream>>>(
+      x, reinterpret_cast<float4*>(xs), reinterpret_cast<float4*>(xs_lo), N, H, W);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_pack_input: %s", cudaGetErrorString(e));
   return 0;
 }
-int launch_stem_pack_weight(const float* w, float* ws, int K, cudaStream_t stream) {
-  stem_pack_weight_kernel<<<64, 256, 0, stream>>>(w, ws, K);
+int launch_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, cudaStream_t stream) {
+  stem_pack_weight_kernel<<<64, 256, 0, stream>>>(w, ws, ws_lo, K);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_pack_weight: %s", cudaGetErrorString(e));
   return 0;
@@ -104,8 +117,8 @@ int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t st
 // (same tie rule as ATen's max_pool2d, torchvision resnet.py:271).  idx may be null (eval).
 __global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
                                        const float* __restrict__ shift, float4* __restrict__ a,
-                                       uchar4* __restrict__ idx, int N, int H, int W, int P, int Q,
-                                       int C4) {
+                                       float4* __restrict__ a_lo, uchar4* __restrict__ idx, int N,
+                                       int H, int W, int P, int Q, int C4) {
   const size_t total = static_cast<size_t>(N) * P * Q * C4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
@@ -135,7 +148,12 @@ __global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float
           if (z[k] > best[k]) { best[k] = z[k]; bi[k] = static_cast<unsigned char>(r * 3 + s); }
       }
     }
-    a[t] = make_float4(tf32_rn(best[0]), tf32_rn(best[1]), tf32_rn(best[2]), tf32_rn(best[3]));
+    const float4 hi = make_float4(tf32_rn(best[0]), tf32_rn(best[1]), tf32_rn(best[2]),
+                                  tf32_rn(best[3]));
+    a[t] = hi;
+    if (a_lo != nullptr)
+      a_lo[t] = make_float4(tf32_rn(best[0] - hi.x), tf32_rn(best[1] - hi.y),
+                            tf32_rn(best[2] - hi.z), tf32_rn(best[3] - hi.w));
     if (idx != nullptr) idx[t] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
   }
 }
@@ -195,13 +213,14 @@ static unsigned grid_for(size_t total, int threads) {
 }
 
 int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                           unsigned char* idx, int N, int H, int W, int C, cudaStream_t stream) {
+                           float* a_lo, unsigned char* idx, int N, int H, int W, int C,
+                           cudaStream_t stream) {
   if (C % 4 != 0) return set_error("bn_relu_maxpool: C %% 4 != 0");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 4);
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
       reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a),
-      reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C / 4);
+      reinterpret_cast<float4*>(a_lo), reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C / 4);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_relu_maxpool: %s", cudaGetErrorString(e));
   return 0;
@@ -224,11 +243,15 @@ int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const flo
 
 // ------------------------------------------------------------ global avg-pool
 // a: [N][HW][C] -> e: [N][C]  (AdaptiveAvgPool2d(1) + flatten, torchvision resnet.py:278-279)
-__global__ void avgpool_fwd_kernel(const float* __restrict__ a, float* __restrict__ e, int HW, int C) {
+__global__ void avgpool_fwd_kernel(const float* __restrict__ a, const float* __restrict__ a_lo,
+                                   float* __restrict__ e, int HW, int C) {
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
-    for (int i = 0; i < HW; ++i) acc += a[(static_cast<size_t>(n) * HW + i) * C + c];
+    for (int i = 0; i < HW; ++i) {
+      const size_t o = (static_cast<size_t>(n) * HW + i) * C + c;
+      acc += a_lo != nullptr ? a[o] + a_lo[o] : a[o];
+    }
     e[static_cast<size_t>(n) * C + c] = acc / static_cast<float>(HW);
   }
 }
@@ -238,8 +261,9 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ ge, float* __restri
   for (int t = threadIdx.x; t < HW * C; t += blockDim.x)
     g[static_cast<size_t>(n) * HW * C + t] = ge[static_cast<size_t>(n) * C + (t % C)] * inv;
 }
-int launch_avgpool_fwd(const float* a, float* e, int N, int HW, int C, cudaStream_t stream) {
-  avgpool_fwd_kernel<<<N, 256, 0, stream>>>(a, e, HW, C);
+int launch_avgpool_fwd(const float* a, const float* a_lo, float* e, int N, int HW, int C,
+                       cudaStream_t stream) {
+  avgpool_fwd_kernel<<<N, 256, 0, stream>>>(a, a_lo, e, HW, C);
   cudaError_t er = cudaGetLastError();
   if (er != cudaSuccess) return set_error("avgpool_fwd: %s", cudaGetErrorString(er));
   return 0;

@@ -60,10 +60,11 @@ class _PackCache:
 
 
 def _pack_fwd(w):
+    """(hi, lo) TF32 pair of the forward operand [K][(r*S+s)*C + c]."""
     K, C, R, S = w.shape
-    out = torch.empty(K, R * S * C, device=w.device, dtype=torch.float32)
-    call("b2n_pack_weight_fwd", w, out, K, C, R, S)
-    return out
+    out = torch.empty(2, K, R * S * C, device=w.device, dtype=torch.float32)
+    call("b2n_pack_weight_fwd", w, out[0], out[1], K, C, R, S)
+    return out[0], out[1]
 
 
 def _pack_dgrad(w):
@@ -74,9 +75,9 @@ def _pack_dgrad(w):
 
 
 def _pack_stem(w):
-    out = torch.empty(w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float32)
-    call("b2n_stem_pack_weight", w, out, w.shape[0])
-    return out
+    out = torch.empty(2, w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float32)
+    call("b2n_stem_pack_weight", w, out[0], out[1], w.shape[0])
+    return out[0], out[1]
 
 
 class ResNet18Trunk(nn.Module):
@@ -129,7 +130,7 @@ class ResNet18Trunk(nn.Module):
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError("expected (N,3,H,W) input, got %s" % (tuple(x.shape),))
         params = [p for p in self.parameters()]
-        return _TrunkFn.apply(x, self, n_updates, *params)
+        return _TrunkFn.apply(x, self, n_updates, torch.is_grad_enabled(), *params)
 
 
 # ====================================================================== execution
@@ -155,24 +156,47 @@ def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs
     return st
 
 
+class _Act:
+    """An activation tensor as an error-compensated (hi, lo) pair of TF32 planes:
+    hi = tf32(a), lo = tf32(a - hi).  Forward convs consume both planes (3xTF32); the backward
+    pass (TF32) and the ReLU gates only ever need ``hi``, so ``lo`` is dropped after use."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, shape, dev, with_lo=True):
+        self.hi = torch.empty(shape, device=dev, dtype=torch.float32)
+        self.lo = torch.empty(shape, device=dev, dtype=torch.float32) if with_lo else None
+
+
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
-          resid=None, mask=None, relu=0, rnd=0, stats=None, out=None):
+          resid=None, resid_lo=None, mask=None, relu=0, rnd=0, stats=None, out=None, out_lo=None,
+          alg=1.0):
+    """One conv launch.  ``x`` / ``wp`` are either plain tensors (single TF32 pass: data
+    gradients) or (hi, lo) pairs (error-compensated forward).  ``alg``: algorithmic / executed
+    FLOP ratio of this launch (the stem runs 147 real taps in a 512-wide padded reduction; a
+    zero-stuffed stride-2 data gradient executes 4x the useful MACs) -- only used for the
+    roofline accounting in bench.py."""
+    x_hi, x_lo = (x.hi, x.lo) if isinstance(x, _Act) else (x, None)
+    w_hi, w_lo = wp if isinstance(wp, tuple) else (wp, None)
+    if (x_lo is None) != (w_lo is None):
+        w_lo = None if x_lo is None else w_lo
+        x_lo = None if w_lo is None else x_lo
     P = (H + pad_lo + pad_hi - R) // stride + 1
     Q = (W + pad_lo + pad_hi - R) // stride + 1
     if out is None:
-        out = torch.empty(N, P, Q, Cout, device=x.device, dtype=torch.float32)
-    call("b2n_conv_fwd", x, wp, out, N, H, W, Cin, Cout, R, R, stride, pad_lo, pad_hi, pad_lo,
-         pad_hi, scale, shift, resid, mask, relu, rnd, stats)
+        out = torch.empty(N, P, Q, Cout, device=x_hi.device, dtype=torch.float32)
+    call("b2n_conv_fwd", x_hi, x_lo, w_hi, w_lo, out, out_lo, N, H, W, Cin, Cout, R, R, stride,
+         pad_lo, pad_hi, pad_lo, pad_hi, scale, shift, resid, resid_lo, mask, relu, rnd, stats,
+         work=2.0 * N * P * Q * Cout * R * R * Cin * alg)
     return out
 
 
 class _TrunkFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, trunk: ResNet18Trunk, n_updates: int, *params):
+    def forward(ctx, x, trunk: ResNet18Trunk, n_updates: int, grad_mode: bool, *params):
         training = trunk.training
-        # (grad mode is always off inside Function.forward; needs_input_grad already folds in
-        # torch.no_grad() and requires_grad of every parameter)
-        any_grad = any(ctx.needs_input_grad[3:])
+        # grad mode is always off inside Function.forward and needs_input_grad ignores
+        # torch.no_grad(), so the caller's grad mode is passed in explicitly
+        any_grad = grad_mode and any(ctx.needs_input_grad[4:])
         if any_grad and not training:
             raise NotImplementedError(
                 "eval-mode BatchNorm with trainable trunk parameters is not on the reference's "
@@ -190,7 +214,7 @@ class _TrunkFn(torch.autograd.Function):
         bufs = torch.empty(4, total_c, device=dev, dtype=torch.float32)
         slot = [0]
 
-        def next_bn(bn, count):
+        def next_bn(bn):
             C = bn.num_features
             s = slot[0]
             slot[0] += C
@@ -198,29 +222,30 @@ class _TrunkFn(torch.autograd.Function):
             return s, stats
 
         saved = {"N": N, "H": H, "W": W, "blocks": []}
+        stem_alg = 147.0 / (16 * STEM_C)
 
         # ---- stem: s2d pack -> 4x4 tensor-core conv -> BN+ReLU+maxpool
         H2, W2 = H // 2, W // 2
-        xs = torch.empty(N, H2, W2, STEM_C, device=dev, dtype=torch.float32)
-        call("b2n_stem_pack_input", x, xs, N, H, W)
+        xs = _Act((N, H2, W2, STEM_C), dev)
+        call("b2n_stem_pack_input", x, xs.hi, xs.lo, N, H, W)
         ws = packs.get("stem", trunk.conv1.weight, _pack_stem)
-        s0, stats0 = next_bn(trunk.bn1, N * H2 * W2)
+        s0, stats0 = next_bn(trunk.bn1)
         PH, PW = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
-        a = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.float32)
+        a = _Act((N, PH, PW, 64), dev)
         if training:
-            y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0)
+            y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg)
             bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0)
             idx = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.uint8) if save else None
-            call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a, idx, N, H2, W2, 64)
+            call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a.hi, a.lo, idx, N, H2, W2, 64)
             if save:
-                saved.update(xs=xs, y0=y0, bn0=bn0, idx=idx)
+                saved.update(xs=xs.hi, y0=y0, bn0=bn0, idx=idx)
         else:
             bn0 = _bn_affine(trunk.bn1, False, None, 0, 0, bufs, s0)
             z0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, scale=bn0.scale, shift=bn0.shift,
-                       relu=1)
+                       relu=1, alg=stem_alg)
             ones = torch.ones(64, device=dev)
             zeros = torch.zeros(64, device=dev)
-            call("b2n_bn_relu_maxpool", z0, ones, zeros, a, None, N, H2, W2, 64)
+            call("b2n_bn_relu_maxpool", z0, ones, zeros, a.hi, a.lo, None, N, H2, W2, 64)
         h, w = PH, PW
 
         # ---- eight basic blocks
@@ -230,50 +255,52 @@ class _TrunkFn(torch.autograd.Function):
             w1 = packs.get("b%d.w1" % bi, blk.conv1.weight, _pack_fwd)
             w2 = packs.get("b%d.w2" % bi, blk.conv2.weight, _pack_fwd)
             rows = N * ph * pw
-            rec = {"a_in": a, "h": h, "w": w, "ph": ph, "pw": pw}
-            s1, st1 = next_bn(blk.bn1, rows)
-            s2, st2 = next_bn(blk.bn2, rows)
+            rec = {"a_in": a.hi, "h": h, "w": w, "ph": ph, "pw": pw}
+            s1, st1 = next_bn(blk.bn1)
+            s2, st2 = next_bn(blk.bn2)
             if blk.downsample is not None:
                 wd = packs.get("b%d.wd" % bi, blk.downsample[0].weight, _pack_fwd)
-                sd, std = next_bn(blk.downsample[1], rows)
+                sd, std = next_bn(blk.downsample[1])
+            a1 = _Act((N, ph, pw, cout), dev)
+            a_out = _Act((N, ph, pw, cout), dev)
             if training:
                 y1 = _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, stats=st1)
                 b1 = _bn_affine(blk.bn1, True, st1, rows, n_updates, bufs, s1)
-                a1 = torch.empty_like(y1)
-                call("b2n_bn_apply", y1, b1.scale, b1.shift, None, None, None, a1, rows, cout, 1, 1)
+                call("b2n_bn_apply", y1, b1.scale, b1.shift, None, None, None, None, a1.hi, a1.lo,
+                     rows, cout, 1, 0)
                 y2 = _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, stats=st2)
                 b2 = _bn_affine(blk.bn2, True, st2, rows, n_updates, bufs, s2)
-                a_out = torch.empty_like(y2)
                 if blk.downsample is not None:
                     yd = _conv(a, wd, N, h, w, cin, cout, 1, s, 0, 0, stats=std)
                     bd = _bn_affine(blk.downsample[1], True, std, rows, n_updates, bufs, sd)
-                    call("b2n_bn_apply", y2, b2.scale, b2.shift, yd, bd.scale, bd.shift, a_out, rows,
-                         cout, 1, 1)
+                    call("b2n_bn_apply", y2, b2.scale, b2.shift, yd, None, bd.scale, bd.shift,
+                         a_out.hi, a_out.lo, rows, cout, 1, 0)
                     rec.update(yd=yd, bd=bd)
                 else:
-                    call("b2n_bn_apply", y2, b2.scale, b2.shift, a, None, None, a_out, rows, cout,
-                         1, 1)
-                rec.update(y1=y1, a1=a1, y2=y2, a_out=a_out, b1=b1, b2=b2)
+                    call("b2n_bn_apply", y2, b2.scale, b2.shift, a.hi, a.lo, None, None, a_out.hi,
+                         a_out.lo, rows, cout, 1, 0)
+                rec.update(y1=y1, a1=a1.hi, y2=y2, a_out=a_out.hi, b1=b1, b2=b2)
             else:
                 # eval: BN folded into the conv epilogue, no intermediate tensors
                 b1 = _bn_affine(blk.bn1, False, None, 0, 0, bufs, s1)
                 b2 = _bn_affine(blk.bn2, False, None, 0, 0, bufs, s2)
-                a1 = _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, scale=b1.scale, shift=b1.shift,
-                           relu=1, rnd=1)
+                _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, scale=b1.scale, shift=b1.shift, relu=1,
+                      out=a1.hi, out_lo=a1.lo)
                 if blk.downsample is not None:
                     bd = _bn_affine(blk.downsample[1], False, None, 0, 0, bufs, sd)
                     idn = _conv(a, wd, N, h, w, cin, cout, 1, s, 0, 0, scale=bd.scale,
                                 shift=bd.shift)
+                    idn_lo = None
                 else:
-                    idn = a
-                a_out = _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, scale=b2.scale,
-                              shift=b2.shift, resid=idn, relu=1, rnd=1)
+                    idn, idn_lo = a.hi, a.lo
+                _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, scale=b2.scale, shift=b2.shift,
+                      resid=idn, resid_lo=idn_lo, relu=1, out=a_out.hi, out_lo=a_out.lo)
             if save:
                 saved["blocks"].append(rec)
             a, h, w = a_out, ph, pw
 
         e = torch.empty(N, 512, device=dev, dtype=torch.float32)
-        call("b2n_avgpool_fwd", a, e, N, h * w, 512)
+        call("b2n_avgpool_fwd", a.hi, a.lo, e, N, h * w, 512)
         ctx.trunk = trunk
         ctx.saved = saved if save else None
         ctx.bufs = bufs
@@ -286,7 +313,7 @@ class _TrunkFn(torch.autograd.Function):
             raise RuntimeError("trunk backward called without saved activations")
         ctx.saved = None  # free activations as early as possible
         params = list(trunk.parameters())
-        needs = ctx.needs_input_grad[3:]
+        needs = ctx.needs_input_grad[4:]
         grads = {id(p): None for p in params}
         need = {id(p): n for p, n in zip(params, needs)}
         dev = ge.device
@@ -299,7 +326,7 @@ class _TrunkFn(torch.autograd.Function):
 
         unit_need = [unit_needs([trunk.conv1, trunk.bn1])] + [unit_needs([b]) for b in blocks]
         if not any(unit_need):
-            return (None, None, None) + tuple(None for _ in params)
+            return (None, None, None, None) + tuple(None for _ in params)
         min_unit = min(i for i, n in enumerate(unit_need) if n)
 
         def bn_backward(g, mask, y, st, bn, rows, C):
@@ -321,7 +348,9 @@ class _TrunkFn(torch.autograd.Function):
                 return
             K, C, R, S = conv.weight.shape
             dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
-            call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad)
+            P, Q = dy.shape[1], dy.shape[2]
+            call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
+                 work=2.0 * N * P * Q * K * R * S * C)
             dw = torch.empty_like(conv.weight)
             call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
             grads[id(conv.weight)] = dw
@@ -356,10 +385,10 @@ class _TrunkFn(torch.autograd.Function):
                     up = torch.empty(N, h, w, cout, device=dev, dtype=torch.float32)
                     call("b2n_upsample_zero", dyd, up, N, ph, pw, h, w, cout)
                     wdd = packs.get("b%d.wdd" % bi, dconv.weight, _pack_dgrad)
-                    g_in = _conv(up, wdd, N, h, w, cout, cin, 1, 1, 0, 0)
+                    g_in = _conv(up, wdd, N, h, w, cout, cin, 1, 1, 0, 0, alg=0.25)
                     call("b2n_upsample_zero", dy1, up, N, ph, pw, h, w, cout)
                     wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
-                    _conv(up, wd1, N, h, w, cout, cin, 3, 1, 1, 1, resid=g_in, out=g_in)
+                    _conv(up, wd1, N, h, w, cout, cin, 3, 1, 1, 1, resid=g_in, out=g_in, alg=0.25)
             elif need_in:
                 wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
                 # identity shortcut: add the ReLU-gated upstream gradient in the epilogue
@@ -375,9 +404,10 @@ class _TrunkFn(torch.autograd.Function):
             dy0 = bn_backward(gz, None, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
             if need[id(trunk.conv1.weight)]:
                 dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
-                call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1)
+                call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
+                     work=2.0 * N * H2 * W2 * 64 * 147)
                 dw = torch.empty_like(trunk.conv1.weight)
                 call("b2n_stem_unpack_wgrad", dws, dw, 64)
                 grads[id(trunk.conv1.weight)] = dw
 
-        return (None, None, None) + tuple(grads[id(p)] for p in params)
+        return (None, None, None, None) + tuple(grads[id(p)] for p in params)

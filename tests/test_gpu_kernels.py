@@ -1,0 +1,394 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (libb2n.so via ctypes) against plain
+torch fp32 CPU references of the same op.  Integer-valued inputs make TF32 products and FP32
+sums exact, so the tensor-core kernels are required to be BIT-EXACT there; element-wise and
+FP32-GEMM kernels are held to fp32 round-off."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ssl_cr_histo_b200 import _lib, losses, weights
+from ssl_cr_histo_b200._lib import call
+from oracle import ref_net as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ints(shape, lo, hi, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(lo, hi + 1, shape, generator=g).float() * scale
+
+
+def to_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def from_nhwc(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def pack_fwd(w, split=False):
+    K, C, R, S = w.shape
+    out = torch.empty(2, K, R * S * C, device=DEV)
+    call("b2n_pack_weight_fwd", w.to(DEV), out[0], out[1] if split else None, K, C, R, S)
+    return (out[0], out[1]) if split else out[0]
+
+
+def split_pair(t):
+    """(hi, lo) TF32 pair of an fp32 tensor, as the producing kernels store activations."""
+    hi = O.tf32_round(t)
+    return hi, O.tf32_round(t - hi)
+
+
+def pack_dgrad(w):
+    K, C, R, S = w.shape
+    out = torch.empty(C, R * S * K, device=DEV)
+    call("b2n_pack_weight_dgrad", w.to(DEV), out, K, C, R, S)
+    return out
+
+
+def conv(x_nhwc, wp, N, H, W, Cin, Cout, R, stride, plo, phi, **kw):
+    """x_nhwc / wp: plain tensors (one TF32 pass) or (hi, lo) pairs (error-compensated)."""
+    P = (H + plo + phi - R) // stride + 1
+    Q = (W + plo + phi - R) // stride + 1
+    y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+    x_hi, x_lo = x_nhwc if isinstance(x_nhwc, tuple) else (x_nhwc, None)
+    w_hi, w_lo = wp if isinstance(wp, tuple) else (wp, None)
+    call("b2n_conv_fwd", x_hi, x_lo, w_hi, w_lo, y, kw.get("y_lo"), N, H, W, Cin, Cout, R, R, stride,
+         plo, phi, plo, phi, kw.get("scale"), kw.get("shift"), kw.get("resid"), kw.get("resid_lo"),
+         kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"))
+    return y
+
+
+def test_device_is_blackwell():
+    assert _lib.load().b2n_device_ok() == 1, "tests need a compute-capability 10.x device"
+
+
+CONV_CASES = [  # N, H, W, Cin, Cout, R, stride, pad   (every ResNet18 conv shape class + ragged M)
+    (2, 56, 56, 64, 64, 3, 1, 1),
+    (2, 56, 56, 64, 128, 3, 2, 1),
+    (2, 56, 56, 64, 128, 1, 2, 0),
+    (3, 28, 28, 128, 128, 3, 1, 1),
+    (2, 28, 28, 128, 256, 3, 2, 1),
+    (3, 14, 14, 256, 256, 3, 1, 1),
+    (2, 14, 14, 256, 512, 1, 2, 0),
+    (5, 7, 7, 512, 512, 3, 1, 1),
+    (1, 7, 7, 256, 512, 3, 2, 1),       # odd input, 4x4 output
+    (1, 4, 4, 64, 64, 3, 1, 1),         # M = 16 < one tile
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_bit_exact_with_bn_statistics(case):
+    N, H, W, Cin, Cout, R, s, p = case
+    x = ints((N, Cin, H, W), -4, 4, 1)
+    w = ints((Cout, Cin, R, R), -2, 2, 2, 0.25)
+    ref = F.conv2d(x, w, None, s, p)
+    stats = torch.zeros(2 * Cout, device=DEV, dtype=torch.float64)
+    y = conv(to_nhwc(x).to(DEV), pack_fwd(w), N, H, W, Cin, Cout, R, s, p, p, stats=stats)
+    assert torch.equal(from_nhwc(y.cpu()), ref)
+    assert torch.allclose(stats[:Cout].cpu(), ref.double().sum((0, 2, 3)), rtol=1e-12, atol=1e-6)
+    assert torch.allclose(stats[Cout:].cpu(), ref.double().pow(2).sum((0, 2, 3)), rtol=1e-6)
+
+
+@pytest.mark.parametrize("case", [CONV_CASES[0], CONV_CASES[1], CONV_CASES[7], (2, 32, 32, 32, 64, 4, 1, None)])
+def test_conv_split_mode_is_fp32_accurate(case):
+    """3xTF32: generic fp32 operands as (hi, lo) pairs -> result within a few fp32 ulps of the
+    exact convolution, where a single TF32 pass is only good to ~5e-4; also checks the (hi, lo)
+    output path and the split residual."""
+    N, H, W, Cin, Cout, R, s, p = case
+    plo, phi = (p, p) if p is not None else (2, 1)            # the stem's asymmetric padding
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(N, Cin, H, W, generator=g) * 3 + 1
+    w = torch.randn(Cout, Cin, R, R, generator=g) * 0.05
+    xp = F.pad(x.double(), (plo, phi, plo, phi))
+    ref = F.conv2d(xp, w.double(), None, s, 0)
+    scale = float(ref.abs().max())
+    xh, xl = split_pair(to_nhwc(x))
+    y = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, plo, phi)
+    err3 = float((from_nhwc(y.cpu()).double() - ref).abs().max()) / scale
+    y1 = conv(xh.to(DEV), pack_fwd(w), N, H, W, Cin, Cout, R, s, plo, phi)
+    err1 = float((from_nhwc(y1.cpu()).double() - ref).abs().max()) / scale
+    assert err3 < 1e-4, err3      # floor = the tensor core's FP32 accumulation (K up to 4608)
+    assert err1 > 10 * err3                                    # the compensation is what does it
+    res = torch.randn(ref.shape, generator=g)
+    rh, rl = split_pair(to_nhwc(res))
+    y_lo = torch.empty_like(y)
+    y2 = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, plo, phi,
+              resid=rh.to(DEV), resid_lo=rl.to(DEV), relu=1, y_lo=y_lo)
+    want = torch.relu(ref + res.double())
+    got = from_nhwc((y2.double() + y_lo.double()).cpu())
+    assert float((got - want).abs().max()) / scale < 1e-4
+    assert torch.equal(y2.cpu(), O.tf32_round(y2.cpu()))      # hi plane is TF32-representable
+
+
+def test_conv_epilogue_scale_shift_resid_mask_relu_round():
+    N, H, W, Cin, Cout = 2, 14, 14, 64, 128
+    x, w = ints((N, Cin, H, W), -4, 4, 3), ints((Cout, Cin, 3, 3), -2, 2, 4, 0.25)
+    scale, shift = ints((Cout,), 1, 4, 5, 0.5), ints((Cout,), -8, 8, 6)
+    resid, mask = ints((N, Cout, H, W), -16, 16, 7), ints((N, Cout, H, W), -1, 1, 8)
+    acc = F.conv2d(x, w, None, 1, 1)
+    ref = torch.relu(acc * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+                     + torch.where(mask > 0, resid, torch.zeros(())))
+    y = conv(to_nhwc(x).to(DEV), pack_fwd(w), N, H, W, Cin, Cout, 3, 1, 1, 1, scale=scale.to(DEV),
+             shift=shift.to(DEV), resid=to_nhwc(resid).to(DEV), mask=to_nhwc(mask).to(DEV), relu=1,
+             rnd=1)
+    assert torch.equal(from_nhwc(y.cpu()), O.tf32_round(ref))
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad_bit_exact(case):
+    N, H, W, Cin, Cout, R, s, p = case
+    x = ints((N, Cin, H, W), -2, 2, 11)
+    P = (H + 2 * p - R) // s + 1
+    dy = ints((N, Cout, P, P), -2, 2, 12, 0.5)
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, R, R), dy, stride=s, padding=p)
+    dwp = torch.zeros(Cout, R * R * Cin, device=DEV)
+    call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
+         p, p, p, p)
+    dw = torch.empty(Cout, Cin, R, R, device=DEV)
+    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R)
+    assert torch.equal(dw.cpu(), ref)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad_bit_exact(case):
+    """data gradient = forward kernel over the (zero-stuffed) output gradient with the flipped,
+    transposed weight pack."""
+    N, H, W, Cin, Cout, R, s, p = case
+    w = ints((Cout, Cin, R, R), -2, 2, 21, 0.25)
+    P = (H + 2 * p - R) // s + 1
+    dy = ints((N, Cout, P, P), -4, 4, 22)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=s, padding=p)
+    g = to_nhwc(dy).to(DEV)
+    if s == 2:
+        up = torch.full((N, H, W, Cout), float("nan"), device=DEV)
+        call("b2n_upsample_zero", g, up, N, P, P, H, W, Cout)
+        g, gh = up, H
+    else:
+        gh = P
+    pad = R - 1 - p
+    dx = conv(g, pack_dgrad(w), N, gh, gh, Cout, Cin, R, 1, pad, pad)
+    assert torch.equal(from_nhwc(dx.cpu()), ref)
+
+
+@pytest.mark.parametrize("size", [(2, 64, 64), (1, 224, 224), (3, 34, 46)])
+def test_stem_space_to_depth_conv_and_wgrad(size):
+    N, H, W = size
+    x = ints((N, 3, H, W), 0, 255, 31)                       # uint8-valued patches
+    w = ints((64, 3, 7, 7), -2, 2, 32, 0.25)
+    ref = F.conv2d(x, w, None, 2, 3)
+    xs = torch.empty(N, H // 2, W // 2, 32, device=DEV)
+    call("b2n_stem_pack_input", x.to(DEV), xs, None, N, H, W)
+    ws = torch.empty(64, 16 * 32, device=DEV)
+    call("b2n_stem_pack_weight", w.to(DEV), ws, None, 64)
+    y = conv(xs, ws, N, H // 2, W // 2, 32, 64, 4, 1, 2, 1)
+    assert torch.equal(from_nhwc(y.cpu()), ref)
+    dy = ints(tuple(ref.shape), -1, 1, 33)
+    ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=3)
+    dws = torch.zeros(64, 16 * 32, device=DEV)
+    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1)
+    dw = torch.empty(64, 3, 7, 7, device=DEV)
+    call("b2n_stem_unpack_wgrad", dws, dw, 64)
+    assert torch.equal(dw.cpu(), ref_dw)
+
+
+def test_conv_rejects_bad_shapes_loudly():
+    x = torch.zeros(1, 4, 4, 24, device=DEV)
+    with pytest.raises(RuntimeError, match="Cin=24"):
+        conv(x, torch.zeros(64, 24 * 9, device=DEV), 1, 4, 4, 24, 64, 3, 1, 1, 1)
+
+
+@pytest.mark.parametrize("C,rows,n_updates", [(64, 1000, 1), (512, 98, 3), (128, 7, 1)])
+def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
+    g = torch.Generator().manual_seed(C + rows)
+    y = (torch.randn(rows, C, generator=g) * 3 + 1.5)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(rows, C, generator=g)
+    gout = torch.randn(rows, C, generator=g)
+    bn = torch.nn.BatchNorm1d(C)
+    bn.weight.data.copy_(gamma); bn.bias.data.copy_(beta)
+    bn.running_mean.data.uniform_(-1, 1, generator=g); bn.running_var.data.uniform_(0.5, 2, generator=g)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    yr = y.clone().requires_grad_(True)
+    for _ in range(n_updates):
+        z = bn(yr)
+    out_ref = torch.relu(z + res)
+    out_ref.backward(gout)
+
+    yd = y.to(DEV)
+    stats = torch.stack([yd.double().sum(0), yd.double().pow(2).sum(0)]).flatten().contiguous()
+    rm, rv = rm0.to(DEV), rv0.to(DEV)
+    scale, shift, mean, invstd = (torch.empty(C, device=DEV) for _ in range(4))
+    call("b2n_bn_finalize", stats, gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, mean, invstd, C,
+         float(rows), 0.1, 1e-5, n_updates)
+    out = torch.empty(rows, C, device=DEV)
+    call("b2n_bn_apply", yd, scale, shift, res.to(DEV), None, None, None, out, None, rows, C, 1, 0)
+    rh, rl = split_pair(res)
+    o_hi, o_lo = torch.empty(rows, C, device=DEV), torch.empty(rows, C, device=DEV)
+    call("b2n_bn_apply", yd, scale, shift, rh.to(DEV), rl.to(DEV), None, None, o_hi, o_lo, rows, C, 1, 0)
+    assert torch.allclose((o_hi + o_lo).cpu(), out_ref.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.equal(o_hi.cpu(), O.tf32_round(o_hi.cpu()))
+    assert float((o_hi + o_lo - out).abs().max()) <= 1e-6 * float(out.abs().max())
+    assert torch.allclose(out.cpu(), out_ref.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm.cpu(), bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv.cpu(), bn.running_var, rtol=1e-5, atol=1e-6)
+    sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    call("b2n_bn_bwd_reduce", gout.to(DEV), out, yd, mean, invstd, sums, rows, C)
+    dy, dgamma, dbeta = torch.empty(rows, C, device=DEV), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    call("b2n_bn_bwd_apply", gout.to(DEV), out, yd, mean, invstd, gamma.to(DEV), sums, dy, dgamma,
+         dbeta, rows, C, 0)
+    scale_t = float(yr.grad.abs().max())
+    assert float((dy.cpu() - yr.grad).abs().max()) < 2e-4 * scale_t
+    assert torch.allclose(dgamma.cpu(), bn.weight.grad, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(dbeta.cpu(), bn.bias.grad, rtol=1e-4, atol=1e-4)
+    # eval-mode fold
+    call("b2n_bn_fold_eval", gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, C, 1e-5)
+    bn.eval()
+    call("b2n_bn_apply", yd, scale, shift, None, None, None, None, out, None, rows, C, 0, 0)
+    assert torch.allclose(out.cpu(), bn(y).detach(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 7, 9, 64), (3, 112, 112, 64)])
+def test_bn_relu_maxpool_forward_backward(shape):
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(H * W)
+    y = torch.randn(N, C, H, W, generator=g)
+    scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    yr = y.clone().requires_grad_(True)
+    z = torch.relu(yr * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    a_ref = F.max_pool2d(z, 3, 2, 1)
+    z.retain_grad()
+    ga = torch.randn(a_ref.shape, generator=g)
+    a_ref.backward(ga)
+    P, Q = a_ref.shape[2:]
+    a = torch.empty(N, P, Q, C, device=DEV)
+    idx = torch.empty(N, P, Q, C, device=DEV, dtype=torch.uint8)
+    yd = to_nhwc(y).to(DEV)
+    a_lo = torch.empty_like(a)
+    call("b2n_bn_relu_maxpool", yd, scale.to(DEV), shift.to(DEV), a, a_lo, idx, N, H, W, C)
+    assert torch.allclose(from_nhwc((a + a_lo).cpu()), a_ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(a.cpu(), O.tf32_round(a.cpu()))
+    gz = torch.empty(N, H, W, C, device=DEV)
+    call("b2n_maxpool_relu_bwd", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), gz, N, H,
+         W, C)
+    assert torch.allclose(from_nhwc(gz.cpu()), z.grad * (z.detach() > 0), rtol=1e-6, atol=1e-7)
+
+
+def test_avgpool():
+    a = torch.randn(5, 49, 512)
+    e = torch.empty(5, 512, device=DEV)
+    call("b2n_avgpool_fwd", a.to(DEV), None, e, 5, 49, 512)
+    assert torch.allclose(e.cpu(), a.mean(1), rtol=1e-5, atol=1e-6)
+    ah, al = split_pair(a)
+    call("b2n_avgpool_fwd", ah.to(DEV), al.to(DEV), e, 5, 49, 512)
+    assert torch.allclose(e.cpu(), a.mean(1), rtol=1e-5, atol=1e-6)
+    ge = torch.randn(5, 512)
+    g = torch.empty(5, 49, 512, device=DEV)
+    call("b2n_avgpool_bwd", ge.to(DEV), g, 5, 49, 512)
+    assert torch.allclose(g.cpu(), (ge / 49).unsqueeze(1).expand(5, 49, 512), rtol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 2, 77, 768])
+def test_heads_forward_backward_fp32(n):
+    from ssl_cr_histo_b200 import heads
+
+    torch.manual_seed(n)
+    l1, l2 = torch.nn.Linear(1024, 512), torch.nn.Linear(512, 256)
+    x = torch.randn(n, 1024)
+    dy = torch.randn(n, 256)
+    xr = x.clone().requires_grad_(True)
+    ref = l2(torch.relu(l1(xr)))
+    ref.backward(dy)
+    m1, m2 = torch.nn.Linear(1024, 512).to(DEV), torch.nn.Linear(512, 256).to(DEV)
+    m1.load_state_dict(l1.state_dict()); m2.load_state_dict(l2.state_dict())
+    xm = x.to(DEV).requires_grad_(True)
+    out = heads.mlp2(xm, m1, m2)
+    out.backward(dy.to(DEV))
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(xm.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-5)
+    for a, b in ((m1, l1), (m2, l2)):
+        assert torch.allclose(a.weight.grad.cpu(), b.weight.grad, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(a.bias.grad.cpu(), b.bias.grad, rtol=1e-4, atol=1e-4)
+    lin, lin_m = torch.nn.Linear(768, 9), torch.nn.Linear(768, 9).to(DEV)
+    lin_m.load_state_dict(lin.state_dict())
+    f = torch.randn(n, 768)
+    assert torch.allclose(heads.linear(f.to(DEV), lin_m).cpu(), lin(f).detach(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_losses_match_torch():
+    g = torch.Generator().manual_seed(9)
+    # RSP cross-entropy + argmax
+    lg = torch.randn(37, 6, generator=g)
+    tgt = torch.randint(0, 6, (37,), generator=g)
+    lr = lg.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, tgt)
+    ref.backward()
+    lm = lg.to(DEV).requires_grad_(True)
+    loss, pred = losses.cross_entropy(lm, tgt.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-6 * max(1, abs(float(ref)))
+    assert torch.equal(pred.cpu(), torch.argmax(lg, 1))
+    assert torch.allclose(lm.grad.cpu(), lr.grad, rtol=1e-5, atol=1e-7)
+    # BreastPathQ MSE / MSE
+    lx, tx = torch.randn(12, 1, generator=g), torch.rand(12, generator=g)
+    lw, ls = torch.randn(20, 1, generator=g), torch.randn(20, 1, generator=g)
+    a, b = lx.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    ref = F.mse_loss(a, tx.view(-1, 1)) + 0.7 * F.mse_loss(lw, b)
+    ref.backward()
+    am, bm = lx.to(DEV).requires_grad_(True), ls.to(DEV).requires_grad_(True)
+    total, parts = losses.consistency_mse(am, tx.to(DEV), lw.to(DEV), bm, 0.7)
+    total.backward()
+    assert abs(float(total) - float(ref)) < 1e-6 and abs(float(parts[2]) - float(ref)) < 1e-6
+    assert torch.allclose(am.grad.cpu(), a.grad, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(bm.grad.cpu(), b.grad, rtol=1e-5, atol=1e-8)
+    # Kather CE + CE-to-teacher-argmax
+    lx, tx = torch.randn(9, 9, generator=g), torch.randint(0, 9, (9,), generator=g)
+    lw, ls = torch.randn(24, 9, generator=g), torch.randn(24, 9, generator=g)
+    a, b = lx.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    tu = torch.max(torch.softmax(lw, -1), -1)[1]
+    ref = F.cross_entropy(a, tx) + 1.0 * F.cross_entropy(b, tu)
+    ref.backward()
+    am, bm = lx.to(DEV).requires_grad_(True), ls.to(DEV).requires_grad_(True)
+    total, parts, pred, pseudo = losses.consistency_ce(am, tx.to(DEV), lw.to(DEV), bm, 1.0)
+    total.backward()
+    assert abs(float(total) - float(ref)) < 1e-6 * max(1, abs(float(ref)))
+    assert torch.equal(pseudo.cpu(), tu) and torch.equal(pred.cpu(), torch.argmax(lx, 1))
+    assert torch.allclose(am.grad.cpu(), a.grad, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(bm.grad.cpu(), b.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_lerp_handoff_bitwise_and_lookahead_golden():
+    from util import golden
+
+    g = golden("lookahead.npz")
+    shapes = [(7,), (3, 5), (2, 2, 2)]
+    flat, grads = torch.tensor(g["init"]), torch.tensor(g["grads"])
+    params, gs, off = [], [], 0
+    for s in shapes:
+        n = int(np.prod(s))
+        params.append(flat[off:off + n].clone().view(s).to(DEV)); gs.append(grads[off:off + n].view(s).to(DEV))
+        off += n
+    cached = [p.clone() for p in params]
+    for step in range(7):
+        for p, gr in zip(params, gs):
+            p.add_(gr, alpha=-0.1)
+        if (step + 1) % 5 == 0:
+            weights.lookahead_pull_(params, cached, 0.5)
+            for p, c in zip(params, cached):
+                assert torch.equal(p, c)
+        now = torch.cat([p.flatten() for p in params]).cpu()
+        ref = torch.tensor(g["trace"][step])
+        assert float((now - ref).abs().max()) <= 1.2e-7 * float(ref.abs().max()), step  # <= 1 ulp
+    # alpha = 1 is a bit-exact copy even over inf / nan destinations
+    dst = [torch.full((1000,), float("nan"), device=DEV), torch.full((3, 3), float("inf"), device=DEV)]
+    src = [torch.randn(1000, device=DEV), torch.randn(3, 3, device=DEV)]
+    weights.lerp_(dst, src, 1.0)
+    assert all(torch.equal(d, s) for d, s in zip(dst, src))
+    # empty list and > 96 tensors (table chunking)
+    weights.lerp_([], [], 0.5)
+    many_d = [torch.zeros(5, device=DEV) for _ in range(130)]
+    many_s = [torch.full((5,), float(i), device=DEV) for i in range(130)]
+    weights.lerp_(many_d, many_s, 0.25)
+    assert all(torch.allclose(d, s * 0.25) for d, s in zip(many_d, many_s))

@@ -1,0 +1,312 @@
+"""End-to-end GPU parity: the drop-in classes driven by the reference's own (restated) loop
+bodies, against (a) golden vectors produced by the REAL reference modules and (b) the CPU oracle
+on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8d):
+  * fp32 logits and losses: max|d| / max|ref| <= 1e-3 (measured ~1e-5: forward convs run
+    error-compensated 3xTF32);
+  * RSP argmax: bit-exact, with an asserted top-2 margin floor;
+  * BN running statistics: <= 1e-3 relative (measured ~3e-5), counters exact;
+  * gradients: <= 3e-2 relative L2 per tensor (measured ~1e-2).  The backward convs multiply
+    plain TF32 operands, and -- the larger part -- a forward difference of only ~5e-5 (the
+    tensor core's FP32 accumulation order) already flips ~1e-5 of the ReLU gates, which a
+    gradient with random-sign terms sees as sqrt(flipped fraction).  DESIGN.md, "Numerics".
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ssl_cr_histo_b200.net as net
+from ssl_cr_histo_b200 import weights
+from oracle import ref_net as O
+from util import golden, max_rel, rel_l2, top2_margin
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-3
+GRAD_TOL = 3e-2
+
+
+def pair(kind, head, seed=42):
+    """(oracle model, oracle head, CUDA model, CUDA head) with the reference's seeded init."""
+    st, hs = O.reference_state(seed, head)
+    om = O.TripletNet("resnet18") if kind == "triplet" else O.TripletNet_Finetune("resnet18")
+    gm = net.TripletNet("resnet18") if kind == "triplet" else net.TripletNet_Finetune("resnet18")
+    if head[0] == "classifier":
+        oh, gh = O.Classifier(768, head[1]), net.Classifier(768, head[1])
+    else:
+        oh, gh = O.FinetuneResNet(head[1]), net.FinetuneResNet(head[1])
+    for m in (om, gm):
+        m.load_state_dict(st)
+    for h in (oh, gh):
+        h.load_state_dict(hs)
+    return om, oh, gm.to(DEV), gh.to(DEV)
+
+
+def grads_of(mods):
+    return [(n, p.grad) for m in mods for n, p in m.named_parameters()]
+
+
+def assert_grads_close(mine, ref, tol=GRAD_TOL):
+    worst = ("", 0.0)
+    for (n1, g1), (n2, g2) in zip(grads_of(mine), grads_of(ref)):
+        assert n1 == n2
+        assert (g1 is None) == (g2 is None), n1
+        if g1 is None:
+            continue
+        r = rel_l2(g1, g2)
+        if r > worst[1]:
+            worst = (n1, r)
+    assert worst[1] <= tol, "gradient %s differs by %.3e relative L2" % worst
+    return worst[1]
+
+
+def assert_buffers_close(mine, ref, tol=TOL):
+    for (k1, b1), (k2, b2) in zip(mine.named_buffers(), ref.named_buffers()):
+        assert k1 == k2
+        if b1.dtype == torch.long:
+            assert int(b1) == int(b2), k1
+        else:
+            assert max_rel(b1, b2) <= tol, k1
+
+
+# ------------------------------------------------------------------ golden (real reference)
+def test_cfg1_rsp_forward_matches_reference_golden():
+    """BASELINE.json configs[0]: 8 synthetic 224x224 triples, batch 2, logits + permutation id."""
+    g = golden("cfg1_rsp_forward.npz")
+    _, _, model, cls = pair("triplet", ("classifier", 6))
+    model.train(); cls.train()
+    i1, i2, i3 = (O.synthetic_patches(8, 224, seed=s).to(DEV) for s in (0, 1, 2))
+    feats, logits = [], []
+    with torch.no_grad():
+        for b in range(4):
+            sl = slice(2 * b, 2 * b + 2)
+            f = model(i1[sl], i2[sl], i3[sl])
+            feats.append(f); logits.append(cls(f))
+    feats, logits = torch.cat(feats), torch.cat(logits)
+    assert max_rel(logits, g["logits"]) <= TOL
+    assert max_rel(feats, g["feats"]) <= TOL
+    margin = top2_margin(g["logits"])
+    err = float((logits.cpu() - torch.tensor(g["logits"])).abs().max())
+    assert margin > 10 * err, "top-2 margin %.2e too small against error %.2e" % (margin, err)
+    assert np.array_equal(torch.argmax(logits, 1).cpu().numpy(), g["pred"])      # bit-exact argmax
+    buf = np.array([float(b.double().sum()) for b in model.buffers()])
+    assert np.allclose(buf, g["buffers"], rtol=TOL, atol=1e-2)
+    assert int(model.model.bn1.num_batches_tracked) == 12                         # 4 iters x 3 passes
+
+
+def test_step_goldens_losses_and_logits():
+    g = golden("rsp_step.npz")
+    _, _, model, cls = pair("triplet", ("classifier", 6))
+    model.train(); cls.train()
+    opt = O.make_rsp_optimizer(list(model.parameters()) + list(cls.parameters()))
+    i1, i2, i3 = (O.synthetic_patches(2, 64, seed=s).to(DEV) for s in (0, 1, 2))
+    out = O.rsp_pretrain_step(model, cls, opt, i1, i2, i3, torch.tensor([3, 5], device=DEV))
+    assert abs(float(out["loss"]) - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    assert max_rel(out["output"], g["output"]) <= TOL
+    assert np.array_equal(out["pred"].cpu().numpy(), g["pred"])
+    gn = np.array([float(p.grad.double().norm()) for m in (model, cls) for p in m.parameters()])
+    assert np.allclose(gn, g["grad_norms"], rtol=GRAD_TOL, atol=1e-7)
+    for kind, C in (("mse", 1), ("ce", 9)):
+        g = golden("cr_step_%s.npz" % kind)
+        _, _, student, cls_s = pair("finetune", ("finetune", C))
+        teacher, cls_t = copy.deepcopy(student), copy.deepcopy(cls_s)
+        O.freeze_by_index(teacher, 64)
+        for p in cls_t.parameters():
+            p.requires_grad = False
+        teacher.eval(); cls_t.eval(); student.train(); cls_s.train()
+        opt = O.make_cr_optimizer(list(student.parameters()) + list(cls_s.parameters()))
+        tx = torch.tensor([0.25] * 3) if kind == "mse" else torch.tensor([4, 4, 4])
+        out = O.consistency_step(teacher, student, cls_t, cls_s, opt,
+                                 O.synthetic_patches(3, 64, seed=10).to(DEV), tx.to(DEV),
+                                 O.synthetic_patches(2, 64, seed=11).to(DEV),
+                                 O.synthetic_patches(2, 64, seed=12).to(DEV), 1.0, kind)
+        for k, gk in (("sup", "sup"), ("cons", "cons"), ("loss", "final")):
+            assert abs(float(out[k]) - float(g[gk])) <= TOL * max(abs(float(g[gk])), 1e-3), (kind, k)
+        for k in ("logits_x", "logits_u_s", "logits_u_w"):
+            assert max_rel(out[k], g[k]) <= TOL, (kind, k)
+    g = golden("finetune_step.npz")
+    _, _, model, cls = pair("finetune", ("finetune", 9))
+    model.train(); cls.train()
+    opt = torch.optim.Adam(list(model.parameters()) + list(cls.parameters()), lr=1e-5,
+                           weight_decay=1e-4)
+    out = O.finetune_step(model, cls, opt, O.synthetic_patches(4, 64, seed=20).to(DEV),
+                          torch.tensor([0, 8, 3, 3], device=DEV))
+    assert abs(float(out["loss"]) - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    assert max_rel(out["output"], g["output"]) <= TOL
+    assert np.array_equal(out["pred"].cpu().numpy(), g["pred"])
+    assert int(model.model.bn1.num_batches_tracked) == 3
+
+
+# ------------------------------------------------------------------ oracle, same inputs
+@pytest.mark.parametrize("N,size", [(8, 224), (6, 96)])
+def test_rsp_pretrain_step_parity(N, size):
+    """cfg2 shape class (pretrain_BreastPathQ.py:53-68): logits / loss / argmax / BN buffers /
+    gradients / the SGD-Nesterov-updated weights."""
+    i1, i2, i3 = (O.synthetic_patches(N, size, seed=s) for s in (0, 1, 2))
+    target = torch.randint(0, 6, (N,), generator=torch.Generator().manual_seed(5))
+    om, oh, gm, gh = pair("triplet", ("classifier", 6))
+    for m in (om, oh, gm, gh):
+        m.train()
+    opt_g = O.make_rsp_optimizer(list(gm.parameters()) + list(gh.parameters()))
+    out_g = O.rsp_pretrain_step(gm, gh, opt_g, i1.to(DEV), i2.to(DEV), i3.to(DEV), target.to(DEV))
+    opt_o = O.make_rsp_optimizer(list(om.parameters()) + list(oh.parameters()))
+    out_o = O.rsp_pretrain_step(om, oh, opt_o, i1, i2, i3, target)
+    assert max_rel(out_g["output"], out_o["output"]) <= TOL
+    assert max_rel(out_g["feats"], out_o["feats"]) <= TOL
+    assert abs(float(out_g["loss"]) - float(out_o["loss"])) <= TOL * float(out_o["loss"])
+    err = float((out_g["output"].cpu() - out_o["output"]).abs().max())
+    assert top2_margin(out_o["output"]) > 10 * err
+    assert torch.equal(out_g["pred"].cpu(), out_o["pred"])                 # bit-exact argmax
+    assert_buffers_close(gm, om)
+    assert_grads_close([gm, gh], [om, oh])
+    for (n, p), (_, q) in zip(gm.named_parameters(), om.named_parameters()):
+        # weights after the step (biases start at 0, so the bound is absolute there)
+        assert float((p.cpu() - q).abs().max()) <= TOL * float(q.abs().max()) + 1e-6, n
+
+
+@pytest.mark.parametrize("kind,C", [("mse", 1), ("ce", 9)])
+def test_consistency_step_parity(kind, C):
+    """cfg3 shape class (eval_BreastPathQ_SSL_CR.py:76-105 / eval_Kather_SSL_CR.py:71-105),
+    --modules_student 0, b=2 labeled items x 3 views, mu=4, 224x224."""
+    b, mu, size = 2, 4, 224
+    ix = O.synthetic_patches(3 * b, size, seed=10)
+    iw, is_ = O.synthetic_patches(b * mu, size, seed=11), O.synthetic_patches(b * mu, size, seed=12)
+    g = torch.Generator().manual_seed(6)
+    tx = torch.rand(3 * b, generator=g) if kind == "mse" else torch.randint(0, C, (3 * b,), generator=g)
+
+    def run(models, dev):
+        student, cls_s = models
+        teacher, cls_t = copy.deepcopy(student), copy.deepcopy(cls_s)      # :394-402 same ckpt
+        O.freeze_by_index(teacher, 64)
+        for p in cls_t.parameters():
+            p.requires_grad = False
+        teacher.eval(); cls_t.eval(); student.train(); cls_s.train()
+        opt = O.make_cr_optimizer(list(student.parameters()) + list(cls_s.parameters()))
+        return O.consistency_step(teacher, student, cls_t, cls_s, opt, ix.to(dev), tx.to(dev),
+                                  iw.to(dev), is_.to(dev), 1.0, kind)
+
+    om, oh, gm, gh = pair("finetune", ("finetune", C))
+    out_g = run((gm, gh), DEV)
+    out_o = run((om, oh), "cpu")
+    for k in ("logits_u_w", "logits_x", "logits_u_s"):       # teacher (eval) and student (train)
+        assert max_rel(out_g[k], out_o[k]) <= TOL, k
+    for k in ("sup", "cons", "loss"):
+        assert abs(float(out_g[k]) - float(out_o[k])) <= TOL * max(abs(float(out_o[k])), 1e-3), k
+    assert_buffers_close(gm, om)                             # incl. num_batches_tracked == 3
+    assert_grads_close([gm, gh], [om, oh])
+
+
+def test_frozen_trunk_default_and_partial_freeze():
+    """--modules_student 60 (reference default: no conv backward at all) and --modules 45
+    (layer4 + heads trainable): frozen parameters get no gradient, the rest match."""
+    x = O.synthetic_patches(4, 96, seed=30)
+    tgt = torch.tensor([1, 0, 1, 1])
+    for n_frozen in (60, 45):
+        om, oh, gm, gh = pair("finetune", ("finetune", 2))
+        for m in (om, gm):
+            O.freeze_by_index(m, n_frozen)
+            m.train()
+        lo = F.cross_entropy(oh(om(x)), tgt)
+        lo.backward()
+        lg = F.cross_entropy(gh(gm(x.to(DEV))), tgt.to(DEV))
+        lg.backward()
+        assert abs(float(lg) - float(lo)) <= 1e-4 * float(lo)
+        for i, ((n, p), (_, q)) in enumerate(zip(gm.named_parameters(), om.named_parameters())):
+            if i < n_frozen:
+                assert p.grad is None and q.grad is None, n
+            else:
+                assert rel_l2(p.grad, q.grad) <= GRAD_TOL, n
+        assert_buffers_close(gm, om)                         # BN stays in train mode while frozen
+
+
+def test_finetune_single_pass_equals_three_reference_passes():
+    """models/net.py:86-90 runs the trunk 3x on the same input; the CUDA module runs it once.
+    Feature blocks, summed gradients and the 3-fold BN buffer update must all agree."""
+    x = O.synthetic_patches(4, 96, seed=40)
+    om, oh, gm, gh = pair("finetune", ("finetune", 9))
+    om.train(); gm.train()
+    f = gm(x.to(DEV))
+    assert torch.equal(f[:, :256], f[:, 256:512]) and torch.equal(f[:, :256], f[:, 512:])
+    fo = om(x)
+    assert max_rel(f, fo) <= 1e-4
+    assert_buffers_close(gm, om, 1e-4)
+    assert int(gm.model.layer3[1].bn2.num_batches_tracked) == 3
+    tgt = torch.tensor([0, 3, 8, 8])
+    F.cross_entropy(gh(f), tgt.to(DEV)).backward()
+    F.cross_entropy(oh(fo), tgt).backward()
+    assert_grads_close([gm, gh], [om, oh])
+
+
+def test_triplet_permutation_invariant_and_eval_mode():
+    """In eval mode f12 only depends on (i1, i2); equal inputs give equal blocks; results are
+    deterministic; and the eval-mode (BN folded into the conv epilogue) features match."""
+    om, _, gm, _ = pair("triplet", ("classifier", 6))
+    gm.eval(); om.eval()
+    a, b = O.synthetic_patches(2, 64, seed=1).to(DEV), O.synthetic_patches(2, 64, seed=2).to(DEV)
+    with torch.no_grad():
+        f_aab = gm(a, a, b)
+        f_aaa = gm(a, a, a)
+        f_again = gm(a, a, b)
+        ref = om(a.cpu(), a.cpu(), b.cpu())
+    assert torch.equal(f_aab, f_again)                                    # deterministic
+    assert torch.equal(f_aaa[:, :256], f_aaa[:, 256:512]) and torch.equal(f_aaa[:, :256], f_aaa[:, 512:])
+    assert torch.equal(f_aab[:, :256], f_aaa[:, :256])                    # f12 only depends on (i1,i2)
+    assert torch.equal(f_aab[:, 256:512], f_aab[:, 512:])                 # f23 == f13 when i1 == i2
+    assert max_rel(f_aab, ref) <= TOL
+
+
+def test_eval_mode_with_trainable_trunk_is_rejected_loudly():
+    _, _, gm, _ = pair("finetune", ("finetune", 2))
+    gm.eval()
+    with pytest.raises(NotImplementedError, match="eval-mode BatchNorm"):
+        gm(O.synthetic_patches(1, 32, seed=3).to(DEV))
+    gm.train()
+    with pytest.raises(RuntimeError, match="even"):
+        gm(torch.zeros(1, 3, 33, 32, device=DEV))
+
+
+def test_teacher_handoff_and_weight_cache_invalidation():
+    _, _, student, _ = pair("finetune", ("finetune", 1))
+    teacher = copy.deepcopy(student).eval()
+    x = O.synthetic_patches(2, 64, seed=50).to(DEV)
+    with torch.no_grad():
+        before = teacher(x)
+        for p in student.parameters():
+            p.mul_(1.01)
+        student.model.bn1.running_mean.add_(0.5)
+        student.model.bn1.num_batches_tracked.add_(7)
+    weights.teacher_handoff_(teacher, student)                # alpha = 1, one launch
+    for (k, v), (_, w) in zip(teacher.state_dict().items(), student.state_dict().items()):
+        assert torch.equal(v, w), k                           # bit-exact, incl. int64 counters
+    with torch.no_grad():
+        after = teacher(x)
+        expect = copy.deepcopy(student).eval()(x)             # the reference's deepcopy hand-off
+    assert not torch.equal(before, after)                     # packed-weight cache was refreshed
+    assert torch.equal(after, expect)
+
+
+def test_large_batch_properties():
+    """Size-independent checks at a BASELINE-scale batch (N=128 at 224x224, one trunk pass):
+    batch rows are independent in eval mode (split == whole, bit-exact), and train-mode BN
+    statistics / features of a duplicated batch equal those of the single batch."""
+    _, _, gm, _ = pair("finetune", ("finetune", 9))
+    x = O.synthetic_patches(128, 224, seed=60).to(DEV)
+    gm.eval()
+    with torch.no_grad():
+        whole = gm(x)
+        parts = torch.cat([gm(x[:48]), gm(x[48:])])
+    assert torch.equal(whole, parts)
+    assert torch.isfinite(whole).all()
+    gm.train()
+    a, b = copy.deepcopy(gm), copy.deepcopy(gm)
+    with torch.no_grad():
+        fa = a(x[:32])
+        fb = b(torch.cat([x[:32], x[:32]]))
+    assert max_rel(fb[:32], fa) <= 1e-4
+    for (k, u), (_, v) in zip(a.named_buffers(), b.named_buffers()):
+        if u.dtype != torch.long and "running_mean" in k:
+            assert max_rel(u, v) <= 1e-4, k

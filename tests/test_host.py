@@ -1,0 +1,182 @@
+"""CPU tests of the host-side logic: C-ABI surface, module contract (names / order / init /
+freezing / deepcopy / error behaviour), no-CPU-fallback guarantee, gradient arena + gloo
+all-reduce with world_size 2."""
+import copy
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import ssl_cr_histo_b200 as b2n
+from ssl_cr_histo_b200 import _lib, build, ddp, net
+from oracle import ref_net as O
+from util import golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    path = build.build_lib()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "b2n.h")).read()
+    declared = sorted(set(re.findall(r"\b(b2n_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "libb2n.so does not export %s" % name
+    assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
+    lib.b2n_version.restype = ctypes.c_int
+    assert lib.b2n_version() == 1
+
+
+def test_library_has_blackwell_tensor_core_and_tma_sass():
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", build.build_lib()], capture_output=True,
+                          text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass or re.search(r"UTC\w*MMA", sass)  # tcgen05.mma
+    assert "UTMALDG" in sass and "IM2COL" in sass                                    # TMA im2col
+    assert "LDTM" in sass                                                            # tcgen05.ld
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", build.build_lib()],
+                                       capture_output=True, text=True).stdout
+
+
+# ------------------------------------------------------------- module contract
+def test_constructor_signatures_and_errors_match_reference():
+    with pytest.raises(NotImplementedError, match="not supported model type: vgg"):
+        net.TripletNet("vgg")
+    with pytest.raises(NotImplementedError, match="not supported model type: resnet34"):
+        net.TripletNet_Finetune("resnet34")
+    c = net.Classifier(768, 6)
+    assert [tuple(p.shape) for p in c.parameters()] == [(128, 768), (128,), (6, 128), (6,)]
+    f = net.FinetuneResNet(9)
+    assert [tuple(p.shape) for p in f.parameters()] == [(9, 768), (9,)]
+    assert list(f.state_dict().keys()) == ["classifier.0.weight", "classifier.0.bias"]
+
+
+def test_parameter_names_order_and_seeded_init_equal_the_reference():
+    g = golden("init_seed42.npz")
+    torch.manual_seed(42)
+    m = net.TripletNet("resnet18")
+    c = net.Classifier(768, 6)
+    assert [n for n, _ in m.named_parameters()] == list(g["param_names"])
+    assert list(m.state_dict().keys()) == list(g["keys"])
+    assert list(c.state_dict().keys()) == list(g["keys_cls"])
+    for row, (k, v) in zip(list(g["fp"]) + list(g["fp_cls"]),
+                           list(m.state_dict().items()) + list(c.state_dict().items())):
+        f = v.double().flatten()
+        assert abs(float(f.sum()) - row[0]) <= 1e-9 * max(1.0, abs(row[0])), k
+        assert np.array_equal(f[:4].numpy(), row[2:2 + min(4, f.numel())]), k
+    idx = {n: i for i, (n, _) in enumerate(m.named_parameters())}
+    # the indices the reference's --modules flags freeze against (eval_Kather_SSL.py:229)
+    assert idx["model.layer1.0.conv1.weight"] == 3 and idx["model.layer2.0.conv1.weight"] == 15
+    assert idx["model.layer3.0.conv1.weight"] == 30 and idx["model.layer4.0.conv1.weight"] == 45
+    assert idx["fc.0.weight"] == 60 and len(idx) == 64
+    assert len(list(m.buffers())) == 60
+
+
+def test_state_dict_round_trip_with_oracle_and_module_prefix_strip():
+    ref = O.TripletNet_Finetune("resnet18")
+    mine = net.TripletNet_Finetune("resnet18")
+    mine.load_state_dict(ref.state_dict())                      # strict
+    prefixed = {"module." + k: v for k, v in mine.state_dict().items()}
+    stripped = {k[7:]: v for k, v in prefixed.items()}          # eval_Kather_SSL.py:344-346
+    ref.load_state_dict(stripped)
+
+
+def test_index_based_freezing_and_deepcopy():
+    student = net.TripletNet_Finetune("resnet18")
+    O.freeze_by_index(student, 60)                              # --modules_student 60 default
+    flags = [p.requires_grad for p in student.parameters()]
+    assert flags == [False] * 60 + [True] * 4
+    teacher = copy.deepcopy(student)
+    assert [p.requires_grad for p in teacher.parameters()] == flags
+    for (k1, v1), (k2, v2) in zip(teacher.state_dict().items(), student.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2) and v1.data_ptr() != v2.data_ptr()
+    assert teacher.model._packs is not student.model._packs and not teacher.model._packs.entries
+    assert "_packs" not in "".join(student.state_dict().keys())
+
+
+def test_no_cpu_fallback():
+    m, c = net.TripletNet("resnet18"), net.Classifier(768, 6)
+    x = torch.zeros(1, 3, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c(torch.zeros(2, 768))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b2n.losses.cross_entropy(torch.zeros(2, 6), torch.zeros(2, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        b2n.weights.lerp_([torch.zeros(3)], [torch.ones(3)], 0.5)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ssl_cr_histo_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no CPU fallback", ""), fn
+            assert "torchvision" not in src.replace("torchvision's", "").replace(
+                "torchvision.models", "tv.models") or fn in ("trunk.py", "net.py"), fn
+    for fn in ("trunk.py", "net.py", "heads.py"):
+        src = open(os.path.join(pkg, fn)).read()
+        assert "import torchvision" not in src and "F.conv2d" not in src and "cudnn" not in src
+
+
+# -------------------------------------------------------------- DDP (gloo, CPU)
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)                                  # same weights on every rank
+    frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+    red = ddp.GradAllReducer(list(lin.parameters()) + [frozen])
+    assert red.nbytes == (15 + 3) * 4
+    data = torch.arange(40, dtype=torch.float32).view(8, 5) / 10.0
+    shard = ddp.shard(data, rank, world)
+    red.zero_grad()
+    lin(shard).pow(2).mean().backward()
+    red.all_reduce()
+    out[rank] = torch.cat([p.grad.flatten() for p in lin.parameters()]).clone()
+    assert lin.weight.grad.data_ptr() == red.flat.data_ptr()     # still aliased into the arena
+    dist.destroy_process_group()
+
+
+def test_grad_arena_allreduce_world2_matches_full_batch():
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    data = torch.arange(40, dtype=torch.float32).view(8, 5) / 10.0
+    lin(data).pow(2).mean().backward()
+    full = torch.cat([p.grad.flatten() for p in lin.parameters()])
+    assert torch.allclose(out[0], out[1])
+    assert torch.allclose(out[0], full, rtol=1e-5, atol=1e-6)    # mean of shard means == full mean
+
+
+def test_shard_rejects_ragged_batches():
+    with pytest.raises(RuntimeError, match="does not divide"):
+        ddp.shard(torch.zeros(7, 2), 0, 2)
+    assert ddp.shard(torch.arange(8), 1, 4).tolist() == [2, 3]

@@ -58,13 +58,13 @@ def main():
     e_ref = tr(x)
 
     class Ctx:
-        needs_input_grad = (False,) * 3 + (True,) * 60
+        needs_input_grad = (False,) * 4 + (True,) * 60
 
     ctx = Ctx()
     trunk = mine.model.train()
     params = list(trunk.parameters())
     with torch.enable_grad():
-        e = _TrunkFn.forward(ctx, x.cuda(), trunk, 1, *params)
+        e = _TrunkFn.forward(ctx, x.cuda(), trunk, 1, True, *params)
     torch.cuda.synchronize()
     sv = ctx.saved
     print("%-14s %s" % ("tensor", "max|d|/max|ref|"))
