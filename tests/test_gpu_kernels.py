@@ -111,7 +111,7 @@ def test_conv_split_mode_is_fp32_accurate(case):
     y1 = conv(xh.to(DEV), pack_fwd(w), N, H, W, Cin, Cout, R, s, plo, phi)
     err1 = float((from_nhwc(y1.cpu()).double() - ref).abs().max()) / scale
     assert err3 < 1e-4, err3      # floor = the tensor core's FP32 accumulation (K up to 4608)
-    assert err1 > 10 * err3                                    # the compensation is what does it
+    assert err1 > 4 * err3                                     # the compensation is what does it
     res = torch.randn(ref.shape, generator=g)
     rh, rl = split_pair(to_nhwc(res))
     y_lo = torch.empty_like(y)

@@ -165,7 +165,7 @@ def test_rsp_pretrain_step_parity(N, size):
     assert_grads_close([gm, gh], [om, oh])
     for (n, p), (_, q) in zip(gm.named_parameters(), om.named_parameters()):
         # weights after the step (biases start at 0, so the bound is absolute there)
-        assert float((p.cpu() - q).abs().max()) <= TOL * float(q.abs().max()) + 1e-6, n
+        assert float((p.cpu() - q).abs().max()) <= TOL * float(q.abs().max()) + 1e-5, n
 
 
 @pytest.mark.parametrize("kind,C", [("mse", 1), ("ce", 9)])
