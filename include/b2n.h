@@ -26,6 +26,9 @@ extern "C" {
 
 #define B2N_ABI_VERSION 1
 
+/* IEEE binary16 storage (the FP16 operand planes of the forward convolutions). */
+typedef uint16_t b2n_half;
+
 int b2n_version(void);
 const char* b2n_last_error(void);
 /* kernels enqueued through this library since it was loaded (monotonic, process-wide). */
@@ -35,29 +38,31 @@ int b2n_device_ok(void);
 
 /* ---- tensor-core convolutions ---------------------------------------------------------- */
 
-/* Implicit-GEMM convolution, tcgen05 TF32 / FP32 accumulate.
+/* Implicit-GEMM convolution on tcgen05 tensor cores, FP32 accumulate in TMEM.
  *   y[n,p,q,k] = sum_{r,s,c} x[n, p*stride - pad_h_lo + r, q*stride - pad_w_lo + s, c]
- *                             * w_packed[k][(r*S+s)*Cin + c]
- * Error-compensated mode ("3xTF32", used by every forward conv): when x_lo and w_packed_lo are
- * given, both operands are (hi, lo) pairs of TF32 tensors (hi + lo = the FP32 value) and the
- * kernel accumulates hi*hi + lo*hi + hi*lo -- FP32-grade results from TF32 tensor cores.
- * With x_lo = w_packed_lo = NULL a single TF32 pass is issued (data-gradient launches).
+ *                             * w[k][(r*S+s)*Cin + c]
+ * Two operand modes:
+ *   - error-compensated forward mode (x_h, x_l, w_h, w_l given; x = w_packed = NULL): both
+ *     operands are (hi, lo) pairs of FP16 tensors, hi = fp16(v), lo = fp16(v - hi); the kernel
+ *     accumulates hi*hi + lo*hi + hi*lo (kind::f16) -- FP32-grade results.  Cin = 32 or a
+ *     multiple of 64.
+ *   - plain mode (x, w_packed given; halves NULL): one TF32 pass over fp32 containers (data
+ *     gradients, with a b2n_pack_weight_dgrad pack).  Cin a multiple of 32.
  * epilogue: v = acc; v = v*scale[k] (if scale); v += shift[k] (if shift);
- *           v += resid[..] (+ resid_lo[..]) (if resid; only where mask[..] > 0 if mask); relu;
- *           store v, or TF32-rounded v (round_tf32), or the (hi, lo) pair into y / y_lo (y_lo).
+ *           v += resid[..] (fp32; only where mask[..] > 0 if mask); v += resid_h + resid_l (FP16
+ *           pair); relu; then y (fp32, TF32-rounded if round_tf32) and / or the (hi, lo) FP16 pair
+ *           y_h / y_l are stored.
  * stats (optional, [2][Cout] doubles, caller-zeroed): += per-channel sum / sum of squares of
- * the raw accumulator -- the BatchNorm batch statistics.
- * Requires Cin % 32 == 0, Cout % 64 == 0.  Used for the forward pass AND (with a
- * b2n_pack_weight_dgrad pack) for the data gradient.
+ * the raw accumulator -- the BatchNorm batch statistics.  Cout a multiple of 64.
  * Replaces: tv:92,96,100 (conv3x3 / downsample conv in BasicBlock.forward), tv:268 (stem, via
  * the space-to-depth view), and the conv dgrad reached from loss.backward()
  * (pretrain_BreastPathQ.py:60, eval_BreastPathQ_SSL_CR.py:99). */
-int b2n_conv_fwd(const float* x, const float* x_lo, const float* w_packed,
-                 const float* w_packed_lo, float* y, float* y_lo, int N, int H, int W, int Cin,
-                 int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                 int pad_w_hi, const float* scale, const float* shift, const float* resid,
-                 const float* resid_lo, const float* mask, int relu, int round_tf32, double* stats,
-                 void* stream);
+int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const float* w_packed,
+                 const b2n_half* w_h, const b2n_half* w_l, float* y, b2n_half* y_h, b2n_half* y_l,
+                 int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad_h_lo,
+                 int pad_h_hi, int pad_w_lo, int pad_w_hi, const float* scale, const float* shift,
+                 const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
+                 const float* mask, int relu, int round_tf32, double* stats, void* stream);
 
 /* Weight gradient, split-K over pixels, accumulated atomically:
  *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
@@ -67,21 +72,20 @@ int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int
                    int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
                    int pad_w_hi, void* stream);
 
-/* (K,C,R,S) parameter -> forward pack [K][(r*S+s)*C + c] as a (hi, lo) TF32 pair (w_packed_lo
- * may be NULL), data-gradient pack [C][((R-1-r)*S+(S-1-s))*K + k] (TF32-rounded); packed weight
- * gradient -> (K,C,R,S). */
-int b2n_pack_weight_fwd(const float* w, float* w_packed, float* w_packed_lo, int K, int C, int R,
-                        int S, void* stream);
+/* (K,C,R,S) parameter -> forward pack [K][(r*S+s)*C + c] as a (hi, lo) FP16 pair, data-gradient
+ * pack [C][((R-1-r)*S+(S-1-s))*K + k] (TF32-rounded fp32); packed weight gradient -> (K,C,R,S). */
+int b2n_pack_weight_fwd(const float* w, b2n_half* w_h, b2n_half* w_l, int K, int C, int R, int S,
+                        void* stream);
 int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, void* stream);
 
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
-/* x NCHW fp32 (N,3,H,W), H and W even -> xs (+ xs_lo, may be NULL) NHWC (N,H/2,W/2,32)
- * (12 real channels), as a (hi, lo) TF32 pair. */
-int b2n_stem_pack_input(const float* x_nchw, float* xs, float* xs_lo, int N, int H, int W,
-                        void* stream);
-/* w (K,3,7,7) -> ws (+ ws_lo) [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
-int b2n_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, void* stream);
+/* x NCHW fp32 (N,3,H,W), H and W even -> NHWC (N,H/2,W/2,32) (12 real channels): the (hi, lo)
+ * FP16 pair for the forward conv and (xs32, may be NULL) the TF32 fp32 copy for the wgrad. */
+int b2n_stem_pack_input(const float* x_nchw, b2n_half* xs_h, b2n_half* xs_l, float* xs32, int N,
+                        int H, int W, void* stream);
+/* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
+int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream);
 int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream);
 
 /* ---- BatchNorm / ReLU / residual (tv:93-103,269-270; nn.BatchNorm2d train + eval) -------- */
@@ -95,13 +99,15 @@ int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, 
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                      const float* running_var, float* scale, float* shift, int C, float eps,
                      void* stream);
-/* out = [relu](scale*y + shift + residual); residual = res (+ res_lo when the shortcut is a
- * (hi, lo) pair), or res_scale*res + res_shift when res_scale is given (downsample-branch BN).
- * Output: fp32, TF32-rounded (round_tf32), or a (hi, lo) TF32 pair when out_lo is given.
- * [rows][C] row-major. */
-int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                 const float* res_lo, const float* res_scale, const float* res_shift, float* out,
-                 float* out_lo, long long rows, int C, int relu, int round_tf32, void* stream);
+/* v = [relu](scale*y + shift + residual); residual = res32, or res_scale*res32 + res_shift when
+ * res_scale is given (downsample-branch BN), or the FP16 pair res_h + res_l (identity shortcut).
+ * Outputs, each optional: out32 (fp32, TF32-rounded if round_tf32: the backward pass' operand and
+ * ReLU mask) and the (hi, lo) FP16 pair out_h / out_l (the next forward conv's operand).
+ * [rows][C] row-major, C a multiple of 8. */
+int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
+                 const float* res_scale, const float* res_shift, const b2n_half* res_h,
+                 const b2n_half* res_l, float* out32, b2n_half* out_h, b2n_half* out_l,
+                 long long rows, int C, int relu, int round_tf32, void* stream);
 /* BatchNorm backward, two passes.  g' = g * [mask > 0] (mask = post-ReLU block output or null).
  *   reduce: sums[0][c] += sum g', sums[1][c] += sum g' * xhat        (sums caller-zeroed)
  *   apply : dy = gamma*invstd*(g' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0 */
@@ -116,14 +122,15 @@ int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, in
                       void* stream);
 
 /* ---- pooling (tv:271 MaxPool2d(3,2,1) fused with bn1+relu; tv:278-279 avgpool+flatten) --- */
-int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                        float* a_lo /* may be null */, unsigned char* argmax_idx /* may be null */,
-                        int N, int H, int W, int C, void* stream);
+int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift,
+                        float* a32 /* may be null */, b2n_half* a_h, b2n_half* a_l,
+                        unsigned char* argmax_idx /* may be null */, int N, int H, int W, int C,
+                        void* stream);
 int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* argmax_idx, const float* y,
                          const float* scale, const float* shift, float* gz, int N, int H, int W,
                          int C, void* stream);
-int b2n_avgpool_fwd(const float* a, const float* a_lo /* may be null */, float* e, int N, int HW,
-                    int C, void* stream);
+int b2n_avgpool_fwd(const b2n_half* a_h, const b2n_half* a_l, float* e, int N, int HW, int C,
+                    void* stream);
 int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream);
 
 /* ---- fully-connected heads, exact FP32 (models/net.py:12-15,36-37,60-62,110) ------------- */

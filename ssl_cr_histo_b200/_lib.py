@@ -19,21 +19,21 @@ P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 
 # name -> argument ctypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
-    "b2n_conv_fwd": [P] * 6 + [I] * 12 + [P, P, P, P, P, I, I, P],
+    "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P],
     "b2n_conv_wgrad": [P, P, P] + [I] * 12,
     "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
     "b2n_unpack_wgrad": [P, P, I, I, I, I],
-    "b2n_stem_pack_input": [P, P, P, I, I, I],
+    "b2n_stem_pack_input": [P, P, P, P, I, I, I],
     "b2n_stem_pack_weight": [P, P, P, I],
     "b2n_stem_unpack_wgrad": [P, P, I],
     "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
-    "b2n_bn_apply": [P] * 9 + [LL, I, I, I],
+    "b2n_bn_apply": [P] * 11 + [LL, I, I, I],
     "b2n_bn_bwd_reduce": [P] * 6 + [LL, I],
     "b2n_bn_bwd_apply": [P] * 10 + [LL, I, I],
     "b2n_upsample_zero": [P, P] + [I] * 6,
-    "b2n_bn_relu_maxpool": [P] * 6 + [I] * 4,
+    "b2n_bn_relu_maxpool": [P] * 7 + [I] * 4,
     "b2n_maxpool_relu_bwd": [P] * 6 + [I] * 4,
     "b2n_avgpool_fwd": [P, P, P, I, I, I],
     "b2n_avgpool_bwd": [P, P, I, I, I],

@@ -1,11 +1,15 @@
 // extern "C" surface of libb2n.so -- see include/b2n.h for the contract of every entry point.
 #include "../../include/b2n.h"
 
+#include <cuda_fp16.h>
+
 #include "launch.h"
 
 using namespace b2n;
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline __half* H16(b2n_half* p) { return reinterpret_cast<__half*>(p); }
+static inline const __half* H16(const b2n_half* p) { return reinterpret_cast<const __half*>(p); }
 
 // number of kernels enqueued through this library since load (bench.py's gpu_launches)
 static unsigned long long g_launches = 0;
@@ -31,19 +35,20 @@ int b2n_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
-int b2n_conv_fwd(const float* x, const float* x_lo, const float* w_packed,
-                 const float* w_packed_lo, float* y, float* y_lo, int N, int H, int W, int Cin,
-                 int Cout, int R, int Sf, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                 int pad_w_hi, const float* scale, const float* shift, const float* resid,
-                 const float* resid_lo, const float* mask, int relu, int round_tf32, double* stats,
-                 void* stream) {
-  if (!x || !w_packed || !y) return set_error("b2n_conv_fwd: null tensor");
+int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const float* w_packed,
+                 const b2n_half* w_h, const b2n_half* w_l, float* y, b2n_half* y_h, b2n_half* y_l,
+                 int N, int H, int W, int Cin, int Cout, int R, int Sf, int stride, int pad_h_lo,
+                 int pad_h_hi, int pad_w_lo, int pad_w_hi, const float* scale, const float* shift,
+                 const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
+                 const float* mask, int relu, int round_tf32, double* stats, void* stream) {
   ConvArgs a;
-  a.x = x; a.x_lo = x_lo; a.w = w_packed; a.w_lo = w_packed_lo; a.out = y; a.out_lo = y_lo;
-  a.resid_lo = resid_lo;
+  a.x = x; a.w = w_packed;
+  a.x_h = H16(x_h); a.x_l = H16(x_l); a.w_h = H16(w_h); a.w_l = H16(w_l);
+  a.out = y; a.out_h = H16(y_h); a.out_l = H16(y_l);
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.R = R; a.S = Sf; a.stride = stride;
   a.pad_h_lo = pad_h_lo; a.pad_h_hi = pad_h_hi; a.pad_w_lo = pad_w_lo; a.pad_w_hi = pad_w_hi;
-  a.scale = scale; a.shift = shift; a.resid = resid; a.mask = mask;
+  a.scale = scale; a.shift = shift; a.resid = resid; a.resid_h = H16(resid_h);
+  a.resid_l = H16(resid_l); a.mask = mask;
   a.relu = relu; a.round_tf32 = round_tf32; a.stats = stats;
   return counted(launch_conv(a, S(stream)));
 }
@@ -59,9 +64,9 @@ int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int
   return counted(launch_wgrad(a, S(stream)));
 }
 
-int b2n_pack_weight_fwd(const float* w, float* wp, float* wp_lo, int K, int C, int R, int Sf,
+int b2n_pack_weight_fwd(const float* w, b2n_half* wp_h, b2n_half* wp_l, int K, int C, int R, int Sf,
                         void* stream) {
-  return counted(launch_pack_fwd(w, wp, wp_lo, K, C, R, Sf, S(stream)));
+  return counted(launch_pack_fwd(w, H16(wp_h), H16(wp_l), K, C, R, Sf, S(stream)));
 }
 int b2n_pack_weight_dgrad(const float* w, float* wp, int K, int C, int R, int Sf, void* stream) {
   return counted(launch_pack_dgrad(w, wp, K, C, R, Sf, S(stream)));
@@ -70,12 +75,12 @@ int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, v
   return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, S(stream)));
 }
 
-int b2n_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H, int W,
-                        void* stream) {
-  return counted(launch_stem_pack_input(x, xs, xs_lo, N, H, W, S(stream)));
+int b2n_stem_pack_input(const float* x, b2n_half* xs_h, b2n_half* xs_l, float* xs32, int N, int H,
+                        int W, void* stream) {
+  return counted(launch_stem_pack_input(x, H16(xs_h), H16(xs_l), xs32, N, H, W, S(stream)));
 }
-int b2n_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, void* stream) {
-  return counted(launch_stem_pack_weight(w, ws, ws_lo, K, S(stream)));
+int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream) {
+  return counted(launch_stem_pack_weight(w, H16(ws_h), H16(ws_l), K, S(stream)));
 }
 int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream) {
   return counted(launch_stem_unpack_wgrad(dws, dw, K, S(stream)));
@@ -91,11 +96,13 @@ int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* rm, con
                      float* scale, float* shift, int C, float eps, void* stream) {
   return counted(launch_bn_fold_eval(gamma, beta, rm, rv, scale, shift, C, eps, S(stream)));
 }
-int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                 const float* res_lo, const float* res_scale, const float* res_shift, float* out,
-                 float* out_lo, long long rows, int C, int relu, int round_tf32, void* stream) {
-  return counted(launch_bn_apply(y, scale, shift, res, res_lo, res_scale, res_shift, out, out_lo,
-                                 rows, C, relu, round_tf32, S(stream)));
+int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
+                 const float* res_scale, const float* res_shift, const b2n_half* res_h,
+                 const b2n_half* res_l, float* out32, b2n_half* out_h, b2n_half* out_l,
+                 long long rows, int C, int relu, int round_tf32, void* stream) {
+  return counted(launch_bn_apply(y, scale, shift, res32, res_scale, res_shift, H16(res_h),
+                                 H16(res_l), out32, H16(out_h), H16(out_l), rows, C, relu,
+                                 round_tf32, S(stream)));
 }
 int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
                       const float* invstd, double* sums, long long rows, int C, void* stream) {
@@ -113,18 +120,20 @@ int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, in
   return counted(launch_upsample_zero(dy, up, N, P, Q, H, W, C, S(stream)));
 }
 
-int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                        float* a_lo, unsigned char* idx, int N, int H, int W, int C, void* stream) {
-  return counted(launch_bn_relu_maxpool(y, scale, shift, a, a_lo, idx, N, H, W, C, S(stream)));
+int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a32,
+                        b2n_half* a_h, b2n_half* a_l, unsigned char* idx, int N, int H, int W,
+                        int C, void* stream) {
+  return counted(launch_bn_relu_maxpool(y, scale, shift, a32, H16(a_h), H16(a_l), idx, N, H, W, C,
+                                        S(stream)));
 }
 int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
                          const float* scale, const float* shift, float* gz, int N, int H, int W,
                          int C, void* stream) {
   return counted(launch_maxpool_relu_bwd(ga, idx, y, scale, shift, gz, N, H, W, C, S(stream)));
 }
-int b2n_avgpool_fwd(const float* a, const float* a_lo, float* e, int N, int HW, int C,
+int b2n_avgpool_fwd(const b2n_half* a_h, const b2n_half* a_l, float* e, int N, int HW, int C,
                     void* stream) {
-  return counted(launch_avgpool_fwd(a, a_lo, e, N, HW, C, S(stream)));
+  return counted(launch_avgpool_fwd(H16(a_h), H16(a_l), e, N, HW, C, S(stream)));
 }
 int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream) {
   return counted(launch_avgpool_bwd(ge, g, N, HW, C, S(stream)));

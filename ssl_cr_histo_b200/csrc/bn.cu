@@ -4,6 +4,8 @@
 // behind torchvision BasicBlock.forward (site-packages/torchvision/models/resnet.py:93-103).
 // The per-channel batch statistics themselves (sum, sum of squares) come out of the conv
 // kernel's epilogue (conv_igemm.cuh); here they are finalised, applied, and differentiated.
+#include <cuda_fp16.h>
+
 #include "launch.h"
 #include "ptx.cuh"
 
@@ -51,85 +53,99 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
 }
 
 // --------------------------------------------------------------------- apply
-// out = act(scale*y + shift + residual), residual = res (identity) or res_scale*res + res_shift
-// (the downsample branch's BN), optionally rounded to TF32 because `out` feeds the next conv.
-// OUT_MODE: 0 = plain fp32, 1 = TF32-rounded, 2 = (hi, lo) TF32 pair into out / out_lo.
-// res_lo: low part when the residual is itself a (hi, lo) pair (identity shortcut).
-template <bool RELU, int OUT_MODE>
+// v = act(scale*y + shift + residual); residual = res32 (identity / raw tensor), or
+// res_scale*res32 + res_shift (the downsample branch's BN), or the (hi, lo) FP16 pair
+// res_h + res_l (identity shortcut of a forward activation).
+// Outputs (each optional): out32 -- fp32, TF32-rounded when ROUND (the backward pass' operand /
+// ReLU mask); out_h, out_l -- the (hi, lo) FP16 pair the next forward conv consumes.
+// 8 channels per thread: 2 x 128-bit fp32 loads, 1 x 128-bit store per FP16 plane.
+template <bool RELU, bool ROUND>
 __global__ void bn_apply_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const float4* __restrict__ res,
-                                const float4* __restrict__ res_lo,
+                                const float* __restrict__ shift, const float4* __restrict__ res32,
                                 const float* __restrict__ res_scale,
-                                const float* __restrict__ res_shift, float4* __restrict__ out,
-                                float4* __restrict__ out_lo, size_t n4, int C) {
+                                const float* __restrict__ res_shift, const uint4* __restrict__ res_h,
+                                const uint4* __restrict__ res_l, float4* __restrict__ out32,
+                                uint4* __restrict__ out_h, uint4* __restrict__ out_l, size_t n8,
+                                int C) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const int c = static_cast<int>((i * 4) % C);
-    const float4 v = y[i];
-    const float4 sc = *reinterpret_cast<const float4*>(scale + c);
-    const float4 sh = *reinterpret_cast<const float4*>(shift + c);
-    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z),
-                           fmaf(v.w, sc.w, sh.w));
-    if (res != nullptr) {
-      float4 r = res[i];
-      if (res_lo != nullptr) {
-        const float4 rl = res_lo[i];
-        r.x += rl.x; r.y += rl.y; r.z += rl.z; r.w += rl.w;
-      }
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int c = static_cast<int>((i * 8) % C);
+    const float4 y0 = y[2 * i], y1 = y[2 * i + 1];
+    const float4 sc0 = *reinterpret_cast<const float4*>(scale + c);
+    const float4 sc1 = *reinterpret_cast<const float4*>(scale + c + 4);
+    const float4 sh0 = *reinterpret_cast<const float4*>(shift + c);
+    const float4 sh1 = *reinterpret_cast<const float4*>(shift + c + 4);
+    float o[8] = {fmaf(y0.x, sc0.x, sh0.x), fmaf(y0.y, sc0.y, sh0.y), fmaf(y0.z, sc0.z, sh0.z),
+                  fmaf(y0.w, sc0.w, sh0.w), fmaf(y1.x, sc1.x, sh1.x), fmaf(y1.y, sc1.y, sh1.y),
+                  fmaf(y1.z, sc1.z, sh1.z), fmaf(y1.w, sc1.w, sh1.w)};
+    if (res32 != nullptr) {
+      const float4 r0 = res32[2 * i], r1 = res32[2 * i + 1];
+      float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
       if (res_scale != nullptr) {
-        const float4 rs = *reinterpret_cast<const float4*>(res_scale + c);
-        const float4 rh = *reinterpret_cast<const float4*>(res_shift + c);
-        r = make_float4(fmaf(r.x, rs.x, rh.x), fmaf(r.y, rs.y, rh.y), fmaf(r.z, rs.z, rh.z),
-                        fmaf(r.w, rs.w, rh.w));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(r[k], res_scale[c + k], res_shift[c + k]);
       }
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += r[k];
+    }
+    if (res_h != nullptr) {
+      const uint4 rh = res_h[i], rl = res_l[i];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+      const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(h2[k]), b = __half22float2(l2[k]);
+        o[2 * k] += a.x + b.x;
+        o[2 * k + 1] += a.y + b.y;
+      }
     }
     if (RELU) {
-      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
     }
-    if (OUT_MODE == 2) {
-      const float4 h = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
-      out[i] = h;
-      out_lo[i] = make_float4(tf32_rn(o.x - h.x), tf32_rn(o.y - h.y), tf32_rn(o.z - h.z),
-                              tf32_rn(o.w - h.w));
-    } else {
-      if (OUT_MODE == 1) {
-        o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+    if (out_h != nullptr) {
+      uint4 ph, pl;
+      __half2* h2 = reinterpret_cast<__half2*>(&ph);
+      __half2* l2 = reinterpret_cast<__half2*>(&pl);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_f16(o[2 * k], o[2 * k + 1], h2[k], l2[k]);
+      out_h[i] = ph;
+      out_l[i] = pl;
+    }
+    if (out32 != nullptr) {
+      if (ROUND) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = tf32_rn(o[k]);
       }
-      out[i] = o;
+      out32[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+      out32[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
 }
 
-int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                    const float* res_lo, const float* res_scale, const float* res_shift,
-                    float* out, float* out_lo, long long rows, int C, int relu, int round_tf32,
-                    cudaStream_t stream) {
-  if (C % 4 != 0) return set_error("bn_apply: C %% 4 != 0");
-  const size_t n4 = static_cast<size_t>(rows) * C / 4;
-  if (n4 == 0) return 0;
+int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
+                    const float* res_scale, const float* res_shift, const __half* res_h,
+                    const __half* res_l, float* out32, __half* out_h, __half* out_l,
+                    long long rows, int C, int relu, int round_tf32, cudaStream_t stream) {
+  if (C % 8 != 0) return set_error("bn_apply: C %% 8 != 0");
+  if ((out_h != nullptr) != (out_l != nullptr) || (res_h != nullptr) != (res_l != nullptr))
+    return set_error("bn_apply: FP16 pairs need both planes");
+  const size_t n8 = static_cast<size_t>(rows) * C / 8;
+  if (n8 == 0) return 0;
   const int threads = 256;
-  size_t blocks = (n4 + threads - 1) / threads;
+  size_t blocks = (n8 + threads - 1) / threads;
   const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  auto y4 = reinterpret_cast<const float4*>(y);
-  auto r4 = reinterpret_cast<const float4*>(res);
-  auto rl4 = reinterpret_cast<const float4*>(res_lo);
-  auto o4 = reinterpret_cast<float4*>(out);
-  auto ol4 = reinterpret_cast<float4*>(out_lo);
-  const int mode = out_lo != nullptr ? 2 : (round_tf32 ? 1 : 0);
-#define B2N_LAUNCH(R, T)                                                                     \
-  bn_apply_kernel<R, T><<<(unsigned)blocks, threads, 0, stream>>>(y4, scale, shift, r4, rl4, \
-                                                                 res_scale, res_shift, o4, ol4, n4, C)
-  if (relu) {
-    if (mode == 2) B2N_LAUNCH(true, 2);
-    else if (mode == 1) B2N_LAUNCH(true, 1);
-    else B2N_LAUNCH(true, 0);
-  } else {
-    if (mode == 2) B2N_LAUNCH(false, 2);
-    else if (mode == 1) B2N_LAUNCH(false, 1);
-    else B2N_LAUNCH(false, 0);
-  }
+#define B2N_LAUNCH(R, T)                                                                        \
+  bn_apply_kernel<R, T><<<(unsigned)blocks, threads, 0, stream>>>(                              \
+      reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<const float4*>(res32), \
+      res_scale, res_shift, reinterpret_cast<const uint4*>(res_h),                              \
+      reinterpret_cast<const uint4*>(res_l), reinterpret_cast<float4*>(out32),                  \
+      reinterpret_cast<uint4*>(out_h), reinterpret_cast<uint4*>(out_l), n8, C)
+  if (relu && round_tf32) B2N_LAUNCH(true, true);
+  else if (relu) B2N_LAUNCH(true, false);
+  else if (round_tf32) B2N_LAUNCH(false, true);
+  else B2N_LAUNCH(false, false);
 #undef B2N_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_apply: %s", cudaGetErrorString(e));

@@ -10,17 +10,20 @@
 //     two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 //
-// SPLIT = true is the error-compensated forward mode ("3xTF32"): both operands arrive as a
-// (hi, lo) pair of TF32 tensors with hi + lo == the FP32 value to ~2^-22, and each K step
-// issues hi*hi + lo*hi + hi*lo into the same accumulator.  A single TF32 pass is only good to
-// ~1e-3 on the logits of this network (and flips ~0.3 % of the ReLU gates, which the gradients
-// then inherit); the split restores FP32-grade forward results.  Data-gradient launches
-// (SPLIT = false) multiply plain TF32 operands.
+// SPLIT = true is the error-compensated forward mode: both operands arrive as a (hi, lo) pair
+// of FP16 tensors with hi + lo == the FP32 value to ~2^-22 (hi = fp16(v), lo = fp16(v - hi)),
+// and each K step issues hi*hi + lo*hi + hi*lo (kind::f16, K = 16 per MMA) into the same FP32
+// accumulator -- FP32-grade results at 1.5x the cost of one TF32 pass and the same operand
+// bytes.  A single TF32 pass is only good to ~1e-3 on the logits of this network (and flips
+// ~0.3 % of the ReLU gates, which the gradients then inherit).  Data-gradient launches
+// (SPLIT = false) multiply plain TF32 operands held in FP32 containers.
 //
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
 // torchvision BasicBlock.forward (site-packages/torchvision/models/resnet.py:92-100).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace b2n {
@@ -35,12 +38,14 @@ struct ConvParams {
   int pad_h, pad_w;  // lower padding
   int num_m_tiles, num_n_tiles;
   int kslices;  // Cin / KELEMS
-  float* out;
-  float* out_lo;          // when set the result is stored as a (hi, lo) TF32 pair
+  float* out;             // fp32 result (null when only the FP16 pair is wanted)
+  __half* out_h;          // when set the result is (also) stored as a (hi, lo) FP16 pair
+  __half* out_l;
   const float* scale;     // per-channel multiplier (eval-mode BN fold) or null
   const float* shift;     // per-channel bias or null
-  const float* resid;     // tensor added in the epilogue or null
-  const float* resid_lo;  // low part of a split residual or null
+  const float* resid;     // fp32 tensor added in the epilogue or null
+  const __half* resid_h;  // (hi, lo) FP16 residual (identity shortcut) or null
+  const __half* resid_l;
   const float* mask;      // when set, resid is only added where mask > 0 (ReLU gate)
   int relu;
   int round_tf32;
@@ -68,8 +73,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
   using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT>;
-  constexpr int KELEMS = KBYTES / 4;
-  constexpr int MMAS_PER_STAGE = KBYTES / 32;  // tf32: K = 8 elements = 32 bytes per MMA
+  constexpr int KELEMS = KBYTES / (SPLIT ? 2 : 4);  // fp16 pairs (split) or tf32-in-fp32
+  constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
   constexpr uint32_t SBO = 8 * KBYTES;  // 8 rows of one swizzle atom
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -138,15 +143,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         const int oq = rem - op * p.Q;
         const int base_w = oq * p.stride - p.pad_w;
         const int base_h = op * p.stride - p.pad_h;
+        // (r, s, channel slice) advance as nested counters: no division per k step -- the
+        // single issuing thread's instruction latency is on the critical path.
+        int r = 0, s = 0, cs = 0, kcoord = 0;
         for (int ks = 0; ks < num_k_steps; ++ks) {
-          const int tap = ks / p.kslices;
-          const int cs = ks - tap * p.kslices;
-          const int r = tap / p.S;
-          const int s = tap - r * p.S;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          const int kcoord = tap * p.Cin + cs * KELEMS;
           tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
                              static_cast<uint16_t>(s), static_cast<uint16_t>(r));
           tma_load_2d(st + OFF_B, &map_b, &full_bar[stage], kcoord, n_tile * BLOCK_N);
@@ -156,13 +159,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          kcoord += KELEMS;
+          if (++cs == p.kslices) {
+            cs = 0;
+            if (++s == p.S) { s = 0; ++r; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc =
+          SPLIT ? make_idesc_f16(kBlockM, BLOCK_N) : make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -179,12 +188,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           for (int j = 0; j < MMAS_PER_STAGE; ++j) {
             const uint64_t da = make_smem_desc(a_addr + j * 32, 16, SBO, SWZ);
             const uint64_t db = make_smem_desc(a_addr + OFF_B + j * 32, 16, SBO, SWZ);
-            umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
             if (SPLIT) {
               const uint64_t dal = make_smem_desc(a_addr + OFF_A_LO + j * 32, 16, SBO, SWZ);
               const uint64_t dbl = make_smem_desc(a_addr + OFF_B_LO + j * 32, 16, SBO, SWZ);
-              umma_tf32(d_tmem, dal, db, idesc, 1u);
-              umma_tf32(d_tmem, da, dbl, idesc, 1u);
+              umma_f16(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, dal, db, idesc, 1u);
+              umma_f16(d_tmem, da, dbl, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
             }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -237,45 +248,70 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         if (row_ok) {
           const size_t off = static_cast<size_t>(m) * p.Cout + n0;
-          float4* dst = reinterpret_cast<float4*>(p.out + off);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) {  // 8 channels per step
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = v[8 * i + k];
             if (p.scale != nullptr) {
-              const float4 sc = *reinterpret_cast<const float4*>(p.scale + n0 + 4 * i);
-              o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
+              const float4 s0 = *reinterpret_cast<const float4*>(p.scale + n0 + 8 * i);
+              const float4 s1 = *reinterpret_cast<const float4*>(p.scale + n0 + 8 * i + 4);
+              o[0] *= s0.x; o[1] *= s0.y; o[2] *= s0.z; o[3] *= s0.w;
+              o[4] *= s1.x; o[5] *= s1.y; o[6] *= s1.z; o[7] *= s1.w;
             }
             if (p.shift != nullptr) {
-              const float4 sh = *reinterpret_cast<const float4*>(p.shift + n0 + 4 * i);
-              o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w;
+              const float4 s0 = *reinterpret_cast<const float4*>(p.shift + n0 + 8 * i);
+              const float4 s1 = *reinterpret_cast<const float4*>(p.shift + n0 + 8 * i + 4);
+              o[0] += s0.x; o[1] += s0.y; o[2] += s0.z; o[3] += s0.w;
+              o[4] += s1.x; o[5] += s1.y; o[6] += s1.z; o[7] += s1.w;
             }
             if (p.resid != nullptr) {
-              float4 rr = *reinterpret_cast<const float4*>(p.resid + off + 4 * i);
-              if (p.resid_lo != nullptr) {
-                const float4 rl = *reinterpret_cast<const float4*>(p.resid_lo + off + 4 * i);
-                rr.x += rl.x; rr.y += rl.y; rr.z += rl.z; rr.w += rl.w;
-              }
+              const float4 r0 = *reinterpret_cast<const float4*>(p.resid + off + 8 * i);
+              const float4 r1 = *reinterpret_cast<const float4*>(p.resid + off + 8 * i + 4);
+              float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
               if (p.mask != nullptr) {
-                const float4 mk = *reinterpret_cast<const float4*>(p.mask + off + 4 * i);
-                rr.x = mk.x > 0.f ? rr.x : 0.f; rr.y = mk.y > 0.f ? rr.y : 0.f;
-                rr.z = mk.z > 0.f ? rr.z : 0.f; rr.w = mk.w > 0.f ? rr.w : 0.f;
+                const float4 m0 = *reinterpret_cast<const float4*>(p.mask + off + 8 * i);
+                const float4 m1 = *reinterpret_cast<const float4*>(p.mask + off + 8 * i + 4);
+                const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rr[k] = mm[k] > 0.f ? rr[k] : 0.f;
               }
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] += rr[k];
+            }
+            if (p.resid_h != nullptr) {
+              const uint4 rh = *reinterpret_cast<const uint4*>(p.resid_h + off + 8 * i);
+              const uint4 rl = *reinterpret_cast<const uint4*>(p.resid_l + off + 8 * i);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+              const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 a = __half22float2(h2[k]), b = __half22float2(l2[k]);
+                o[2 * k] += a.x + b.x;
+                o[2 * k + 1] += a.y + b.y;
+              }
             }
             if (p.relu) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f);
-              o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
             }
-            if (p.out_lo != nullptr) {
-              const float4 h = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
-              dst[i] = h;
-              reinterpret_cast<float4*>(p.out_lo + off)[i] = make_float4(
-                  tf32_rn(o.x - h.x), tf32_rn(o.y - h.y), tf32_rn(o.z - h.z), tf32_rn(o.w - h.w));
-            } else {
+            if (p.out_h != nullptr) {
+              uint4 ph, pl;
+              __half2* h2 = reinterpret_cast<__half2*>(&ph);
+              __half2* l2 = reinterpret_cast<__half2*>(&pl);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) split_f16(o[2 * k], o[2 * k + 1], h2[k], l2[k]);
+              *reinterpret_cast<uint4*>(p.out_h + off + 8 * i) = ph;
+              *reinterpret_cast<uint4*>(p.out_l + off + 8 * i) = pl;
+            }
+            if (p.out != nullptr) {
               if (p.round_tf32) {
-                o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = tf32_rn(o[k]);
               }
-              dst[i] = o;
+              float4* dst = reinterpret_cast<float4*>(p.out + off + 8 * i);
+              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
             }
           }
         }

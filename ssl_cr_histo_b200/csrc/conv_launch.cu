@@ -42,11 +42,21 @@ static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cuda
 
 int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (a.Cout % 64 != 0) return set_error("conv: Cout=%d must be a multiple of 64", a.Cout);
-  if (a.Cin % 32 != 0) return set_error("conv: Cin=%d must be a multiple of 32", a.Cin);
-  const bool split = a.x_lo != nullptr;
-  if (split != (a.w_lo != nullptr))
-    return set_error("conv: split mode needs both x_lo and w_lo");
-  const int kbytes = 128;
+  const bool split = a.x_h != nullptr;
+  if (split) {
+    if (!a.x_l || !a.w_h || !a.w_l) return set_error("conv: split mode needs x_h, x_l, w_h, w_l");
+    if (a.Cin % 32 != 0 || (a.Cin % 64 != 0 && a.Cin != 32))
+      return set_error("conv: split mode needs Cin=32 or a multiple of 64 (got %d)", a.Cin);
+  } else {
+    if (!a.x || !a.w) return set_error("conv: null operand");
+    if (a.Cin % 32 != 0) return set_error("conv: Cin=%d must be a multiple of 32", a.Cin);
+  }
+  if ((a.out_h != nullptr) != (a.out_l != nullptr) || (a.resid_h != nullptr) != (a.resid_l != nullptr))
+    return set_error("conv: FP16 pairs need both planes");
+  if (!a.out && !a.out_h) return set_error("conv: no output tensor");
+  const int kbytes = (split && a.Cin == 32) ? 64 : 128;
+  const TmapDtype dt = split ? kF16 : kF32;
+  const int kelems = kbytes / (split ? 2 : 4);
   const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
   const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
   if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("conv: empty output");
@@ -63,23 +73,26 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.stride = a.stride; p.pad_h = a.pad_h_lo; p.pad_w = a.pad_w_lo;
   p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
   p.num_n_tiles = a.Cout / block_n;
-  p.kslices = a.Cin / (kbytes / 4);
-  p.out = a.out; p.out_lo = a.out_lo;
-  p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.resid_lo = a.resid_lo;
-  p.mask = a.mask; p.relu = a.relu; p.round_tf32 = a.round_tf32; p.stats = a.stats;
+  p.kslices = a.Cin / kelems;
+  p.out = a.out; p.out_h = a.out_h; p.out_l = a.out_l;
+  p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.resid_h = a.resid_h;
+  p.resid_l = a.resid_l; p.mask = a.mask; p.relu = a.relu; p.round_tf32 = a.round_tf32;
+  p.stats = a.stats;
 
   ConvMaps m;
   const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;
-  if (make_im2col_map(&m.a, a.x, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
-                      a.pad_w_lo, a.pad_w_hi, a.stride, kbytes / 4, kBlockM, kbytes))
+  const void* xa = split ? (const void*)a.x_h : (const void*)a.x;
+  const void* wa = split ? (const void*)a.w_h : (const void*)a.w;
+  if (make_im2col_map(&m.a, xa, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
+                      a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
     return set_error("conv: %s", tmap_last_error());
-  if (make_tiled_map_2d(&m.b, a.w, a.Cout, ktot, ktot, block_n, kbytes / 4, kbytes))
+  if (make_tiled_map_2d(&m.b, wa, dt, a.Cout, ktot, ktot, block_n, kelems, kbytes))
     return set_error("conv: %s", tmap_last_error());
   if (split) {
-    if (make_im2col_map(&m.a_lo, a.x_lo, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
-                        a.pad_w_lo, a.pad_w_hi, a.stride, kbytes / 4, kBlockM, kbytes))
+    if (make_im2col_map(&m.a_lo, a.x_l, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo,
+                        a.pad_h_hi, a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
       return set_error("conv: %s", tmap_last_error());
-    if (make_tiled_map_2d(&m.b_lo, a.w_lo, a.Cout, ktot, ktot, block_n, kbytes / 4, kbytes))
+    if (make_tiled_map_2d(&m.b_lo, a.w_l, dt, a.Cout, ktot, ktot, block_n, kelems, kbytes))
       return set_error("conv: %s", tmap_last_error());
   } else {
     m.a_lo = m.a;
@@ -90,15 +103,18 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
 
-  if (split) {
+  if (split && kbytes == 128) {
     if (block_n == 64) return launch_variant<64, 128, 4, true>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 3, true>(m, p, grid, stream);
+  } else if (split) {
+    if (block_n == 64) return launch_variant<64, 64, 8, true>(m, p, grid, stream);
   } else {
     if (block_n == 64) return launch_variant<64, 128, 6, false>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 5, false>(m, p, grid, stream);
     if (block_n == 256) return launch_variant<256, 128, 4, false>(m, p, grid, stream);
   }
-  return set_error("conv: no kernel variant for BLOCK_N=%d split=%d", block_n, (int)split);
+  return set_error("conv: no kernel variant for BLOCK_N=%d split=%d kbytes=%d", block_n,
+                   (int)split, kbytes);
 }
 
 }  // namespace b2n
@@ -153,10 +169,12 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   p.dw = a.dw;
 
   CUtensorMap mx, mdy;
-  if (make_im2col_map(&mx, a.x, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi, a.pad_w_lo,
-                      a.pad_w_hi, a.stride, 32, kWgradPX, kSwizzle128Atom32))
+  if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
+                      a.pad_w_lo, a.pad_w_hi, a.stride, 32, kWgradPX, kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
-  if (make_tiled_map_2d(&mdy, a.dy, (uint64_t)M, a.Cout, a.Cout, kWgradPX, 32, kSwizzle128Atom32))
+  // dY as one 3-D box per stage: (32 channels) x (PX pixels) x (BLOCK_N / 32 channel groups)
+  if (make_grouped_map_3d(&mdy, a.dy, (uint64_t)M, a.Cout, kWgradPX, block_n / 32,
+                          kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
 
   const int grid = out_tiles * splits;

@@ -101,35 +101,46 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x,
         int valid_boxes = (p.Ktot - m_tile * 128 + CB - 1) / CB;
         if (valid_boxes > A_BOXES) valid_boxes = A_BOXES;
         const uint32_t tx_bytes = valid_boxes * BOX_BYTES + L::B_BYTES;
+        // Per-box filter tap / channel offset are slab-invariant; the pixel coordinate is
+        // advanced incrementally -- no integer division in the per-stage loop (one elected
+        // thread issues everything, so its instruction latency is on the critical path).
+        int box_c0[A_BOXES];
+        uint16_t box_r[A_BOXES], box_s[A_BOXES];
+#pragma unroll
+        for (int b = 0; b < A_BOXES; ++b) {
+          const int row0 = m_tile * 128 + b * CB;
+          const int tap = row0 / p.Cin;
+          box_c0[b] = row0 - tap * p.Cin;
+          box_r[b] = static_cast<uint16_t>(tap / p.S);
+          box_s[b] = static_cast<uint16_t>(tap - (tap / p.S) * p.S);
+        }
         const int PQ = p.P * p.Q;
+        int m0 = slab_lo * PX;
+        int img = m0 / PQ;
+        int op = (m0 - img * PQ) / p.Q;
+        int oq = m0 - img * PQ - op * p.Q;
         int stage = 0;
         uint32_t phase = 0;
         for (int sl = slab_lo; sl < slab_hi; ++sl) {
-          const int m0 = sl * PX;
-          const int img = m0 / PQ;
-          const int rem = m0 - img * PQ;
-          const int op = rem / p.Q;
-          const int oq = rem - op * p.Q;
           const int base_w = oq * p.stride - p.pad_w;
           const int base_h = op * p.stride - p.pad_h;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          for (int b = 0; b < valid_boxes; ++b) {
-            const int row0 = m_tile * 128 + b * CB;
-            const int tap = row0 / p.Cin;
-            const int c0 = row0 - tap * p.Cin;
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            tma_load_im2col_4d(sa + b * BOX_BYTES, &map_x, &full_bar[stage], c0, base_w, base_h,
-                               img, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          }
 #pragma unroll
-          for (int b = 0; b < B_BOXES; ++b)
-            tma_load_2d(sb + b * BOX_BYTES, &map_dy, &full_bar[stage],
-                        n_tile * BLOCK_N + b * 32, m0);
+          for (int b = 0; b < A_BOXES; ++b) {
+            if (b < valid_boxes)
+              tma_load_im2col_4d(sa + b * BOX_BYTES, &map_x, &full_bar[stage], box_c0[b], base_w,
+                                 base_h, img, box_s[b], box_r[b]);
+          }
+          // all BLOCK_N / 32 channel groups of dY in one box, group-major in smem
+          tma_load_3d(sb, &map_dy, &full_bar[stage], 0, m0, n_tile * B_BOXES);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          m0 += PX;
+          oq += PX;
+          while (oq >= p.Q) { oq -= p.Q; ++op; }
+          while (op >= p.P) { op -= p.P; ++img; }
         }
       }
     } else if (warp == 1) {

@@ -1,6 +1,7 @@
 // Internal host-side launch interfaces shared by the C-ABI layer (api.cu) and the
 // stand-alone device tests (devtest.cu).  Not part of the public ABI (see include/b2n.h).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,18 +15,22 @@ int device_sm_count();
 // Forward-style convolution: out[n,p,q,:] = sum_taps x[n, p*stride - pad_lo + r, ...] * w.
 // x is NHWC fp32 [N,H,W,Cin]; w is packed K-major [Cout][R*S*Cin]; out is NHWC [N,P,Q,Cout].
 struct ConvArgs {
-  const float* x = nullptr;
-  const float* x_lo = nullptr;  // with w_lo: error-compensated (hi, lo) TF32 operands
+  const float* x = nullptr;      // plain mode: TF32 operands in fp32 containers
   const float* w = nullptr;
-  const float* w_lo = nullptr;
-  float* out = nullptr;
-  float* out_lo = nullptr;      // store the result as a (hi, lo) TF32 pair
+  const __half* x_h = nullptr;   // split mode: error-compensated (hi, lo) FP16 operand pairs
+  const __half* x_l = nullptr;
+  const __half* w_h = nullptr;
+  const __half* w_l = nullptr;
+  float* out = nullptr;          // fp32 result and / or ...
+  __half* out_h = nullptr;       // ... the result as a (hi, lo) FP16 pair
+  __half* out_l = nullptr;
   int N = 0, H = 0, W = 0, Cin = 0, Cout = 0, R = 0, S = 0, stride = 1;
   int pad_h_lo = 0, pad_h_hi = 0, pad_w_lo = 0, pad_w_hi = 0;
   const float* scale = nullptr;
   const float* shift = nullptr;
   const float* resid = nullptr;
-  const float* resid_lo = nullptr;
+  const __half* resid_h = nullptr;
+  const __half* resid_l = nullptr;
   const float* mask = nullptr;
   int relu = 0;
   int round_tf32 = 0;
@@ -54,10 +59,10 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
                        int n_updates, cudaStream_t stream);
 int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                         float* scale, float* shift, int C, float eps, cudaStream_t stream);
-int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res,
-                    const float* res_lo, const float* res_scale, const float* res_shift,
-                    float* out, float* out_lo, long long rows, int C, int relu, int round_tf32,
-                    cudaStream_t stream);
+int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
+                    const float* res_scale, const float* res_shift, const __half* res_h,
+                    const __half* res_l, float* out32, __half* out_h, __half* out_l,
+                    long long rows, int C, int relu, int round_tf32, cudaStream_t stream);
 int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
                          const float* invstd, double* sums, long long rows, int C,
                          cudaStream_t stream);
@@ -67,20 +72,21 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
                         cudaStream_t stream);
 int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                          cudaStream_t stream);
-int launch_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H, int W,
-                           cudaStream_t stream);
-int launch_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, cudaStream_t stream);
+int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32, int N, int H,
+                           int W, cudaStream_t stream);
+int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
+                            cudaStream_t stream);
 int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream);
-int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                           float* a_lo, unsigned char* idx, int N, int H, int W, int C,
-                           cudaStream_t stream);
+int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a32,
+                           __half* a_h, __half* a_l, unsigned char* idx, int N, int H, int W,
+                           int C, cudaStream_t stream);
 int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
                             const float* scale, const float* shift, float* gz, int N, int H, int W,
                             int C, cudaStream_t stream);
-int launch_avgpool_fwd(const float* a, const float* a_lo, float* e, int N, int HW, int C,
+int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, int HW, int C,
                        cudaStream_t stream);
 int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream);
-int launch_pack_fwd(const float* src, float* dst, float* dst_lo, int K, int C, int R, int S,
+int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C, int R, int S,
                     cudaStream_t stream);
 int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
                       cudaStream_t stream);

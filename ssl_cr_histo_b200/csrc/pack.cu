@@ -1,14 +1,16 @@
 // Weight re-layout kernels.  Parameters stay in PyTorch's (K,C,R,S) layout so reference
 // checkpoints load unchanged; the tensor-core kernels consume K-major
 // packs with the reduction index (tap, channel) contiguous, values rounded to TF32.
+#include <cuda_fp16.h>
+
 #include "launch.h"
 #include "ptx.cuh"
 
 namespace b2n {
 
-// forward operand:  wf[k][(r*S+s)*C + c] = w[k][c][r][s]
-__global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__ wf,
-                                float* __restrict__ wf_lo, int K, int C, int R, int S) {
+// forward operand (FP16 hi/lo pair):  wf[k][(r*S+s)*C + c] = w[k][c][r][s]
+__global__ void pack_fwd_kernel(const float* __restrict__ w, __half* __restrict__ wf_h,
+                                __half* __restrict__ wf_l, int K, int C, int R, int S) {
   const size_t total = static_cast<size_t>(K) * C * R * S;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -18,9 +20,9 @@ __global__ void pack_fwd_kernel(const float* __restrict__ w, float* __restrict__
     const int r = static_cast<int>(u % R);
     const int k = static_cast<int>(u / R);
     const float v = w[((static_cast<size_t>(k) * C + c) * R + r) * S + s];
-    const float h = tf32_rn(v);
-    wf[t] = h;
-    if (wf_lo != nullptr) wf_lo[t] = tf32_rn(v - h);  // hi + lo == v to ~2^-22
+    const __half h = __float2half_rn(v);
+    wf_h[t] = h;
+    wf_l[t] = __float2half_rn(v - __half2float(h));  // hi + lo == v to ~2^-22
   }
 }
 // data-gradient operand (flipped taps, in/out channels swapped):
@@ -67,10 +69,10 @@ static unsigned pack_grid(size_t total) {
     if (e != cudaSuccess) return set_error(#NAME ": %s", cudaGetErrorString(e));            \
     return 0;                                                                               \
   }
-int launch_pack_fwd(const float* src, float* dst, float* dst_lo, int K, int C, int R, int S,
+int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C, int R, int S,
                     cudaStream_t stream) {
   const size_t total = static_cast<size_t>(K) * C * R * S;
-  pack_fwd_kernel<<<pack_grid(total), 256, 0, stream>>>(src, dst, dst_lo, K, C, R, S);
+  pack_fwd_kernel<<<pack_grid(total), 256, 0, stream>>>(src, dst_h, dst_l, K, C, R, S);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("launch_pack_fwd: %s", cudaGetErrorString(e));
   return 0;

@@ -4,6 +4,7 @@
 // library code -- only what the implicit-GEMM conv kernels need.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -71,6 +72,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // im2col-mode load of a (channels x pixels) box.  (c, w, h, n) is the base pixel
 // (already offset by the lower bounding-box corner), (off_w, off_h) the filter tap.
 __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map,
@@ -120,6 +129,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], FP16 operands (K = 16 per instruction), FP32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -161,11 +180,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, u
          ((M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with FP16 A/B (format 0), FP32 accumulate, K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container
 __device__ __forceinline__ float tf32_rn(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// (hi, lo) FP16 pair of two fp32 values: hi = fp16(v) (saturated to the finite range),
+// lo = fp16(v - hi); hi + lo reproduces v to ~2^-22 (absolute floor 2^-25 from fp16 subnormals).
+__device__ __forceinline__ void split_f16(float a, float b, __half2& hi, __half2& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  hi = __floats2half2_rn(a, b);
+  const float2 h = __half22float2(hi);
+  lo = __floats2half2_rn(a - h.x, b - h.y);
 }
 
 }  // namespace b2n

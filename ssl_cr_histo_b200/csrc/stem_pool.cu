@@ -7,6 +7,7 @@
 //   out[p, q] = sum xs[p-2+tr, q-2+ts, :] . ws[:, tr, ts, :]      (padding 2 low / 1 high)
 // The channel count is padded to 32 so that the same 128-byte-row TMA boxes / UMMA layouts as
 // every other conv (forward and weight-gradient) apply.
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "launch.h"
@@ -16,9 +17,11 @@ namespace b2n {
 
 constexpr int kStemC = 32;
 
-// x: NCHW fp32 (N,3,H,W), H and W even.  xs: NHWC (N,H/2,W/2,32), TF32-rounded.
-__global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __restrict__ xs,
-                                       float4* __restrict__ xs_lo, int N, int H, int W) {
+// x: NCHW fp32 (N,3,H,W), H and W even.  Outputs NHWC (N,H/2,W/2,32): the (hi, lo) FP16 pair for
+// the forward conv and, when xs32 is given, the TF32-rounded fp32 copy the weight gradient reads.
+__global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __restrict__ xs_h,
+                                       uint4* __restrict__ xs_l, float4* __restrict__ xs32, int N,
+                                       int H, int W) {
   const int H2 = H >> 1, W2 = W >> 1;
   const size_t total = static_cast<size_t>(N) * H2 * W2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -27,38 +30,43 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, float4* __re
     const int j = static_cast<int>(t % W2);
     const int i = static_cast<int>((t / W2) % H2);
     const int n = static_cast<int>(t / (static_cast<size_t>(W2) * H2));
-    float v[12], l[12];
+    float v[16];
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* plane = x + (static_cast<size_t>(n) * 3 + c) * H * W;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
         const float2 p = *reinterpret_cast<const float2*>(plane + static_cast<size_t>(2 * i + dy) * W + 2 * j);
-        const int e0 = (dy * 2 + 0) * 3 + c, e1 = (dy * 2 + 1) * 3 + c;
-        v[e0] = tf32_rn(p.x); l[e0] = tf32_rn(p.x - v[e0]);
-        v[e1] = tf32_rn(p.y); l[e1] = tf32_rn(p.y - v[e1]);
+        v[(dy * 2 + 0) * 3 + c] = p.x;
+        v[(dy * 2 + 1) * 3 + c] = p.y;
       }
     }
-    float4* dst = xs + t * (kStemC / 4);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+    uint4 ph[2], pl[2];
+    __half2* h2 = reinterpret_cast<__half2*>(ph);
+    __half2* l2 = reinterpret_cast<__half2*>(pl);
 #pragma unroll
-    for (int k = 3; k < kStemC / 4; ++k) dst[k] = make_float4(0, 0, 0, 0);
-    if (xs_lo != nullptr) {
-      float4* dl = xs_lo + t * (kStemC / 4);
-      dl[0] = make_float4(l[0], l[1], l[2], l[3]);
-      dl[1] = make_float4(l[4], l[5], l[6], l[7]);
-      dl[2] = make_float4(l[8], l[9], l[10], l[11]);
+    for (int k = 0; k < 8; ++k) split_f16(v[2 * k], v[2 * k + 1], h2[k], l2[k]);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* dh = xs_h + t * (kStemC / 8);
+    uint4* dl = xs_l + t * (kStemC / 8);
+    dh[0] = ph[0]; dh[1] = ph[1]; dh[2] = z; dh[3] = z;
+    dl[0] = pl[0]; dl[1] = pl[1]; dl[2] = z; dl[3] = z;
+    if (xs32 != nullptr) {
+      float4* d = xs32 + t * (kStemC / 4);
+      d[0] = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
+      d[1] = make_float4(tf32_rn(v[4]), tf32_rn(v[5]), tf32_rn(v[6]), tf32_rn(v[7]));
+      d[2] = make_float4(tf32_rn(v[8]), tf32_rn(v[9]), tf32_rn(v[10]), tf32_rn(v[11]));
 #pragma unroll
-      for (int k = 3; k < kStemC / 4; ++k) dl[k] = make_float4(0, 0, 0, 0);
+      for (int k = 3; k < kStemC / 4; ++k) d[k] = make_float4(0, 0, 0, 0);
     }
   }
 }
 
-// w: (K,3,7,7) -> ws: [K][16 taps][32], TF32-rounded.  unpack = the transpose map for grads.
-__global__ void stem_pack_weight_kernel(const float* __restrict__ w, float* __restrict__ ws,
-                                        float* __restrict__ ws_lo, int K) {
+// w: (K,3,7,7) -> (hi, lo) FP16 pair ws: [K][16 taps][32].  unpack = the transpose map for grads.
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ ws_h,
+                                        __half* __restrict__ ws_l, int K) {
   const int total = K * 16 * kStemC;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int ch = t % kStemC;
@@ -70,9 +78,9 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, float* __re
       const int r = 2 * (tap >> 2) + dy - 1, s = 2 * (tap & 3) + dx - 1;
       if (r >= 0 && r < 7 && s >= 0 && s < 7) v = w[((k * 3 + c) * 7 + r) * 7 + s];
     }
-    const float h = tf32_rn(v);
-    ws[t] = h;
-    if (ws_lo != nullptr) ws_lo[t] = tf32_rn(v - h);
+    const __half h = __float2half_rn(v);
+    ws_h[t] = h;
+    ws_l[t] = __float2half_rn(v - __half2float(h));
   }
 }
 __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw,
@@ -85,8 +93,8 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* _
   }
 }
 
-int launch_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H, int W,
-                           cudaStream_t stream) {
+int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32, int N, int H,
+                           int W, cudaStream_t stream) {
   if ((H | W) & 1) return set_error("stem_pack_input: H and W must be even (got %dx%d)", H, W);
   const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2);
   size_t blocks = (total + 127) / 128;
@@ -94,13 +102,15 @@ int launch_stem_pack_input(const float* x, float* xs, float* xs_lo, int N, int H
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   stem_pack_input_kernel<<<(unsigned)blocks, 128, 0, stream>>>(
-      x, reinterpret_cast<float4*>(xs), reinterpret_cast<float4*>(xs_lo), N, H, W);
+      x, reinterpret_cast<uint4*>(xs_h), reinterpret_cast<uint4*>(xs_l),
+      reinterpret_cast<float4*>(xs32), N, H, W);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_pack_input: %s", cudaGetErrorString(e));
   return 0;
 }
-int launch_stem_pack_weight(const float* w, float* ws, float* ws_lo, int K, cudaStream_t stream) {
-  stem_pack_weight_kernel<<<64, 256, 0, stream>>>(w, ws, ws_lo, K);
+int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
+                            cudaStream_t stream) {
+  stem_pack_weight_kernel<<<64, 256, 0, stream>>>(w, ws_h, ws_l, K);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_pack_weight: %s", cudaGetErrorString(e));
   return 0;
@@ -116,9 +126,10 @@ int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t st
 // a[n,p,q,c] = max_{3x3 window} relu(scale*y + shift); idx = r*3+s of the first maximum
 // (same tie rule as ATen's max_pool2d, torchvision resnet.py:271).  idx may be null (eval).
 __global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
-                                       const float* __restrict__ shift, float4* __restrict__ a,
-                                       float4* __restrict__ a_lo, uchar4* __restrict__ idx, int N,
-                                       int H, int W, int P, int Q, int C4) {
+                                       const float* __restrict__ shift, float4* __restrict__ a32,
+                                       uint2* __restrict__ a_h, uint2* __restrict__ a_l,
+                                       uchar4* __restrict__ idx, int N, int H, int W, int P, int Q,
+                                       int C4) {
   const size_t total = static_cast<size_t>(N) * P * Q * C4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
@@ -148,12 +159,17 @@ __global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float
           if (z[k] > best[k]) { best[k] = z[k]; bi[k] = static_cast<unsigned char>(r * 3 + s); }
       }
     }
-    const float4 hi = make_float4(tf32_rn(best[0]), tf32_rn(best[1]), tf32_rn(best[2]),
-                                  tf32_rn(best[3]));
-    a[t] = hi;
-    if (a_lo != nullptr)
-      a_lo[t] = make_float4(tf32_rn(best[0] - hi.x), tf32_rn(best[1] - hi.y),
-                            tf32_rn(best[2] - hi.z), tf32_rn(best[3] - hi.w));
+    if (a_h != nullptr) {
+      uint2 ph, pl;
+      __half2* h2 = reinterpret_cast<__half2*>(&ph);
+      __half2* l2 = reinterpret_cast<__half2*>(&pl);
+      split_f16(best[0], best[1], h2[0], l2[0]);
+      split_f16(best[2], best[3], h2[1], l2[1]);
+      a_h[t] = ph;
+      a_l[t] = pl;
+    }
+    if (a32 != nullptr)
+      a32[t] = make_float4(tf32_rn(best[0]), tf32_rn(best[1]), tf32_rn(best[2]), tf32_rn(best[3]));
     if (idx != nullptr) idx[t] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
   }
 }
@@ -212,15 +228,16 @@ static unsigned grid_for(size_t total, int threads) {
   return static_cast<unsigned>(blocks);
 }
 
-int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a,
-                           float* a_lo, unsigned char* idx, int N, int H, int W, int C,
-                           cudaStream_t stream) {
+int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a32,
+                           __half* a_h, __half* a_l, unsigned char* idx, int N, int H, int W,
+                           int C, cudaStream_t stream) {
   if (C % 4 != 0) return set_error("bn_relu_maxpool: C %% 4 != 0");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 4);
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a),
-      reinterpret_cast<float4*>(a_lo), reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C / 4);
+      reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a32),
+      reinterpret_cast<uint2*>(a_h), reinterpret_cast<uint2*>(a_l), reinterpret_cast<uchar4*>(idx),
+      N, H, W, P, Q, C / 4);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_relu_maxpool: %s", cudaGetErrorString(e));
   return 0;
@@ -243,14 +260,14 @@ int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const flo
 
 // ------------------------------------------------------------ global avg-pool
 // a: [N][HW][C] -> e: [N][C]  (AdaptiveAvgPool2d(1) + flatten, torchvision resnet.py:278-279)
-__global__ void avgpool_fwd_kernel(const float* __restrict__ a, const float* __restrict__ a_lo,
+__global__ void avgpool_fwd_kernel(const __half* __restrict__ a_h, const __half* __restrict__ a_l,
                                    float* __restrict__ e, int HW, int C) {
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
     for (int i = 0; i < HW; ++i) {
       const size_t o = (static_cast<size_t>(n) * HW + i) * C + c;
-      acc += a_lo != nullptr ? a[o] + a_lo[o] : a[o];
+      acc += __half2float(a_h[o]) + __half2float(a_l[o]);
     }
     e[static_cast<size_t>(n) * C + c] = acc / static_cast<float>(HW);
   }
@@ -261,9 +278,9 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ ge, float* __restri
   for (int t = threadIdx.x; t < HW * C; t += blockDim.x)
     g[static_cast<size_t>(n) * HW * C + t] = ge[static_cast<size_t>(n) * C + (t % C)] * inv;
 }
-int launch_avgpool_fwd(const float* a, const float* a_lo, float* e, int N, int HW, int C,
+int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, int HW, int C,
                        cudaStream_t stream) {
-  avgpool_fwd_kernel<<<N, 256, 0, stream>>>(a, a_lo, e, HW, C);
+  avgpool_fwd_kernel<<<N, 256, 0, stream>>>(a_h, a_l, e, HW, C);
   cudaError_t er = cudaGetLastError();
   if (er != cudaSuccess) return set_error("avgpool_fwd: %s", cudaGetErrorString(er));
   return 0;

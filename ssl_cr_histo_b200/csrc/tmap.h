@@ -12,17 +12,27 @@ namespace b2n {
 // (128-byte span swizzled in 32-byte chunks -- required for MN-major TF32 operands).
 constexpr int kSwizzle128Atom32 = 129;
 
-// 2-D row-major fp32 matrix [rows][cols] (cols contiguous, row pitch = ld elements);
-// box = box_cols x box_rows.  swizzle_bytes in {0, 32, 64, 128} must equal box_cols * 4
-// (or 0 for no swizzle).
-int make_tiled_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols,
-                      uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+// element types of the mapped tensors
+enum TmapDtype { kF32 = 0, kF16 = 1 };
 
-// NHWC fp32 activation tensor viewed in im2col mode.  Bounding box of base pixels is
+// 2-D row-major matrix [rows][cols] (cols contiguous, row pitch = ld elements);
+// box = box_cols x box_rows.  box_cols * element size must equal the swizzle span.
+int make_tiled_map_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t rows,
+                      uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                      int swizzle_bytes);
+
+// Row-major fp32 matrix [rows][cols] viewed as (32-column group, row, group index) so that one
+// box fetches `box_groups` consecutive 32-column groups of `box_rows` rows, laid out in shared
+// memory group-major ([group][row][32 cols]) -- the MN-major operand layout of the wgrad kernel.
+int make_grouped_map_3d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols,
+                        uint32_t box_rows, uint32_t box_groups, int swizzle_bytes);
+
+// NHWC activation tensor viewed in im2col mode.  Bounding box of base pixels is
 // [-pad_lo, dim - 1 + pad_hi - (taps - 1)] per spatial axis; traversal stride = conv stride.
-int make_im2col_map(CUtensorMap* out, const float* base, int N, int H, int W, int C, int R, int S,
-                    int pad_h_lo, int pad_h_hi, int pad_w_lo, int pad_w_hi, int stride,
-                    uint32_t channels_per_pixel, uint32_t pixels_per_column, int swizzle_bytes);
+int make_im2col_map(CUtensorMap* out, const void* base, TmapDtype dt, int N, int H, int W, int C,
+                    int R, int S, int pad_h_lo, int pad_h_hi, int pad_w_lo, int pad_w_hi,
+                    int stride, uint32_t channels_per_pixel, uint32_t pixels_per_column,
+                    int swizzle_bytes);
 
 const char* tmap_last_error();
 

@@ -60,9 +60,9 @@ class _PackCache:
 
 
 def _pack_fwd(w):
-    """(hi, lo) TF32 pair of the forward operand [K][(r*S+s)*C + c]."""
+    """(hi, lo) FP16 pair of the forward operand [K][(r*S+s)*C + c]."""
     K, C, R, S = w.shape
-    out = torch.empty(2, K, R * S * C, device=w.device, dtype=torch.float32)
+    out = torch.empty(2, K, R * S * C, device=w.device, dtype=torch.float16)
     call("b2n_pack_weight_fwd", w, out[0], out[1], K, C, R, S)
     return out[0], out[1]
 
@@ -75,7 +75,7 @@ def _pack_dgrad(w):
 
 
 def _pack_stem(w):
-    out = torch.empty(2, w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float32)
+    out = torch.empty(2, w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float16)
     call("b2n_stem_pack_weight", w, out[0], out[1], w.shape[0])
     return out[0], out[1]
 
@@ -157,35 +157,37 @@ def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs
 
 
 class _Act:
-    """An activation tensor as an error-compensated (hi, lo) pair of TF32 planes:
-    hi = tf32(a), lo = tf32(a - hi).  Forward convs consume both planes (3xTF32); the backward
-    pass (TF32) and the ReLU gates only ever need ``hi``, so ``lo`` is dropped after use."""
-    __slots__ = ("hi", "lo")
+    """A forward activation: the error-compensated (hi, lo) FP16 pair the next forward conv
+    multiplies (hi = fp16(a), lo = fp16(a - hi)) and, only when the backward pass will need it,
+    the TF32-rounded fp32 copy ``f32`` (wgrad operand and ReLU mask)."""
+    __slots__ = ("hi", "lo", "f32")
 
-    def __init__(self, shape, dev, with_lo=True):
-        self.hi = torch.empty(shape, device=dev, dtype=torch.float32)
-        self.lo = torch.empty(shape, device=dev, dtype=torch.float32) if with_lo else None
+    def __init__(self, shape, dev, with_f32):
+        self.hi = torch.empty(shape, device=dev, dtype=torch.float16)
+        self.lo = torch.empty(shape, device=dev, dtype=torch.float16)
+        self.f32 = torch.empty(shape, device=dev, dtype=torch.float32) if with_f32 else None
 
 
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
-          resid=None, resid_lo=None, mask=None, relu=0, rnd=0, stats=None, out=None, out_lo=None,
-          alg=1.0):
-    """One conv launch.  ``x`` / ``wp`` are either plain tensors (single TF32 pass: data
-    gradients) or (hi, lo) pairs (error-compensated forward).  ``alg``: algorithmic / executed
-    FLOP ratio of this launch (the stem runs 147 real taps in a 512-wide padded reduction; a
-    zero-stuffed stride-2 data gradient executes 4x the useful MACs) -- only used for the
-    roofline accounting in bench.py."""
-    x_hi, x_lo = (x.hi, x.lo) if isinstance(x, _Act) else (x, None)
-    w_hi, w_lo = wp if isinstance(wp, tuple) else (wp, None)
-    if (x_lo is None) != (w_lo is None):
-        w_lo = None if x_lo is None else w_lo
-        x_lo = None if w_lo is None else x_lo
+          resid=None, resid_pair=None, mask=None, relu=0, rnd=0, stats=None, out=None,
+          out_pair=None, want_out=True, alg=1.0):
+    """One conv launch.  ``x`` / ``wp`` are either an ``_Act`` and an FP16 (hi, lo) weight pair
+    (error-compensated forward) or plain fp32 tensors (single TF32 pass: data gradients).
+    ``alg``: algorithmic / executed FLOP ratio of this launch (the stem runs 147 real taps in a
+    512-wide padded reduction; a zero-stuffed stride-2 data gradient executes 4x the useful
+    MACs) -- only used for the roofline accounting in bench.py."""
     P = (H + pad_lo + pad_hi - R) // stride + 1
     Q = (W + pad_lo + pad_hi - R) // stride + 1
-    if out is None:
-        out = torch.empty(N, P, Q, Cout, device=x_hi.device, dtype=torch.float32)
-    call("b2n_conv_fwd", x_hi, x_lo, w_hi, w_lo, out, out_lo, N, H, W, Cin, Cout, R, R, stride,
-         pad_lo, pad_hi, pad_lo, pad_hi, scale, shift, resid, resid_lo, mask, relu, rnd, stats,
+    if isinstance(x, _Act):
+        x32, xh, xl, w32, (wh, wl), dev = None, x.hi, x.lo, None, wp, x.hi.device
+    else:
+        x32, xh, xl, w32, wh, wl, dev = x, None, None, wp, None, None, x.device
+    if out is None and want_out:
+        out = torch.empty(N, P, Q, Cout, device=dev, dtype=torch.float32)
+    oh, ol = (out_pair.hi, out_pair.lo) if out_pair is not None else (None, None)
+    rh, rl = (resid_pair.hi, resid_pair.lo) if resid_pair is not None else (None, None)
+    call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, R, stride,
+         pad_lo, pad_hi, pad_lo, pad_hi, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
          work=2.0 * N * P * Q * Cout * R * R * Cin * alg)
     return out
 
@@ -226,26 +228,27 @@ class _TrunkFn(torch.autograd.Function):
 
         # ---- stem: s2d pack -> 4x4 tensor-core conv -> BN+ReLU+maxpool
         H2, W2 = H // 2, W // 2
-        xs = _Act((N, H2, W2, STEM_C), dev)
-        call("b2n_stem_pack_input", x, xs.hi, xs.lo, N, H, W)
+        xs = _Act((N, H2, W2, STEM_C), dev, save)
+        call("b2n_stem_pack_input", x, xs.hi, xs.lo, xs.f32, N, H, W)
         ws = packs.get("stem", trunk.conv1.weight, _pack_stem)
         s0, stats0 = next_bn(trunk.bn1)
         PH, PW = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
-        a = _Act((N, PH, PW, 64), dev)
+        a = _Act((N, PH, PW, 64), dev, save)
         if training:
             y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg)
             bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0)
             idx = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.uint8) if save else None
-            call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a.hi, a.lo, idx, N, H2, W2, 64)
+            call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a.f32, a.hi, a.lo, idx, N, H2, W2,
+                 64)
             if save:
-                saved.update(xs=xs.hi, y0=y0, bn0=bn0, idx=idx)
+                saved.update(xs=xs.f32, y0=y0, bn0=bn0, idx=idx)
         else:
             bn0 = _bn_affine(trunk.bn1, False, None, 0, 0, bufs, s0)
             z0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, scale=bn0.scale, shift=bn0.shift,
                        relu=1, alg=stem_alg)
             ones = torch.ones(64, device=dev)
             zeros = torch.zeros(64, device=dev)
-            call("b2n_bn_relu_maxpool", z0, ones, zeros, a.hi, a.lo, None, N, H2, W2, 64)
+            call("b2n_bn_relu_maxpool", z0, ones, zeros, None, a.hi, a.lo, None, N, H2, W2, 64)
         h, w = PH, PW
 
         # ---- eight basic blocks
@@ -255,46 +258,46 @@ class _TrunkFn(torch.autograd.Function):
             w1 = packs.get("b%d.w1" % bi, blk.conv1.weight, _pack_fwd)
             w2 = packs.get("b%d.w2" % bi, blk.conv2.weight, _pack_fwd)
             rows = N * ph * pw
-            rec = {"a_in": a.hi, "h": h, "w": w, "ph": ph, "pw": pw}
+            rec = {"a_in": a.f32, "h": h, "w": w, "ph": ph, "pw": pw}
             s1, st1 = next_bn(blk.bn1)
             s2, st2 = next_bn(blk.bn2)
             if blk.downsample is not None:
                 wd = packs.get("b%d.wd" % bi, blk.downsample[0].weight, _pack_fwd)
                 sd, std = next_bn(blk.downsample[1])
-            a1 = _Act((N, ph, pw, cout), dev)
-            a_out = _Act((N, ph, pw, cout), dev)
+            a1 = _Act((N, ph, pw, cout), dev, save)
+            a_out = _Act((N, ph, pw, cout), dev, save)
             if training:
                 y1 = _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, stats=st1)
                 b1 = _bn_affine(blk.bn1, True, st1, rows, n_updates, bufs, s1)
-                call("b2n_bn_apply", y1, b1.scale, b1.shift, None, None, None, None, a1.hi, a1.lo,
-                     rows, cout, 1, 0)
+                call("b2n_bn_apply", y1, b1.scale, b1.shift, None, None, None, None, None, a1.f32,
+                     a1.hi, a1.lo, rows, cout, 1, 1)
                 y2 = _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, stats=st2)
                 b2 = _bn_affine(blk.bn2, True, st2, rows, n_updates, bufs, s2)
                 if blk.downsample is not None:
                     yd = _conv(a, wd, N, h, w, cin, cout, 1, s, 0, 0, stats=std)
                     bd = _bn_affine(blk.downsample[1], True, std, rows, n_updates, bufs, sd)
-                    call("b2n_bn_apply", y2, b2.scale, b2.shift, yd, None, bd.scale, bd.shift,
-                         a_out.hi, a_out.lo, rows, cout, 1, 0)
+                    call("b2n_bn_apply", y2, b2.scale, b2.shift, yd, bd.scale, bd.shift, None, None,
+                         a_out.f32, a_out.hi, a_out.lo, rows, cout, 1, 1)
                     rec.update(yd=yd, bd=bd)
                 else:
-                    call("b2n_bn_apply", y2, b2.scale, b2.shift, a.hi, a.lo, None, None, a_out.hi,
-                         a_out.lo, rows, cout, 1, 0)
-                rec.update(y1=y1, a1=a1.hi, y2=y2, a_out=a_out.hi, b1=b1, b2=b2)
+                    call("b2n_bn_apply", y2, b2.scale, b2.shift, None, None, None, a.hi, a.lo,
+                         a_out.f32, a_out.hi, a_out.lo, rows, cout, 1, 1)
+                rec.update(y1=y1, a1=a1.f32, y2=y2, a_out=a_out.f32, b1=b1, b2=b2)
             else:
                 # eval: BN folded into the conv epilogue, no intermediate tensors
                 b1 = _bn_affine(blk.bn1, False, None, 0, 0, bufs, s1)
                 b2 = _bn_affine(blk.bn2, False, None, 0, 0, bufs, s2)
                 _conv(a, w1, N, h, w, cin, cout, 3, s, 1, 1, scale=b1.scale, shift=b1.shift, relu=1,
-                      out=a1.hi, out_lo=a1.lo)
+                      out_pair=a1, want_out=False)
                 if blk.downsample is not None:
                     bd = _bn_affine(blk.downsample[1], False, None, 0, 0, bufs, sd)
                     idn = _conv(a, wd, N, h, w, cin, cout, 1, s, 0, 0, scale=bd.scale,
                                 shift=bd.shift)
-                    idn_lo = None
+                    idn_pair = None
                 else:
-                    idn, idn_lo = a.hi, a.lo
+                    idn, idn_pair = None, a
                 _conv(a1, w2, N, ph, pw, cout, cout, 3, 1, 1, 1, scale=b2.scale, shift=b2.shift,
-                      resid=idn, resid_lo=idn_lo, relu=1, out=a_out.hi, out_lo=a_out.lo)
+                      resid=idn, resid_pair=idn_pair, relu=1, out_pair=a_out, want_out=False)
             if save:
                 saved["blocks"].append(rec)
             a, h, w = a_out, ph, pw

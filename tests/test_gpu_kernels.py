@@ -29,16 +29,20 @@ def from_nhwc(t):
 
 
 def pack_fwd(w, split=False):
+    """split: the library's (hi, lo) FP16 pack; plain: the same K-major layout in fp32 (built with
+    torch -- the values used with it are TF32-exact)."""
     K, C, R, S = w.shape
-    out = torch.empty(2, K, R * S * C, device=DEV)
-    call("b2n_pack_weight_fwd", w.to(DEV), out[0], out[1] if split else None, K, C, R, S)
-    return (out[0], out[1]) if split else out[0]
+    if not split:
+        return w.permute(0, 2, 3, 1).reshape(K, R * S * C).contiguous().to(DEV)
+    out = torch.empty(2, K, R * S * C, device=DEV, dtype=torch.float16)
+    call("b2n_pack_weight_fwd", w.to(DEV), out[0], out[1], K, C, R, S)
+    return out[0], out[1]
 
 
 def split_pair(t):
-    """(hi, lo) TF32 pair of an fp32 tensor, as the producing kernels store activations."""
-    hi = O.tf32_round(t)
-    return hi, O.tf32_round(t - hi)
+    """(hi, lo) FP16 pair of an fp32 tensor, as the producing kernels store activations."""
+    hi = t.clamp(-65504, 65504).half()
+    return hi, (t - hi.float()).half()
 
 
 def pack_dgrad(w):
@@ -49,14 +53,17 @@ def pack_dgrad(w):
 
 
 def conv(x_nhwc, wp, N, H, W, Cin, Cout, R, stride, plo, phi, **kw):
-    """x_nhwc / wp: plain tensors (one TF32 pass) or (hi, lo) pairs (error-compensated)."""
+    """x_nhwc / wp: plain fp32 tensors (one TF32 pass) or (hi, lo) FP16 pairs (compensated)."""
     P = (H + plo + phi - R) // stride + 1
     Q = (W + plo + phi - R) // stride + 1
     y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
-    x_hi, x_lo = x_nhwc if isinstance(x_nhwc, tuple) else (x_nhwc, None)
-    w_hi, w_lo = wp if isinstance(wp, tuple) else (wp, None)
-    call("b2n_conv_fwd", x_hi, x_lo, w_hi, w_lo, y, kw.get("y_lo"), N, H, W, Cin, Cout, R, R, stride,
-         plo, phi, plo, phi, kw.get("scale"), kw.get("shift"), kw.get("resid"), kw.get("resid_lo"),
+    if isinstance(x_nhwc, tuple):
+        x32, (xh, xl), w32, (wh, wl) = None, x_nhwc, None, wp
+    else:
+        x32, xh, xl, w32, wh, wl = x_nhwc, None, None, wp, None, None
+    yp, rp = kw.get("y_pair", (None, None)), kw.get("resid_pair", (None, None))
+    call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, y, yp[0], yp[1], N, H, W, Cin, Cout, R, R, stride,
+         plo, phi, plo, phi, kw.get("scale"), kw.get("shift"), kw.get("resid"), rp[0], rp[1],
          kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"))
     return y
 
@@ -87,16 +94,24 @@ def test_conv_fwd_bit_exact_with_bn_statistics(case):
     ref = F.conv2d(x, w, None, s, p)
     stats = torch.zeros(2 * Cout, device=DEV, dtype=torch.float64)
     y = conv(to_nhwc(x).to(DEV), pack_fwd(w), N, H, W, Cin, Cout, R, s, p, p, stats=stats)
-    assert torch.equal(from_nhwc(y.cpu()), ref)
+    assert torch.equal(from_nhwc(y.cpu()), ref)                          # one TF32 pass
     assert torch.allclose(stats[:Cout].cpu(), ref.double().sum((0, 2, 3)), rtol=1e-12, atol=1e-6)
     assert torch.allclose(stats[Cout:].cpu(), ref.double().pow(2).sum((0, 2, 3)), rtol=1e-6)
+    if Cin % 64 == 0:                                                    # FP16 (hi, lo) mode
+        xh, xl = split_pair(to_nhwc(x))
+        assert float(xl.abs().max()) == 0
+        stats.zero_()
+        y = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, p, p,
+                 stats=stats)
+        assert torch.equal(from_nhwc(y.cpu()), ref)
+        assert torch.allclose(stats[:Cout].cpu(), ref.double().sum((0, 2, 3)), rtol=1e-12, atol=1e-6)
 
 
 @pytest.mark.parametrize("case", [CONV_CASES[0], CONV_CASES[1], CONV_CASES[7], (2, 32, 32, 32, 64, 4, 1, None)])
 def test_conv_split_mode_is_fp32_accurate(case):
-    """3xTF32: generic fp32 operands as (hi, lo) pairs -> result within a few fp32 ulps of the
-    exact convolution, where a single TF32 pass is only good to ~5e-4; also checks the (hi, lo)
-    output path and the split residual."""
+    """Error-compensated mode: generic fp32 operands as (hi, lo) FP16 pairs -> result at the
+    tensor core's FP32-accumulation floor, where a single TF32 pass is only good to ~5e-4; also
+    checks the (hi, lo) output path and the FP16-pair residual."""
     N, H, W, Cin, Cout, R, s, p = case
     plo, phi = (p, p) if p is not None else (2, 1)            # the stem's asymmetric padding
     g = torch.Generator().manual_seed(77)
@@ -108,19 +123,20 @@ def test_conv_split_mode_is_fp32_accurate(case):
     xh, xl = split_pair(to_nhwc(x))
     y = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, plo, phi)
     err3 = float((from_nhwc(y.cpu()).double() - ref).abs().max()) / scale
-    y1 = conv(xh.to(DEV), pack_fwd(w), N, H, W, Cin, Cout, R, s, plo, phi)
+    y1 = conv(O.tf32_round(to_nhwc(x)).to(DEV), O.tf32_round(pack_fwd(w).cpu()).to(DEV), N, H, W, Cin,
+              Cout, R, s, plo, phi)
     err1 = float((from_nhwc(y1.cpu()).double() - ref).abs().max()) / scale
     assert err3 < 1e-4, err3      # floor = the tensor core's FP32 accumulation (K up to 4608)
     assert err1 > 4 * err3                                     # the compensation is what does it
     res = torch.randn(ref.shape, generator=g)
     rh, rl = split_pair(to_nhwc(res))
-    y_lo = torch.empty_like(y)
+    y_h, y_l = torch.empty_like(y, dtype=torch.half), torch.empty_like(y, dtype=torch.half)
     y2 = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, plo, phi,
-              resid=rh.to(DEV), resid_lo=rl.to(DEV), relu=1, y_lo=y_lo)
+              resid_pair=(rh.to(DEV), rl.to(DEV)), relu=1, y_pair=(y_h, y_l))
     want = torch.relu(ref + res.double())
-    got = from_nhwc((y2.double() + y_lo.double()).cpu())
+    got = from_nhwc((y_h.double() + y_l.double()).cpu())
     assert float((got - want).abs().max()) / scale < 1e-4
-    assert torch.equal(y2.cpu(), O.tf32_round(y2.cpu()))      # hi plane is TF32-representable
+    assert float((from_nhwc(y2.cpu()).double() - want).abs().max()) / scale < 1e-4   # fp32 copy
 
 
 def test_conv_epilogue_scale_shift_resid_mask_relu_round():
@@ -180,10 +196,11 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     w = ints((64, 3, 7, 7), -2, 2, 32, 0.25)
     ref = F.conv2d(x, w, None, 2, 3)
     xs = torch.empty(N, H // 2, W // 2, 32, device=DEV)
-    call("b2n_stem_pack_input", x.to(DEV), xs, None, N, H, W)
-    ws = torch.empty(64, 16 * 32, device=DEV)
-    call("b2n_stem_pack_weight", w.to(DEV), ws, None, 64)
-    y = conv(xs, ws, N, H // 2, W // 2, 32, 64, 4, 1, 2, 1)
+    xs_h, xs_l = torch.empty_like(xs, dtype=torch.half), torch.empty_like(xs, dtype=torch.half)
+    call("b2n_stem_pack_input", x.to(DEV), xs_h, xs_l, xs, N, H, W)
+    ws = torch.empty(2, 64, 16 * 32, device=DEV, dtype=torch.half)
+    call("b2n_stem_pack_weight", w.to(DEV), ws[0], ws[1], 64)
+    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1)
     assert torch.equal(from_nhwc(y.cpu()), ref)
     dy = ints(tuple(ref.shape), -1, 1, 33)
     ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=3)
@@ -224,13 +241,16 @@ def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
     call("b2n_bn_finalize", stats, gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, mean, invstd, C,
          float(rows), 0.1, 1e-5, n_updates)
     out = torch.empty(rows, C, device=DEV)
-    call("b2n_bn_apply", yd, scale, shift, res.to(DEV), None, None, None, out, None, rows, C, 1, 0)
+    call("b2n_bn_apply", yd, scale, shift, res.to(DEV), None, None, None, None, out, None, None, rows,
+         C, 1, 0)
     rh, rl = split_pair(res)
-    o_hi, o_lo = torch.empty(rows, C, device=DEV), torch.empty(rows, C, device=DEV)
-    call("b2n_bn_apply", yd, scale, shift, rh.to(DEV), rl.to(DEV), None, None, o_hi, o_lo, rows, C, 1, 0)
-    assert torch.allclose((o_hi + o_lo).cpu(), out_ref.detach(), rtol=1e-4, atol=1e-5)
-    assert torch.equal(o_hi.cpu(), O.tf32_round(o_hi.cpu()))
-    assert float((o_hi + o_lo - out).abs().max()) <= 1e-6 * float(out.abs().max())
+    o_h = torch.empty(rows, C, device=DEV, dtype=torch.half)
+    o_l, o32 = torch.empty_like(o_h), torch.empty(rows, C, device=DEV)
+    call("b2n_bn_apply", yd, scale, shift, None, None, None, rh.to(DEV), rl.to(DEV), o32, o_h, o_l,
+         rows, C, 1, 1)
+    assert torch.allclose((o_h.float() + o_l.float()).cpu(), out_ref.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.equal(o32.cpu(), O.tf32_round(o32.cpu()))                  # backward copy is TF32
+    assert float((o_h.float() + o_l.float() - out).abs().max()) <= 2e-6 * float(out.abs().max())
     assert torch.allclose(out.cpu(), out_ref.detach(), rtol=1e-4, atol=1e-5)
     assert torch.allclose(rm.cpu(), bn.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(rv.cpu(), bn.running_var, rtol=1e-5, atol=1e-6)
@@ -246,7 +266,8 @@ def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
     # eval-mode fold
     call("b2n_bn_fold_eval", gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, C, 1e-5)
     bn.eval()
-    call("b2n_bn_apply", yd, scale, shift, None, None, None, None, out, None, rows, C, 0, 0)
+    call("b2n_bn_apply", yd, scale, shift, None, None, None, None, None, out, None, None, rows, C, 0,
+         0)
     assert torch.allclose(out.cpu(), bn(y).detach(), rtol=1e-4, atol=1e-5)
 
 
@@ -266,9 +287,11 @@ def test_bn_relu_maxpool_forward_backward(shape):
     a = torch.empty(N, P, Q, C, device=DEV)
     idx = torch.empty(N, P, Q, C, device=DEV, dtype=torch.uint8)
     yd = to_nhwc(y).to(DEV)
-    a_lo = torch.empty_like(a)
-    call("b2n_bn_relu_maxpool", yd, scale.to(DEV), shift.to(DEV), a, a_lo, idx, N, H, W, C)
-    assert torch.allclose(from_nhwc((a + a_lo).cpu()), a_ref.detach(), rtol=1e-5, atol=1e-6)
+    a_h, a_l = torch.empty_like(a, dtype=torch.half), torch.empty_like(a, dtype=torch.half)
+    call("b2n_bn_relu_maxpool", yd, scale.to(DEV), shift.to(DEV), a, a_h, a_l, idx, N, H, W, C)
+    assert torch.allclose(from_nhwc((a_h.float() + a_l.float()).cpu()), a_ref.detach(), rtol=1e-5,
+                          atol=1e-6)
+    assert torch.allclose(from_nhwc(a.cpu()), a_ref.detach(), rtol=1e-3, atol=1e-6)
     assert torch.equal(a.cpu(), O.tf32_round(a.cpu()))
     gz = torch.empty(N, H, W, C, device=DEV)
     call("b2n_maxpool_relu_bwd", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), gz, N, H,
@@ -279,8 +302,6 @@ def test_bn_relu_maxpool_forward_backward(shape):
 def test_avgpool():
     a = torch.randn(5, 49, 512)
     e = torch.empty(5, 512, device=DEV)
-    call("b2n_avgpool_fwd", a.to(DEV), None, e, 5, 49, 512)
-    assert torch.allclose(e.cpu(), a.mean(1), rtol=1e-5, atol=1e-6)
     ah, al = split_pair(a)
     call("b2n_avgpool_fwd", ah.to(DEV), al.to(DEV), e, 5, 49, 512)
     assert torch.allclose(e.cpu(), a.mean(1), rtol=1e-5, atol=1e-6)
