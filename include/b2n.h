@@ -62,7 +62,9 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
                  int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad_h_lo,
                  int pad_h_hi, int pad_w_lo, int pad_w_hi, const float* scale, const float* shift,
                  const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
-                 const float* mask, int relu, int round_tf32, double* stats, void* stream);
+                 const float* mask, int relu, int round_tf32, double* stats,
+                 const int* x_l_nonzero /* optional device flag: 0 => x_l is all zero, skip it */,
+                 void* stream);
 
 /* Weight gradient, split-K over pixels, accumulated atomically:
  *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
@@ -82,8 +84,9 @@ int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
 /* x NCHW fp32 (N,3,H,W), H and W even -> NHWC (N,H/2,W/2,32) (12 real channels): the (hi, lo)
  * FP16 pair for the forward conv and (xs32, may be NULL) the TF32 fp32 copy for the wgrad. */
-int b2n_stem_pack_input(const float* x_nchw, b2n_half* xs_h, b2n_half* xs_l, float* xs32, int N,
-                        int H, int W, void* stream);
+int b2n_stem_pack_input(const float* x_nchw, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
+                        int* xs_l_nonzero /* optional, caller-zeroed: set to 1 if any lo != 0 */,
+                        int N, int H, int W, void* stream);
 /* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream);
 int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream);

@@ -40,8 +40,10 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
                  int N, int H, int W, int Cin, int Cout, int R, int Sf, int stride, int pad_h_lo,
                  int pad_h_hi, int pad_w_lo, int pad_w_hi, const float* scale, const float* shift,
                  const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
-                 const float* mask, int relu, int round_tf32, double* stats, void* stream) {
+                 const float* mask, int relu, int round_tf32, double* stats,
+                 const int* x_l_nonzero, void* stream) {
   ConvArgs a;
+  a.a_lo_nonzero = x_l_nonzero;
   a.x = x; a.w = w_packed;
   a.x_h = H16(x_h); a.x_l = H16(x_l); a.w_h = H16(w_h); a.w_l = H16(w_l);
   a.out = y; a.out_h = H16(y_h); a.out_l = H16(y_l);
@@ -75,9 +77,10 @@ int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, v
   return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, S(stream)));
 }
 
-int b2n_stem_pack_input(const float* x, b2n_half* xs_h, b2n_half* xs_l, float* xs32, int N, int H,
-                        int W, void* stream) {
-  return counted(launch_stem_pack_input(x, H16(xs_h), H16(xs_l), xs32, N, H, W, S(stream)));
+int b2n_stem_pack_input(const float* x, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
+                        int* xs_l_nonzero, int N, int H, int W, void* stream) {
+  return counted(launch_stem_pack_input(x, H16(xs_h), H16(xs_l), xs32, xs_l_nonzero, N, H, W,
+                                        S(stream)));
 }
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream) {
   return counted(launch_stem_pack_weight(w, H16(ws_h), H16(ws_l), K, S(stream)));

@@ -18,6 +18,11 @@
 // ~0.3 % of the ReLU gates, which the gradients then inherit).  Data-gradient launches
 // (SPLIT = false) multiply plain TF32 operands held in FP32 containers.
 //
+// RES_B = true keeps the whole packed weight matrix of the launch resident in shared memory
+// (loaded once per CTA) instead of streaming a weight slab with every K step -- possible when
+// it fits next to the activation ring (Cout = 64 layers and the stem), where it removes a third
+// to two thirds of the L2->SM traffic that bounds this kernel.
+//
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
 // torchvision BasicBlock.forward (site-packages/torchvision/models/resnet.py:92-100).
@@ -50,55 +55,67 @@ struct ConvParams {
   int relu;
   int round_tf32;
   double* stats;  // [2][Cout] per-channel sum / sum of squares of the raw accumulator, or null
+  int a_tiled2d;            // experiment: A is a plain [M][Cin] matrix loaded in tiled mode
+  const int* a_lo_nonzero;  // split mode: device flag; 0 => the activation lo plane is all zero
+                            // (integer-valued images) and its loads / MMAs are skipped
 };
 
 constexpr int kConvThreads = 192;
 constexpr int kBlockM = 128;
+constexpr int kConvCtrlBytes = 8192;  // stats accumulators + barriers + tmem pointer
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
 struct ConvSmem {
+  static constexpr int PLANES = SPLIT ? 2 : 1;
   static constexpr int A_BYTES = kBlockM * KBYTES;
   static constexpr int B_BYTES = BLOCK_N * KBYTES;
-  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + (RES_B ? 0 : B_BYTES));
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STATS_FLOATS = 2 * 512;
-  // ring | stats accumulators | barriers | tmem ptr   (+1024 slack for manual alignment)
-  static constexpr int TOTAL = RING_BYTES + STATS_FLOATS * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  // [1024-align slack] ctrl (stats | barriers | tmem ptr) | ring | resident B (RES_B only)
+  static constexpr int total(int num_k_steps) {
+    return 1024 + kConvCtrlBytes + RING_BYTES + (RES_B ? num_k_steps * PLANES * B_BYTES : 0);
+  }
 };
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT>;
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B>;
   constexpr int KELEMS = KBYTES / (SPLIT ? 2 : 4);  // fp16 pairs (split) or tf32-in-fp32
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
   constexpr uint32_t SBO = 8 * KBYTES;  // 8 rows of one swizzle atom
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  // stage layout: A_hi | B_hi | A_lo | B_lo
-  constexpr int OFF_B = L::A_BYTES;
-  constexpr int OFF_A_LO = L::A_BYTES + L::B_BYTES;
-  constexpr int OFF_B_LO = 2 * L::A_BYTES + L::B_BYTES;
+  // streamed stage layout: A_hi | A_lo | B_hi | B_lo   (B part absent when RES_B)
+  constexpr int OFF_A_LO = L::A_BYTES;
+  constexpr int OFF_B = L::PLANES * L::A_BYTES;
+  constexpr int OFF_B_LO = OFF_B + L::B_BYTES;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+  static_assert(L::STATS_FLOATS * 4 + (2 * STAGES + 5) * 8 + 16 <= kConvCtrlBytes, "ctrl region");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  float* s_stats = reinterpret_cast<float*>(smem + L::RING_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::STATS_FLOATS * 4);
+  float* s_stats = reinterpret_cast<float*>(base);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + L::STATS_FLOATS * 4);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint8_t* smem = base + kConvCtrlBytes;         // activation (+ weight) ring
+  uint8_t* resb = smem + L::RING_BYTES;          // resident weights: [plane][k step][B tile]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_k_steps = p.R * p.S * p.kslices;
+  const bool skip_a_lo = SPLIT && p.a_lo_nonzero != nullptr && *p.a_lo_nonzero == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -115,6 +132,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -129,81 +147,108 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int PQ = p.P * p.Q;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
-        const int m0 = m_tile * kBlockM;
-        const int img = m0 / PQ;
-        const int rem = m0 - img * PQ;
-        const int op = rem / p.Q;
-        const int oq = rem - op * p.Q;
-        const int base_w = oq * p.stride - p.pad_w;
-        const int base_h = op * p.stride - p.pad_h;
-        // (r, s, channel slice) advance as nested counters: no division per k step -- the
-        // single issuing thread's instruction latency is on the critical path.
-        int r = 0, s = 0, cs = 0, kcoord = 0;
-        for (int ks = 0; ks < num_k_steps; ++ks) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // (whole warp, uniform control flow, one elected lane issues -- see the MMA warp)
+    if (RES_B && elect_one()) {
+      // whole weight matrix (num_n_tiles == 1), one barrier for all of it
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(num_k_steps) * L::PLANES * L::B_BYTES);
+      for (int ks = 0; ks < num_k_steps; ++ks) {
+        tma_load_2d(resb + ks * L::B_BYTES, &map_b, bres_bar, ks * KELEMS, 0);
+        if (SPLIT)
+          tma_load_2d(resb + (num_k_steps + ks) * L::B_BYTES, &map_b_lo, bres_bar, ks * KELEMS, 0);
+      }
+    }
+    __syncwarp();
+    const uint32_t tx_bytes = L::STAGE_BYTES - (skip_a_lo ? L::A_BYTES : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int PQ = p.P * p.Q;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int m0 = m_tile * kBlockM;
+      const int img = m0 / PQ;
+      const int rem = m0 - img * PQ;
+      const int op = rem / p.Q;
+      const int oq = rem - op * p.Q;
+      const int base_w = oq * p.stride - p.pad_w;
+      const int base_h = op * p.stride - p.pad_h;
+      // (r, s, channel slice) advance as nested counters: no division per k step
+      int r = 0, s = 0, cs = 0, kcoord = 0;
+      for (int ks = 0; ks < num_k_steps; ++ks) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* st = smem + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
-                             static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          tma_load_2d(st + OFF_B, &map_b, &full_bar[stage], kcoord, n_tile * BLOCK_N);
-          if (SPLIT) {
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.a_tiled2d)
+            tma_load_2d(st, &map_a, &full_bar[stage], cs * KELEMS, m0);
+          else
+            tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
+                               static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+          if (SPLIT && !skip_a_lo)
             tma_load_im2col_4d(st + OFF_A_LO, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w,
                                base_h, img, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-            tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+          if (!RES_B) {
+            tma_load_2d(st + OFF_B, &map_b, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+            if (SPLIT)
+              tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          kcoord += KELEMS;
-          if (++cs == p.kslices) {
-            cs = 0;
-            if (++s == p.S) { s = 0; ++r; }
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        kcoord += KELEMS;
+        if (++cs == p.kslices) {
+          cs = 0;
+          if (++s == p.S) { s = 0; ++r; }
         }
       }
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc =
-          SPLIT ? make_idesc_f16(kBlockM, BLOCK_N) : make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // The whole warp runs this loop with uniform control flow and one elected lane issues: the
+    // issuing thread's own instruction stream (descriptor arithmetic between MMAs) is the
+    // critical path of a 128 x 64 tile, so everything is kept in warp-uniform values (uniform
+    // registers) and a descriptor is one 32-bit add on a precomputed template.
+    constexpr uint32_t idesc =
+        SPLIT ? make_idesc_f16(kBlockM, BLOCK_N) : make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+    const uint64_t desc0 = make_smem_desc(0, 16, SBO, SWZ);  // address field filled per MMA
+    const uint32_t ring16 = smem_u32(smem) >> 4;             // all offsets in 16-byte units
+    const uint32_t resb16 = smem_u32(resb) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (RES_B) mbar_wait(bres_bar, 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int ks = 0; ks < num_k_steps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int ks = 0; ks < num_k_steps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t b16 = RES_B ? resb16 + ks * (L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
+          const uint32_t bl16 = RES_B ? resb16 + (num_k_steps + ks) * (L::B_BYTES >> 4)
+                                      : a16 + (OFF_B_LO >> 4);
 #pragma unroll
           for (int j = 0; j < MMAS_PER_STAGE; ++j) {
-            const uint64_t da = make_smem_desc(a_addr + j * 32, 16, SBO, SWZ);
-            const uint64_t db = make_smem_desc(a_addr + OFF_B + j * 32, 16, SBO, SWZ);
+            const uint64_t da = desc0 + (a16 + 2 * j);
+            const uint64_t db = desc0 + (b16 + 2 * j);
             if (SPLIT) {
-              const uint64_t dal = make_smem_desc(a_addr + OFF_A_LO + j * 32, 16, SBO, SWZ);
-              const uint64_t dbl = make_smem_desc(a_addr + OFF_B_LO + j * 32, 16, SBO, SWZ);
               umma_f16(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, dal, db, idesc, 1u);
-              umma_f16(d_tmem, da, dbl, idesc, 1u);
+              umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
+              if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
             } else {
               umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
             }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (ks == num_k_steps - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ========================================================= epilogue

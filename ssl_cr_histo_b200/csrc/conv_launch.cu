@@ -22,19 +22,22 @@ struct ConvMaps {
   CUtensorMap a, b, a_lo, b_lo;
 };
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT>
+constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT>;
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B>;
+  const int smem = L::total(p.R * p.S * p.kslices);
+  if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (e != cudaSuccess) return set_error("conv: cudaFuncSetAttribute(%d B): %s", L::TOTAL,
-                                           cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         RES_B ? kMaxDynSmem : L::total(0));
+    if (e != cudaSuccess) return set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, kConvThreads, L::TOTAL, stream>>>(m.a, m.b, m.a_lo, m.b_lo, p);
+  kern<<<grid, kConvThreads, smem, stream>>>(m.a, m.b, m.a_lo, m.b_lo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv launch: %s", cudaGetErrorString(e));
   return 0;
@@ -78,13 +81,19 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.resid_h = a.resid_h;
   p.resid_l = a.resid_l; p.mask = a.mask; p.relu = a.relu; p.round_tf32 = a.round_tf32;
   p.stats = a.stats;
+  p.a_lo_nonzero = a.a_lo_nonzero;
+  p.a_tiled2d = a.a_tiled2d;
 
   ConvMaps m;
   const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;
   const void* xa = split ? (const void*)a.x_h : (const void*)a.x;
   const void* wa = split ? (const void*)a.w_h : (const void*)a.w;
-  if (make_im2col_map(&m.a, xa, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
-                      a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
+  if (a.a_tiled2d) {
+    if (split || a.R != 1 || a.S != 1 || a.stride != 1) return set_error("conv: a_tiled2d misuse");
+    if (make_tiled_map_2d(&m.a, xa, dt, (uint64_t)M, a.Cin, a.Cin, kBlockM, kelems, kbytes))
+      return set_error("conv: %s", tmap_last_error());
+  } else if (make_im2col_map(&m.a, xa, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
+                             a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
     return set_error("conv: %s", tmap_last_error());
   if (make_tiled_map_2d(&m.b, wa, dt, a.Cout, ktot, ktot, block_n, kelems, kbytes))
     return set_error("conv: %s", tmap_last_error());
@@ -103,15 +112,25 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
 
+  // Resident weights when the whole packed matrix fits next to the activation ring.
+  const int ksteps = a.R * a.S * p.kslices;
+  if (p.num_n_tiles == 1 && block_n == 64 && !a.no_resident_weights) {
+    if (split && kbytes == 128 && ConvSmem<64, 128, 2, true, true>::total(ksteps) <= kMaxDynSmem)
+      return launch_variant<64, 128, 2, true, true>(m, p, grid, stream);
+    if (split && kbytes == 64 && ConvSmem<64, 64, 5, true, true>::total(ksteps) <= kMaxDynSmem)
+      return launch_variant<64, 64, 5, true, true>(m, p, grid, stream);
+    if (!split && ConvSmem<64, 128, 4, false, true>::total(ksteps) <= kMaxDynSmem)
+      return launch_variant<64, 128, 4, false, true>(m, p, grid, stream);
+  }
   if (split && kbytes == 128) {
-    if (block_n == 64) return launch_variant<64, 128, 4, true>(m, p, grid, stream);
-    if (block_n == 128) return launch_variant<128, 128, 3, true>(m, p, grid, stream);
+    if (block_n == 64) return launch_variant<64, 128, 4, true, false>(m, p, grid, stream);
+    if (block_n == 128) return launch_variant<128, 128, 3, true, false>(m, p, grid, stream);
   } else if (split) {
-    if (block_n == 64) return launch_variant<64, 64, 8, true>(m, p, grid, stream);
+    if (block_n == 64) return launch_variant<64, 64, 8, true, false>(m, p, grid, stream);
   } else {
-    if (block_n == 64) return launch_variant<64, 128, 6, false>(m, p, grid, stream);
-    if (block_n == 128) return launch_variant<128, 128, 5, false>(m, p, grid, stream);
-    if (block_n == 256) return launch_variant<256, 128, 4, false>(m, p, grid, stream);
+    if (block_n == 64) return launch_variant<64, 128, 6, false, false>(m, p, grid, stream);
+    if (block_n == 128) return launch_variant<128, 128, 5, false, false>(m, p, grid, stream);
+    if (block_n == 256) return launch_variant<256, 128, 4, false, false>(m, p, grid, stream);
   }
   return set_error("conv: no kernel variant for BLOCK_N=%d split=%d kbytes=%d", block_n,
                    (int)split, kbytes);

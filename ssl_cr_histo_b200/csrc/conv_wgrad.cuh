@@ -144,27 +144,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x,
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < num_slabs; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
+      // whole warp, uniform control flow, one elected lane issues; descriptors are one add on
+      // a precomputed template (the issuing thread's instruction stream is the critical path)
+      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
+      // MN-major: LBO = stride between 32-channel groups (one TMA box), SBO = stride between
+      // 4-pixel groups (one swizzle atom); a K=8 step spans two atoms.
+      const uint64_t desc0 = make_smem_desc(0, BOX_BYTES, ATOM, kSwz128B32);
+      const uint32_t ring16 = smem_u32(smem) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_slabs; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t b16 = a16 + (L::A_BYTES >> 4);
 #pragma unroll
-          for (int j = 0; j < PX / 8; ++j) {
-            // MN-major: LBO = stride between 32-channel groups (one TMA box), SBO = stride
-            // between 4-pixel groups (one swizzle atom); a K=8 step spans two atoms.
-            const uint64_t da = make_smem_desc(a_addr + j * 2 * ATOM, BOX_BYTES, ATOM, kSwz128B32);
-            const uint64_t db = make_smem_desc(b_addr + j * 2 * ATOM, BOX_BYTES, ATOM, kSwz128B32);
-            umma_tf32(tmem_base, da, db, idesc, (it | j) != 0 ? 1u : 0u);
-          }
+          for (int j = 0; j < PX / 8; ++j)
+            umma_tf32(tmem_base, desc0 + (a16 + j * (2 * ATOM >> 4)), desc0 + (b16 + j * (2 * ATOM >> 4)),
+                      idesc, (it | j) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (it == num_slabs - 1) tc_commit(tfull_bar);
         }
-        tc_commit(tfull_bar);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     } else {
       const int quad = warp & 3;

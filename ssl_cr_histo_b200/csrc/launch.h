@@ -36,6 +36,9 @@ struct ConvArgs {
   int round_tf32 = 0;
   double* stats = nullptr;
   int force_block_n = 0;  // 0 = heuristic
+  int a_tiled2d = 0;                  // experiment: 1x1/s1 conv with A loaded in tiled mode
+  int no_resident_weights = 0;        // force the streamed-weights variant (tests)
+  const int* a_lo_nonzero = nullptr;  // split mode: device flag, 0 => x_l is all zero (skipped)
 };
 int launch_conv(const ConvArgs& a, cudaStream_t stream);
 
@@ -72,8 +75,8 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
                         cudaStream_t stream);
 int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                          cudaStream_t stream);
-int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32, int N, int H,
-                           int W, cudaStream_t stream);
+int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
+                           int* lo_nonzero, int N, int H, int W, cudaStream_t stream);
 int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
                             cudaStream_t stream);
 int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream);

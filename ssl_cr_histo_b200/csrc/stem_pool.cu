@@ -20,8 +20,8 @@ constexpr int kStemC = 32;
 // x: NCHW fp32 (N,3,H,W), H and W even.  Outputs NHWC (N,H/2,W/2,32): the (hi, lo) FP16 pair for
 // the forward conv and, when xs32 is given, the TF32-rounded fp32 copy the weight gradient reads.
 __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __restrict__ xs_h,
-                                       uint4* __restrict__ xs_l, float4* __restrict__ xs32, int N,
-                                       int H, int W) {
+                                       uint4* __restrict__ xs_l, float4* __restrict__ xs32,
+                                       int* __restrict__ lo_nonzero, int N, int H, int W) {
   const int H2 = H >> 1, W2 = W >> 1;
   const size_t total = static_cast<size_t>(N) * H2 * W2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -48,6 +48,11 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __res
     __half2* l2 = reinterpret_cast<__half2*>(pl);
 #pragma unroll
     for (int k = 0; k < 8; ++k) split_f16(v[2 * k], v[2 * k + 1], h2[k], l2[k]);
+    // integer-valued images (uint8 patches cast to float, dataset.py:65-67) are exact in fp16:
+    // tell the stem conv it may skip the all-zero lo plane
+    if (lo_nonzero != nullptr && ((pl[0].x | pl[0].y | pl[0].z | pl[0].w | pl[1].x | pl[1].y |
+                                   pl[1].z | pl[1].w) & 0x7fff7fffu) != 0)
+      atomicOr(lo_nonzero, 1);
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4* dh = xs_h + t * (kStemC / 8);
     uint4* dl = xs_l + t * (kStemC / 8);
@@ -93,8 +98,8 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* _
   }
 }
 
-int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32, int N, int H,
-                           int W, cudaStream_t stream) {
+int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
+                           int* lo_nonzero, int N, int H, int W, cudaStream_t stream) {
   if ((H | W) & 1) return set_error("stem_pack_input: H and W must be even (got %dx%d)", H, W);
   const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2);
   size_t blocks = (total + 127) / 128;
@@ -103,7 +108,7 @@ int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs
   if (blocks < 1) blocks = 1;
   stem_pack_input_kernel<<<(unsigned)blocks, 128, 0, stream>>>(
       x, reinterpret_cast<uint4*>(xs_h), reinterpret_cast<uint4*>(xs_l),
-      reinterpret_cast<float4*>(xs32), N, H, W);
+      reinterpret_cast<float4*>(xs32), lo_nonzero, N, H, W);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_pack_input: %s", cudaGetErrorString(e));
   return 0;

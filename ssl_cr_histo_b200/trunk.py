@@ -170,7 +170,7 @@ class _Act:
 
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
           resid=None, resid_pair=None, mask=None, relu=0, rnd=0, stats=None, out=None,
-          out_pair=None, want_out=True, alg=1.0):
+          out_pair=None, want_out=True, alg=1.0, lo_flag=None):
     """One conv launch.  ``x`` / ``wp`` are either an ``_Act`` and an FP16 (hi, lo) weight pair
     (error-compensated forward) or plain fp32 tensors (single TF32 pass: data gradients).
     ``alg``: algorithmic / executed FLOP ratio of this launch (the stem runs 147 real taps in a
@@ -188,7 +188,7 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
     rh, rl = (resid_pair.hi, resid_pair.lo) if resid_pair is not None else (None, None)
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, R, stride,
          pad_lo, pad_hi, pad_lo, pad_hi, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
-         work=2.0 * N * P * Q * Cout * R * R * Cin * alg)
+         lo_flag, work=2.0 * N * P * Q * Cout * R * R * Cin * alg)
     return out
 
 
@@ -229,13 +229,15 @@ class _TrunkFn(torch.autograd.Function):
         # ---- stem: s2d pack -> 4x4 tensor-core conv -> BN+ReLU+maxpool
         H2, W2 = H // 2, W // 2
         xs = _Act((N, H2, W2, STEM_C), dev, save)
-        call("b2n_stem_pack_input", x, xs.hi, xs.lo, xs.f32, N, H, W)
+        lo_flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        call("b2n_stem_pack_input", x, xs.hi, xs.lo, xs.f32, lo_flag, N, H, W)
         ws = packs.get("stem", trunk.conv1.weight, _pack_stem)
         s0, stats0 = next_bn(trunk.bn1)
         PH, PW = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
         a = _Act((N, PH, PW, 64), dev, save)
         if training:
-            y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg)
+            y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg,
+                       lo_flag=lo_flag)
             bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0)
             idx = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.uint8) if save else None
             call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a.f32, a.hi, a.lo, idx, N, H2, W2,
@@ -245,7 +247,7 @@ class _TrunkFn(torch.autograd.Function):
         else:
             bn0 = _bn_affine(trunk.bn1, False, None, 0, 0, bufs, s0)
             z0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, scale=bn0.scale, shift=bn0.shift,
-                       relu=1, alg=stem_alg)
+                       relu=1, alg=stem_alg, lo_flag=lo_flag)
             ones = torch.ones(64, device=dev)
             zeros = torch.zeros(64, device=dev)
             call("b2n_bn_relu_maxpool", z0, ones, zeros, None, a.hi, a.lo, None, N, H2, W2, 64)

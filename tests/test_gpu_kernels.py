@@ -64,7 +64,7 @@ def conv(x_nhwc, wp, N, H, W, Cin, Cout, R, stride, plo, phi, **kw):
     yp, rp = kw.get("y_pair", (None, None)), kw.get("resid_pair", (None, None))
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, y, yp[0], yp[1], N, H, W, Cin, Cout, R, R, stride,
          plo, phi, plo, phi, kw.get("scale"), kw.get("shift"), kw.get("resid"), rp[0], rp[1],
-         kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"))
+         kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"), kw.get("lo_flag"))
     return y
 
 
@@ -197,11 +197,22 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     ref = F.conv2d(x, w, None, 2, 3)
     xs = torch.empty(N, H // 2, W // 2, 32, device=DEV)
     xs_h, xs_l = torch.empty_like(xs, dtype=torch.half), torch.empty_like(xs, dtype=torch.half)
-    call("b2n_stem_pack_input", x.to(DEV), xs_h, xs_l, xs, N, H, W)
+    flag = torch.zeros(1, device=DEV, dtype=torch.int32)
+    call("b2n_stem_pack_input", x.to(DEV), xs_h, xs_l, xs, flag, N, H, W)
+    assert int(flag) == 0                                     # uint8-valued input: lo plane is zero
     ws = torch.empty(2, 64, 16 * 32, device=DEV, dtype=torch.half)
     call("b2n_stem_pack_weight", w.to(DEV), ws[0], ws[1], 64)
     y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1)
     assert torch.equal(from_nhwc(y.cpu()), ref)
+    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1, lo_flag=flag)
+    assert torch.equal(from_nhwc(y.cpu()), ref)               # lo plane skipped
+    xf = x + 0.37                                             # non-integer image: flag raised
+    flag.zero_()
+    call("b2n_stem_pack_input", xf.to(DEV), xs_h, xs_l, None, flag, N, H, W)
+    assert int(flag) == 1
+    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1, lo_flag=flag)
+    ref_f = F.conv2d(xf.double(), w.double(), None, 2, 3)
+    assert float((from_nhwc(y.cpu()).double() - ref_f).abs().max()) < 1e-5 * float(ref_f.abs().max())
     dy = ints(tuple(ref.shape), -1, 1, 33)
     ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=3)
     dws = torch.zeros(64, 16 * 32, device=DEV)
