@@ -62,7 +62,7 @@ struct ConvParams {
 
 constexpr int kConvThreads = 192;
 constexpr int kBlockM = 128;
-constexpr int kConvCtrlBytes = 8192;  // stats accumulators + barriers + tmem pointer
+constexpr int kConvCtrlBytes = 17408;  // per-warp stats accumulators + barriers + tmem pointer
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
 struct ConvSmem {
@@ -71,7 +71,7 @@ struct ConvSmem {
   static constexpr int B_BYTES = BLOCK_N * KBYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + (RES_B ? 0 : B_BYTES));
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STATS_FLOATS = 2 * 512;
+  static constexpr int STATS_FLOATS = 4 * 2 * 512;  // one private [sum | sumsq] row per epilogue warp
   // [1024-align slack] ctrl (stats | barriers | tmem ptr) | ring | resident B (RES_B only)
   static constexpr int total(int num_k_steps) {
     return 1024 + kConvCtrlBytes + RING_BYTES + (RES_B ? num_k_steps * PLANES * B_BYTES : 0);
@@ -287,9 +287,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               rq[i] = kq_ + __shfl_xor_sync(0xffffffffu, sq_, off);
             }
           }
-          // lane l now owns the 32-row partial sums of column n0 + l
-          atomicAdd(&s_stats[n0 + lane], rs[0]);
-          atomicAdd(&s_stats[512 + n0 + lane], rq[0]);
+          // lane l now owns the 32-row partial sums of column n0 + l; each epilogue warp
+          // accumulates into its own smem row (no atomics, no cross-warp contention)
+          float* mine = s_stats + quad * 1024;
+          mine[n0 + lane] += rs[0];
+          mine[512 + n0 + lane] += rq[0];
         }
         if (row_ok) {
           const size_t off = static_cast<size_t>(m) * p.Cout + n0;
@@ -371,7 +373,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       // epilogue-only named barrier (warps 2..5 = 128 threads), then flush CTA partials
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = threadIdx.x - 64; c < p.Cout; c += 128) {
-        const float a = s_stats[c], b = s_stats[512 + c];
+        const float a = s_stats[c] + s_stats[1024 + c] + s_stats[2048 + c] + s_stats[3072 + c];
+        const float b = s_stats[512 + c] + s_stats[1536 + c] + s_stats[2560 + c] + s_stats[3584 + c];
         if (a != 0.f || b != 0.f) {
           atomicAdd(&p.stats[c], static_cast<double>(a));
           atomicAdd(&p.stats[p.Cout + c], static_cast<double>(b));

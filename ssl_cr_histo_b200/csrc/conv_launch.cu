@@ -66,6 +66,9 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   const long long M = 1ll * a.N * P * Q;
   if (M > 2000000000ll) return set_error("conv: too many output pixels");
   int block_n = a.Cout % 128 == 0 ? 128 : 64;
+  // 256-wide tiles halve the activation-operand smem reads per MAC (the SS-mode UMMA operand
+  // fetch, not the math, bounds these kernels) when there are enough tiles to fill the GPU
+  if (a.Cout % 256 == 0 && (M / kBlockM) * (a.Cout / 256) >= 2 * device_sm_count()) block_n = 256;
   if (a.force_block_n) block_n = a.force_block_n;
   if (a.Cout % block_n != 0) return set_error("conv: Cout %% BLOCK_N != 0");
 
@@ -125,6 +128,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (split && kbytes == 128) {
     if (block_n == 64) return launch_variant<64, 128, 4, true, false>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 3, true, false>(m, p, grid, stream);
+    if (block_n == 256) return launch_variant<256, 128, 2, true, false>(m, p, grid, stream);
   } else if (split) {
     if (block_n == 64) return launch_variant<64, 64, 8, true, false>(m, p, grid, stream);
   } else {
@@ -143,11 +147,11 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
 
 namespace b2n {
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int PX>
 static int launch_wgrad_variant(const CUtensorMap& mx, const CUtensorMap& mdy,
                                 const WgradParams& p, int grid, cudaStream_t stream) {
-  using L = WgradSmem<BLOCK_N, STAGES>;
-  auto kern = conv_wgrad_kernel<BLOCK_N, STAGES>;
+  using L = WgradSmem<BLOCK_N, STAGES, PX>;
+  auto kern = conv_wgrad_kernel<BLOCK_N, STAGES, PX>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -179,7 +183,8 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   p.Ktot = a.R * a.S * a.Cin;
   p.num_m_tiles = (p.Ktot + 127) / 128;
   p.num_n_tiles = a.Cout / block_n;
-  p.slabs_total = (int)((M + kWgradPX - 1) / kWgradPX);
+  const int px = block_n == 256 ? 32 : 64;  // pixels per stage (bigger boxes amortise TMA issue)
+  p.slabs_total = (int)((M + px - 1) / px);
   const int out_tiles = p.num_m_tiles * p.num_n_tiles;
   int splits = a.force_splits > 0 ? a.force_splits : device_sm_count() / out_tiles;
   if (splits < 1) splits = 1;
@@ -189,17 +194,17 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
 
   CUtensorMap mx, mdy;
   if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
-                      a.pad_w_lo, a.pad_w_hi, a.stride, 32, kWgradPX, kSwizzle128Atom32))
+                      a.pad_w_lo, a.pad_w_hi, a.stride, 32, px, kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
   // dY as one 3-D box per stage: (32 channels) x (PX pixels) x (BLOCK_N / 32 channel groups)
-  if (make_grouped_map_3d(&mdy, a.dy, (uint64_t)M, a.Cout, kWgradPX, block_n / 32,
+  if (make_grouped_map_3d(&mdy, a.dy, (uint64_t)M, a.Cout, px, block_n / 32,
                           kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
 
   const int grid = out_tiles * splits;
-  if (block_n == 64) return launch_wgrad_variant<64, 6>(mx, mdy, p, grid, stream);
-  if (block_n == 128) return launch_wgrad_variant<128, 5>(mx, mdy, p, grid, stream);
-  return launch_wgrad_variant<256, 4>(mx, mdy, p, grid, stream);
+  if (block_n == 64) return launch_wgrad_variant<64, 4, 64>(mx, mdy, p, grid, stream);
+  if (block_n == 128) return launch_wgrad_variant<128, 3, 64>(mx, mdy, p, grid, stream);
+  return launch_wgrad_variant<256, 4, 32>(mx, mdy, p, grid, stream);
 }
 
 }  // namespace b2n

@@ -30,23 +30,22 @@ struct WgradParams {
 };
 
 constexpr int kWgradThreads = 192;
-constexpr int kWgradPX = 32;  // pixels per pipeline stage
 
-template <int BLOCK_N, int STAGES>
+// PX = pixels per pipeline stage (multiple of 8)
+template <int BLOCK_N, int STAGES, int PX>
 struct WgradSmem {
-  static constexpr int A_BYTES = 128 * kWgradPX * 4;
-  static constexpr int B_BYTES = BLOCK_N * kWgradPX * 4;
+  static constexpr int A_BYTES = 128 * PX * 4;
+  static constexpr int B_BYTES = BLOCK_N * PX * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = RING_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int PX>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ CUtensorMap map_dy, const WgradParams p) {
-  using L = WgradSmem<BLOCK_N, STAGES>;
-  constexpr int PX = kWgradPX;
+  using L = WgradSmem<BLOCK_N, STAGES, PX>;
   constexpr int CB = 32;                         // channels per TMA box (128 B rows)
   constexpr int A_BOXES = 128 / CB;              // boxes per 128-row tile
   constexpr int BOX_BYTES = PX * 128;
