@@ -52,6 +52,10 @@ int b2n_device_ok(void);
  *           v += resid[..] (fp32; only where mask[..] > 0 if mask); v += resid_h + resid_l (FP16
  *           pair); relu; then y (fp32, TF32-rounded if round_tf32) and / or the (hi, lo) FP16 pair
  *           y_h / y_l are stored.
+ * Output placement: o_step == 0 -> dense [N,P,Q,Cout]; otherwise output pixel (i, j) of image n
+ * goes to (o_h0 + i*o_step, o_w0 + j*o_step) of an [N,o_H,o_W,Cout] tensor (resid / mask are
+ * addressed the same way; pixels outside are dropped) -- the parity classes of a stride-2 data
+ * gradient (b2n_pack_weight_dgrad_s2).
  * stats (optional, [2][Cout] doubles, caller-zeroed): += per-channel sum / sum of squares of
  * the raw accumulator -- the BatchNorm batch statistics.  Cout a multiple of 64.
  * Replaces: tv:92,96,100 (conv3x3 / downsample conv in BasicBlock.forward), tv:268 (stem, via
@@ -64,7 +68,7 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
                  const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
                  const float* mask, int relu, int round_tf32, double* stats,
                  const int* x_l_nonzero /* optional device flag: 0 => x_l is all zero, skip it */,
-                 void* stream);
+                 int o_step, int o_h0, int o_w0, int o_H, int o_W, void* stream);
 
 /* Weight gradient, split-K over pixels, accumulated atomically:
  *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
@@ -79,6 +83,10 @@ int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int
 int b2n_pack_weight_fwd(const float* w, b2n_half* w_h, b2n_half* w_l, int K, int C, int R, int S,
                         void* stream);
 int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
+/* Stride-2 3x3/pad-1 data gradient by output parity: four stride-1 tap subsets (1, 2, 2, 4 taps)
+ * over dY, packs stored back to back [C][ntaps*K] in class order (0,0), (0,1), (1,0), (1,1);
+ * 9*C*K floats. */
+int b2n_pack_weight_dgrad_s2(const float* w, float* w_packed, int K, int C, void* stream);
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, void* stream);
 
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */

@@ -19,10 +19,11 @@ P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 
 # name -> argument ctypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
-    "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P, P],
+    "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P, P] + [I] * 5,
     "b2n_conv_wgrad": [P, P, P] + [I] * 12,
     "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
+    "b2n_pack_weight_dgrad_s2": [P, P, I, I],
     "b2n_unpack_wgrad": [P, P, I, I, I, I],
     "b2n_stem_pack_input": [P, P, P, P, P, I, I, I],
     "b2n_stem_pack_weight": [P, P, P, I],

@@ -41,9 +41,11 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
                  int pad_h_hi, int pad_w_lo, int pad_w_hi, const float* scale, const float* shift,
                  const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
                  const float* mask, int relu, int round_tf32, double* stats,
-                 const int* x_l_nonzero, void* stream) {
+                 const int* x_l_nonzero, int o_step, int o_h0, int o_w0, int o_H, int o_W,
+                 void* stream) {
   ConvArgs a;
   a.a_lo_nonzero = x_l_nonzero;
+  a.o_step = o_step; a.o_h0 = o_h0; a.o_w0 = o_w0; a.o_H = o_H; a.o_W = o_W;
   a.x = x; a.w = w_packed;
   a.x_h = H16(x_h); a.x_l = H16(x_l); a.w_h = H16(w_h); a.w_l = H16(w_l);
   a.out = y; a.out_h = H16(y_h); a.out_l = H16(y_l);
@@ -72,6 +74,9 @@ int b2n_pack_weight_fwd(const float* w, b2n_half* wp_h, b2n_half* wp_l, int K, i
 }
 int b2n_pack_weight_dgrad(const float* w, float* wp, int K, int C, int R, int Sf, void* stream) {
   return counted(launch_pack_dgrad(w, wp, K, C, R, Sf, S(stream)));
+}
+int b2n_pack_weight_dgrad_s2(const float* w, float* wp, int K, int C, void* stream) {
+  return counted(launch_pack_dgrad_s2(w, wp, K, C, S(stream)));
 }
 int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, void* stream) {
   return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, S(stream)));

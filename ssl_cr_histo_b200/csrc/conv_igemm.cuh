@@ -55,6 +55,10 @@ struct ConvParams {
   int relu;
   int round_tf32;
   double* stats;  // [2][Cout] per-channel sum / sum of squares of the raw accumulator, or null
+  // Strided output placement (parity classes of a stride-2 data gradient): output pixel (i, j)
+  // of image n is stored at (o_h0 + i*o_step, o_w0 + j*o_step) of an [*, o_H, o_W, Cout]
+  // tensor; pixels falling outside are dropped.  o_step == 0 selects the dense layout.
+  int o_step, o_h0, o_w0, o_H, o_W;
   int a_tiled2d;            // experiment: A is a plain [M][Cin] matrix loaded in tiled mode
   const int* a_lo_nonzero;  // split mode: device flag; 0 => the activation lo plane is all zero
                             // (integer-valued images) and its loads / MMAs are skipped
@@ -260,7 +264,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
       const long long m = static_cast<long long>(m_tile) * kBlockM + row_in_tile;
-      const bool row_ok = m < p.M_total;
+      bool row_ok = m < p.M_total;
+      size_t row_off = static_cast<size_t>(m) * p.Cout;
+      if (p.o_step != 0 && row_ok) {
+        const int PQ = p.P * p.Q;
+        const int img = static_cast<int>(m / PQ);
+        const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
+        const int oi = rem / p.Q;
+        const int oh = p.o_h0 + oi * p.o_step;
+        const int ow = p.o_w0 + (rem - oi * p.Q) * p.o_step;
+        row_ok = oh < p.o_H && ow < p.o_W;
+        row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
@@ -294,7 +309,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           mine[512 + n0 + lane] += rq[0];
         }
         if (row_ok) {
-          const size_t off = static_cast<size_t>(m) * p.Cout + n0;
+          const size_t off = row_off + n0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {  // 8 channels per step
             float o[8];

@@ -86,6 +86,8 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.stats = a.stats;
   p.a_lo_nonzero = a.a_lo_nonzero;
   p.a_tiled2d = a.a_tiled2d;
+  p.o_step = a.o_step; p.o_h0 = a.o_h0; p.o_w0 = a.o_w0; p.o_H = a.o_H; p.o_W = a.o_W;
+  if (a.o_step != 0 && a.stats != nullptr) return set_error("conv: stats with strided output");
 
   ConvMaps m;
   const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;

@@ -36,6 +36,7 @@ struct ConvArgs {
   int round_tf32 = 0;
   double* stats = nullptr;
   int force_block_n = 0;  // 0 = heuristic
+  int o_step = 0, o_h0 = 0, o_w0 = 0, o_H = 0, o_W = 0;  // strided output placement (0 = dense)
   int a_tiled2d = 0;                  // experiment: 1x1/s1 conv with A loaded in tiled mode
   int no_resident_weights = 0;        // force the streamed-weights variant (tests)
   const int* a_lo_nonzero = nullptr;  // split mode: device flag, 0 => x_l is all zero (skipped)
@@ -93,6 +94,7 @@ int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C
                     cudaStream_t stream);
 int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
                       cudaStream_t stream);
+int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream);
 int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S,
                         cudaStream_t stream);
 int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,

@@ -40,6 +40,36 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, float* __restrict
     wd[t] = tf32_rn(w[((static_cast<size_t>(k) * C + c) * R + (R - 1 - r2)) * S + (S - 1 - s2)]);
   }
 }
+// Stride-2 3x3 (pad 1) data gradient, split by output-pixel parity (ph, pw): only the taps
+// with r = h + 1 (mod 2), s = w + 1 (mod 2) reach dx[h, w], so each class is a small stride-1
+// convolution over dY with 1, 2, 2 or 4 taps:
+//   dx[2i+ph, 2j+pw, c] = sum_{a < nr(ph), b < ns(pw), k} dY[i+a, j+b, k] * w[k][c][rr(ph,a)][ss(pw,b)]
+//   ph = 0: one tap (a = 0 -> r = 1);  ph = 1: two taps (a = 0 -> r = 2, a = 1 -> r = 0)
+// The four packs [C][(a*ns + b)*K + k] are stored back to back (9 * C * K floats in total, class
+// order (0,0), (0,1), (1,0), (1,1)).
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, float* __restrict__ wd, int K,
+                                     int C) {
+  const size_t per_tap = static_cast<size_t>(C) * K;
+  const size_t total = 9 * per_tap;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // class offsets in taps: (0,0):0 [1 tap], (0,1):1 [2], (1,0):3 [2], (1,1):5 [4]
+    const int g = static_cast<int>(t / per_tap);
+    const int cls = g < 1 ? 0 : (g < 3 ? 1 : (g < 5 ? 2 : 3));
+    const int first = cls == 0 ? 0 : (cls == 1 ? 1 : (cls == 2 ? 3 : 5));
+    const int ntap = cls == 0 ? 1 : (cls == 3 ? 4 : 2);
+    const int ph = cls >> 1, pw = cls & 1;
+    const int ns = pw ? 2 : 1;
+    const size_t u = t - first * per_tap;         // index inside the class pack [C][ntap*K]
+    const int k = static_cast<int>(u % K);
+    const int tap = static_cast<int>((u / K) % ntap);
+    const int c = static_cast<int>(u / (static_cast<size_t>(K) * ntap));
+    const int a = tap / ns, b = tap - a * ns;
+    const int r = ph ? (a == 0 ? 2 : 0) : 1;
+    const int s = pw ? (b == 0 ? 2 : 0) : 1;
+    wd[t] = tf32_rn(w[((static_cast<size_t>(k) * C + c) * 3 + r) * 3 + s]);
+  }
+}
 // weight-gradient result back to the parameter layout: dw[k][c][r][s] = dwf[k][(r*S+s)*C + c]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, float* __restrict__ dw, int K,
                                     int C, int R, int S) {
@@ -80,5 +110,13 @@ int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C
 B2N_PACK_LAUNCH(launch_pack_dgrad, pack_dgrad_kernel)
 B2N_PACK_LAUNCH(launch_unpack_wgrad, unpack_wgrad_kernel)
 #undef B2N_PACK_LAUNCH
+
+int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream) {
+  pack_dgrad_s2_kernel<<<pack_grid(static_cast<size_t>(9) * C * K), 256, 0, stream>>>(src, dst, K, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("launch_pack_dgrad_s2: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 
 }  // namespace b2n

@@ -74,6 +74,18 @@ def _pack_dgrad(w):
     return out
 
 
+def _pack_dgrad_s2(w):
+    """Four parity-class packs of a stride-2 3x3 data gradient (views of one buffer)."""
+    K, C = w.shape[0], w.shape[1]
+    buf = torch.empty(9 * C * K, device=w.device, dtype=torch.float32)
+    call("b2n_pack_weight_dgrad_s2", w, buf, K, C)
+    out, off = [], 0
+    for ntap in (1, 2, 2, 4):
+        out.append(buf[off:off + C * ntap * K].view(C, ntap * K))
+        off += C * ntap * K
+    return out
+
+
 def _pack_stem(w):
     out = torch.empty(2, w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float16)
     call("b2n_stem_pack_weight", w, out[0], out[1], w.shape[0])
@@ -170,14 +182,17 @@ class _Act:
 
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
           resid=None, resid_pair=None, mask=None, relu=0, rnd=0, stats=None, out=None,
-          out_pair=None, want_out=True, alg=1.0, lo_flag=None):
+          out_pair=None, want_out=True, alg=1.0, lo_flag=None, pad_hi_w=None, R_w=None,
+          placement=(0, 0, 0, 0, 0)):
     """One conv launch.  ``x`` / ``wp`` are either an ``_Act`` and an FP16 (hi, lo) weight pair
     (error-compensated forward) or plain fp32 tensors (single TF32 pass: data gradients).
     ``alg``: algorithmic / executed FLOP ratio of this launch (the stem runs 147 real taps in a
     512-wide padded reduction; a zero-stuffed stride-2 data gradient executes 4x the useful
     MACs) -- only used for the roofline accounting in bench.py."""
+    S = R if R_w is None else R_w                 # taps / upper padding may differ per axis
+    phw = pad_hi if pad_hi_w is None else pad_hi_w
     P = (H + pad_lo + pad_hi - R) // stride + 1
-    Q = (W + pad_lo + pad_hi - R) // stride + 1
+    Q = (W + pad_lo + phw - S) // stride + 1
     if isinstance(x, _Act):
         x32, xh, xl, w32, (wh, wl), dev = None, x.hi, x.lo, None, wp, x.hi.device
     else:
@@ -186,9 +201,9 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
         out = torch.empty(N, P, Q, Cout, device=dev, dtype=torch.float32)
     oh, ol = (out_pair.hi, out_pair.lo) if out_pair is not None else (None, None)
     rh, rl = (resid_pair.hi, resid_pair.lo) if resid_pair is not None else (None, None)
-    call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, R, stride,
-         pad_lo, pad_hi, pad_lo, pad_hi, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
-         lo_flag, work=2.0 * N * P * Q * Cout * R * R * Cin * alg)
+    call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, S, stride,
+         pad_lo, pad_hi, pad_lo, phw, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
+         lo_flag, *placement, work=2.0 * N * P * Q * Cout * R * S * Cin * alg)
     return out
 
 
@@ -387,13 +402,18 @@ class _TrunkFn(torch.autograd.Function):
                 dyd = bn_backward(g, rec["a_out"], rec["yd"], rec["bd"], dbn, rows, cout)
                 wgrad(dconv, rec["a_in"], dyd, h, w, s, 0)
                 if need_in:
-                    up = torch.empty(N, h, w, cout, device=dev, dtype=torch.float32)
-                    call("b2n_upsample_zero", dyd, up, N, ph, pw, h, w, cout)
+                    # stride-2 data gradients by output parity (no zero-stuffing): the 1x1
+                    # shortcut conv only reaches even pixels; the 3x3 conv is four small stride-1
+                    # tap subsets over dY, each writing its own quarter of g_in.
+                    g_in = torch.empty(N, h, w, cin, device=dev, dtype=torch.float32)
                     wdd = packs.get("b%d.wdd" % bi, dconv.weight, _pack_dgrad)
-                    g_in = _conv(up, wdd, N, h, w, cout, cin, 1, 1, 0, 0, alg=0.25)
-                    call("b2n_upsample_zero", dy1, up, N, ph, pw, h, w, cout)
-                    wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
-                    _conv(up, wd1, N, h, w, cout, cin, 3, 1, 1, 1, resid=g_in, out=g_in, alg=0.25)
+                    _conv(dyd, wdd, N, ph, pw, cout, cin, 1, 1, 0, 0, out=g_in,
+                          placement=(2, 0, 0, h, w))
+                    wcls = packs.get("b%d.w1s2" % bi, blk.conv1.weight, _pack_dgrad_s2)
+                    for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                        _conv(dy1, wcls[cls], N, ph, pw, cout, cin, 1 + a0, 1, 0, a0, R_w=1 + b0,
+                              pad_hi_w=b0, out=g_in, resid=g_in if cls == 0 else None,
+                              placement=(2, a0, b0, h, w))
             elif need_in:
                 wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
                 # identity shortcut: add the ReLU-gated upstream gradient in the epilogue

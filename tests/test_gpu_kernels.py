@@ -64,7 +64,8 @@ def conv(x_nhwc, wp, N, H, W, Cin, Cout, R, stride, plo, phi, **kw):
     yp, rp = kw.get("y_pair", (None, None)), kw.get("resid_pair", (None, None))
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, y, yp[0], yp[1], N, H, W, Cin, Cout, R, R, stride,
          plo, phi, plo, phi, kw.get("scale"), kw.get("shift"), kw.get("resid"), rp[0], rp[1],
-         kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"), kw.get("lo_flag"))
+         kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"), kw.get("lo_flag"),
+         0, 0, 0, 0, 0)
     return y
 
 
@@ -187,6 +188,34 @@ def test_conv_dgrad_bit_exact(case):
     pad = R - 1 - p
     dx = conv(g, pack_dgrad(w), N, gh, gh, Cout, Cin, R, 1, pad, pad)
     assert torch.equal(from_nhwc(dx.cpu()), ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 56, 56, 64, 128), (3, 7, 7, 256, 512), (2, 14, 10, 128, 256)])
+def test_conv_dgrad_stride2_parity_classes_bit_exact(shape):
+    """stride-2 3x3 data gradient as four parity-class convs + the 1x1 shortcut gradient on the
+    even pixels, accumulated in place -- exactly what the trunk's backward pass launches."""
+    N, H, W, Cin, Cout = shape
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    w3, w1 = ints((Cout, Cin, 3, 3), -2, 2, 41, 0.25), ints((Cout, Cin, 1, 1), -2, 2, 42, 0.25)
+    dy3, dy1 = ints((N, Cout, P, Q), -4, 4, 43), ints((N, Cout, P, Q), -4, 4, 44)
+    ref = (torch.nn.grad.conv2d_input((N, Cin, H, W), w3, dy3, stride=2, padding=1)
+           + torch.nn.grad.conv2d_input((N, Cin, H, W), w1, dy1, stride=2, padding=0))
+    g_in = torch.full((N, H, W, Cin), float("nan"), device=DEV)
+    buf = torch.empty(9 * Cin * Cout, device=DEV)
+    call("b2n_pack_weight_dgrad_s2", w3.to(DEV), buf, Cout, Cin)
+
+    def launch(x, wp, R, S, phi_h, phi_w, resid, place):
+        call("b2n_conv_fwd", x, None, None, wp, None, None, g_in, None, None, N, P, Q, Cout, Cin, R, S,
+             1, 0, phi_h, 0, phi_w, None, None, resid, None, None, None, 0, 0, None, None, *place)
+
+    launch(to_nhwc(dy1).to(DEV), pack_dgrad(w1), 1, 1, 0, 0, None, (2, 0, 0, H, W))
+    d3, off = to_nhwc(dy3).to(DEV), 0
+    for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        n = Cin * (1 + a0) * (1 + b0) * Cout
+        launch(d3, buf[off:off + n], 1 + a0, 1 + b0, a0, b0, g_in if cls == 0 else None,
+               (2, a0, b0, H, W))
+        off += n
+    assert torch.equal(from_nhwc(g_in.cpu()), ref)
 
 
 @pytest.mark.parametrize("size", [(2, 64, 64), (1, 224, 224), (3, 34, 46)])
