@@ -90,12 +90,14 @@ int b2n_pack_weight_dgrad_s2(const float* w, float* w_packed, int K, int C, void
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, void* stream);
 
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
-/* x NCHW fp32 (N,3,H,W), H and W even -> NHWC (N,H/2,W/2,32) (12 real channels): the (hi, lo)
- * FP16 pair for the forward conv and (xs32, may be NULL) the TF32 fp32 copy for the wgrad. */
+/* x NCHW fp32 (N,3,H,W), H and W even -> NHWC space-to-depth views (12 real channels): the
+ * (hi, lo) FP16 pair (N,H/2,W/2,16) for the forward conv and (xs32, may be NULL) the TF32 fp32
+ * copy (N,H/2,W/2,32) for the wgrad. */
 int b2n_stem_pack_input(const float* x_nchw, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
                         int* xs_l_nonzero /* optional, caller-zeroed: set to 1 if any lo != 0 */,
                         int N, int H, int W, void* stream);
-/* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16*32];  packed gradient [K][16*32] -> (K,3,7,7). */
+/* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16 taps * 16];  packed gradient [K][16 taps * 32] ->
+ * (K,3,7,7). */
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream);
 int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream);
 

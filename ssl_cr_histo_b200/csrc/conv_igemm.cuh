@@ -23,6 +23,16 @@
 // it fits next to the activation ring (Cout = 64 layers and the stem), where it removes a third
 // to two thirds of the L2->SM traffic that bounds this kernel.
 //
+// HALO = true (stride-1 "same-width" convs with resident weights: layer1's 3x3 and the 4x4
+// space-to-depth stem) shares one activation box between the S horizontal filter taps: the M tile
+// is 128 consecutive positions of the *padded-width* raster (W + S - 1 positions per image row --
+// the im2col map's bounding box spans the pad columns, so TMA zero-fills them), one
+// (128 + S - 1) pixel box is loaded per filter row r and channel slice, and tap s is the same box
+// read through a descriptor whose start address is advanced by s pixel rows.  A tile then pulls
+// R boxes instead of R*S from L2 -- the L2->SM path, not the tensor pipe, bounds the 64-channel
+// layers.  The S - 1 raster positions per image row that fall on pad columns produce garbage
+// accumulator rows which the epilogue drops.
+//
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
 // torchvision BasicBlock.forward (site-packages/torchvision/models/resnet.py:92-100).
@@ -66,29 +76,37 @@ struct ConvParams {
 
 constexpr int kConvThreads = 192;
 constexpr int kBlockM = 128;
-constexpr int kConvCtrlBytes = 17408;  // per-warp stats accumulators + barriers + tmem pointer
+constexpr int kHaloMaxS = 4;                       // widest filter row the HALO variant handles
+constexpr int kHaloRows = kBlockM + kHaloMaxS - 1;  // pixels of the largest HALO activation box
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false>
 struct ConvSmem {
   static constexpr int PLANES = SPLIT ? 2 : 1;
-  static constexpr int A_BYTES = kBlockM * KBYTES;
+  // HALO boxes hold kBlockM + S - 1 pixels; every plane stays 1024-byte aligned
+  static constexpr int A_BYTES = HALO ? (kHaloRows * KBYTES + 1023) / 1024 * 1024 : kBlockM * KBYTES;
   static constexpr int B_BYTES = BLOCK_N * KBYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + (RES_B ? 0 : B_BYTES));
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STATS_FLOATS = 4 * 2 * 512;  // one private [sum | sumsq] row per epilogue warp
-  // [1024-align slack] ctrl (stats | barriers | tmem ptr) | ring | resident B (RES_B only)
+  // one private [sum | sumsq] row per epilogue warp; resident-weight launches have one N tile
+  static constexpr int STATS_C = RES_B ? BLOCK_N : 512;
+  static constexpr int STATS_FLOATS = 4 * 2 * STATS_C;
+  static constexpr int STAGING_BYTES = 4 * 16 * 128;  // per epilogue warp: 16 rows x 32 floats
+  // stats | staging | barriers | tmem pointer, rounded up to keep the ring 1024-byte aligned
+  static constexpr int CTRL_BYTES =
+      (STATS_FLOATS * 4 + STAGING_BYTES + (2 * STAGES + 5) * 8 + 16 + 1023) / 1024 * 1024;
+  // [1024-align slack] ctrl | ring | resident B (RES_B only)
   static constexpr int total(int num_k_steps) {
-    return 1024 + kConvCtrlBytes + RING_BYTES + (RES_B ? num_k_steps * PLANES * B_BYTES : 0);
+    return 1024 + CTRL_BYTES + RING_BYTES + (RES_B ? num_k_steps * PLANES * B_BYTES : 0);
   }
 };
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B>;
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
   constexpr int KELEMS = KBYTES / (SPLIT ? 2 : 4);  // fp16 pairs (split) or tf32-in-fp32
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
@@ -100,19 +118,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   constexpr int OFF_B_LO = OFF_B + L::B_BYTES;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
-  static_assert(L::STATS_FLOATS * 4 + (2 * STAGES + 5) * 8 + 16 <= kConvCtrlBytes, "ctrl region");
+  static_assert(!HALO || RES_B, "HALO needs resident weights");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   float* s_stats = reinterpret_cast<float*>(base);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + L::STATS_FLOATS * 4);
+  float4* s_stage = reinterpret_cast<float4*>(base + L::STATS_FLOATS * 4);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + L::STATS_FLOATS * 4 + L::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* bres_bar = tempty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
-  uint8_t* smem = base + kConvCtrlBytes;         // activation (+ weight) ring
+  uint8_t* smem = base + L::CTRL_BYTES;            // activation (+ weight) ring
   uint8_t* resb = smem + L::RING_BYTES;          // resident weights: [plane][k step][B tile]
 
   const int warp = threadIdx.x >> 5;
@@ -162,9 +181,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
     __syncwarp();
-    const uint32_t tx_bytes = L::STAGE_BYTES - (skip_a_lo ? L::A_BYTES : 0);
+    const uint32_t a_tx = (HALO ? kBlockM + p.S - 1 : kBlockM) * KBYTES;  // bytes one box delivers
+    const uint32_t tx_bytes = L::PLANES * (a_tx + (RES_B ? 0 : L::B_BYTES)) - (skip_a_lo ? a_tx : 0);
     int stage = 0;
     uint32_t phase = 0;
+    if (HALO) {
+      // one (kBlockM + S - 1)-pixel box per filter row and channel slice; the tile starts at
+      // position m0 of the padded-width raster (Q + S - 1 positions per image row)
+      const int Wp = p.Q + p.S - 1;
+      const int PWp = p.P * Wp;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * kBlockM;
+        const int img = m0 / PWp;
+        const int rem = m0 - img * PWp;
+        const int op = rem / Wp;
+        const int base_w = (rem - op * Wp) - p.pad_w;
+        const int base_h = op - p.pad_h;
+        for (int r = 0; r < p.R; ++r) {
+          for (int cs = 0; cs < p.kslices; ++cs) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* st = smem + stage * L::STAGE_BYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img, 0,
+                                 static_cast<uint16_t>(r));
+              if (SPLIT && !skip_a_lo)
+                tma_load_im2col_4d(st + OFF_A_LO, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w,
+                                   base_h, img, 0, static_cast<uint16_t>(r));
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else {
     const int PQ = p.P * p.Q;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
@@ -206,6 +256,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     }
+    }
   } else if (warp == 1) {
     // ======================================================= MMA issuer
     // The whole warp runs this loop with uniform control flow and one elected lane issues: the
@@ -226,6 +277,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      if (HALO) {
+        const int nstages = p.R * p.kslices;
+        int r = 0, cs = 0;
+        for (int si = 0; si < nstages; ++si) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
+#pragma unroll
+            for (int s = 0; s < kHaloMaxS; ++s) {
+              if (s >= p.S) break;
+              // tap s = the same box, start address advanced by s pixel rows (KBYTES each).  The
+              // 128B swizzle is a function of the absolute smem address (measured: the shifted
+              // descriptor reads correctly with base_offset = 0, not with base_offset = s).
+              const int ks = (r * p.S + s) * p.kslices + cs;
+              const uint32_t b16 = resb16 + ks * (L::B_BYTES >> 4);
+              const uint32_t bl16 = resb16 + (num_k_steps + ks) * (L::B_BYTES >> 4);
+#pragma unroll
+              for (int j = 0; j < MMAS_PER_STAGE; ++j) {
+                const uint64_t da = desc0 + (a16 + (KBYTES / 16) * s + 2 * j);
+                const uint64_t db = desc0 + (b16 + 2 * j);
+                const uint32_t accum = (si | s | j) != 0 ? 1u : 0u;
+                if (SPLIT) {
+                  umma_f16(d_tmem, da, db, idesc, accum);
+                  umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
+                  if (!skip_a_lo)
+                    umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + (KBYTES / 16) * s + 2 * j), db, idesc, 1u);
+                } else {
+                  umma_tf32(d_tmem, da, db, idesc, accum);
+                }
+              }
+            }
+            tc_commit(&empty_bar[stage]);
+            if (si == nstages - 1) tc_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++cs == p.kslices) { cs = 0; ++r; }
+        }
+      } else {
       for (int ks = 0; ks < num_k_steps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -252,12 +343,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ========================================================= epilogue
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
+    float4* stg = s_stage + quad * (16 * 8);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -266,7 +359,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       const long long m = static_cast<long long>(m_tile) * kBlockM + row_in_tile;
       bool row_ok = m < p.M_total;
       size_t row_off = static_cast<size_t>(m) * p.Cout;
-      if (p.o_step != 0 && row_ok) {
+      if (HALO) {
+        // m indexes the padded-width raster: drop the S - 1 pad columns of every image row
+        const int Wp = p.Q + p.S - 1;
+        const int PWp = p.P * Wp;
+        const int img = static_cast<int>(m / PWp);
+        const int rem = static_cast<int>(m - static_cast<long long>(img) * PWp);
+        const int op = rem / Wp;
+        const int oq = rem - op * Wp;
+        row_ok = row_ok && oq < p.Q;
+        row_off = ((static_cast<size_t>(img) * p.P + op) * p.Q + oq) * p.Cout;
+      } else if (p.o_step != 0 && row_ok) {
         const int PQ = p.P * p.Q;
         const int img = static_cast<int>(m / PQ);
         const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
@@ -276,6 +379,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         row_ok = oh < p.o_H && ow < p.o_W;
         row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
       }
+      // output row start in float4 units (rows are Cout-aligned); all-ones = row not stored
+      const uint32_t my_row4 = row_ok ? static_cast<uint32_t>(row_off >> 2) : 0xFFFFFFFFu;
+      // after the transpose a lane serves row 4*i + (lane >> 3) of half-round h: slot = 4*h + i
+      uint32_t row4[8];
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl)
+        row4[sl] = __shfl_sync(0xffffffffu, my_row4, (sl >> 2) * 16 + 4 * (sl & 3) + (lane >> 3));
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
@@ -283,98 +393,139 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
         float v[32];
         tmem_ld_32x32(t_addr + ch * 32, v);
-        tmem_ld_wait();
         const int n0 = n_tile * BLOCK_N + ch * 32;
-        if (p.stats != nullptr) {
-          float rs[32], rq[32];
+        // Residual operands of the whole chunk are fetched up front: eight independent loads per
+        // lane in flight (and overlapped with the TMEM read) instead of one load -> use -> store
+        // round trip per row group -- the stores below may alias, so the compiler cannot hoist.
+        const int c4 = n0 + 4 * (lane & 7);
+        float4 pre_r[8], pre_m[8];
+        uint2 pre_h[8], pre_l[8];
+        if (p.resid != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { rs[i] = v[i]; rq[i] = v[i] * v[i]; }
+          for (int sl = 0; sl < 8; ++sl)
+            pre_r[sl] = row4[sl] != 0xFFFFFFFFu
+                            ? *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(row4[sl]) << 2) + c4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.mask != nullptr) {
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
+            for (int sl = 0; sl < 8; ++sl)
+              pre_m[sl] = row4[sl] != 0xFFFFFFFFu
+                              ? *reinterpret_cast<const float4*>(p.mask + (static_cast<size_t>(row4[sl]) << 2) + c4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (p.resid_h != nullptr) {
 #pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float ks_ = up ? rs[i + off] : rs[i];
-              const float ss_ = up ? rs[i] : rs[i + off];
-              rs[i] = ks_ + __shfl_xor_sync(0xffffffffu, ss_, off);
-              const float kq_ = up ? rq[i + off] : rq[i];
-              const float sq_ = up ? rq[i] : rq[i + off];
-              rq[i] = kq_ + __shfl_xor_sync(0xffffffffu, sq_, off);
+          for (int sl = 0; sl < 8; ++sl) {
+            const bool ok = row4[sl] != 0xFFFFFFFFu;
+            const size_t o = (static_cast<size_t>(row4[sl]) << 2) + c4;
+            pre_h[sl] = ok ? *reinterpret_cast<const uint2*>(p.resid_h + o) : make_uint2(0u, 0u);
+            pre_l[sl] = ok ? *reinterpret_cast<const uint2*>(p.resid_l + o) : make_uint2(0u, 0u);
+          }
+        }
+        tmem_ld_wait();
+        // per-channel affine while a thread still owns a whole row of the chunk
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = *reinterpret_cast<const float4*>(p.scale + n0 + 4 * i);
+            v[4 * i] *= sc.x; v[4 * i + 1] *= sc.y; v[4 * i + 2] *= sc.z; v[4 * i + 3] *= sc.w;
+          }
+        }
+        if (p.shift != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sh = *reinterpret_cast<const float4*>(p.shift + n0 + 4 * i);
+            v[4 * i] += sh.x; v[4 * i + 1] += sh.y; v[4 * i + 2] += sh.z; v[4 * i + 3] += sh.w;
+          }
+        }
+        // Transpose through the warp's staging tile (16 rows x 128 B per round, 16-byte chunks
+        // XOR-swizzled by row) so that global memory is touched row-major: 8 lanes cover the
+        // 128 contiguous bytes of one output row -- 4 lines per warp instruction instead of 32.
+        float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if ((lane >> 4) == h) {
+            const int r = lane & 15;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              stg[r * 8 + (c ^ (r & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const int c = lane & 7;
+            const float4 t = stg[r * 8 + (c ^ (r & 7))];
+            const int sl = 4 * h + i;
+            if (row4[sl] != 0xFFFFFFFFu) {
+              const size_t off = (static_cast<size_t>(row4[sl]) << 2) + c4;
+              float o[4] = {t.x, t.y, t.z, t.w};
+              if (p.stats != nullptr) {  // BN batch statistics of the raw conv output
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { st_s[k] += o[k]; st_q[k] += o[k] * o[k]; }
+              }
+              if (p.resid != nullptr) {
+                const float4 r0 = pre_r[sl];
+                float rr[4] = {r0.x, r0.y, r0.z, r0.w};
+                if (p.mask != nullptr) {
+                  const float4 m0 = pre_m[sl];
+                  rr[0] = m0.x > 0.f ? rr[0] : 0.f; rr[1] = m0.y > 0.f ? rr[1] : 0.f;
+                  rr[2] = m0.z > 0.f ? rr[2] : 0.f; rr[3] = m0.w > 0.f ? rr[3] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] += rr[k];
+              }
+              if (p.resid_h != nullptr) {
+                const uint2 rh = pre_h[sl];
+                const uint2 rl = pre_l[sl];
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+                const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  const float2 a = __half22float2(h2[k]), b = __half22float2(l2[k]);
+                  o[2 * k] += a.x + b.x;
+                  o[2 * k + 1] += a.y + b.y;
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
+              }
+              if (p.out_h != nullptr) {
+                uint2 ph, pl;
+                __half2* h2 = reinterpret_cast<__half2*>(&ph);
+                __half2* l2 = reinterpret_cast<__half2*>(&pl);
+                split_f16(o[0], o[1], h2[0], l2[0]);
+                split_f16(o[2], o[3], h2[1], l2[1]);
+                *reinterpret_cast<uint2*>(p.out_h + off) = ph;
+                *reinterpret_cast<uint2*>(p.out_l + off) = pl;
+              }
+              if (p.out != nullptr) {
+                if (p.round_tf32) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) o[k] = tf32_rn(o[k]);
+                }
+                *reinterpret_cast<float4*>(p.out + off) = make_float4(o[0], o[1], o[2], o[3]);
+              }
             }
           }
-          // lane l now owns the 32-row partial sums of column n0 + l; each epilogue warp
-          // accumulates into its own smem row (no atomics, no cross-warp contention)
-          float* mine = s_stats + quad * 1024;
-          mine[n0 + lane] += rs[0];
-          mine[512 + n0 + lane] += rq[0];
+          __syncwarp();
         }
-        if (row_ok) {
-          const size_t off = row_off + n0;
+        if (p.stats != nullptr) {
+          // lanes l, l+8, l+16, l+24 hold the same four channels (different rows); each epilogue
+          // warp accumulates into its own smem row (no atomics, no cross-warp contention)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {  // 8 channels per step
-            float o[8];
+          for (int k = 0; k < 4; ++k) {
+            st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], 8);
+            st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 8);
+            st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], 16);
+            st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 16);
+          }
+          if (lane < 8) {
+            float* mine = s_stats + quad * (2 * L::STATS_C) + n0 + 4 * lane;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = v[8 * i + k];
-            if (p.scale != nullptr) {
-              const float4 s0 = *reinterpret_cast<const float4*>(p.scale + n0 + 8 * i);
-              const float4 s1 = *reinterpret_cast<const float4*>(p.scale + n0 + 8 * i + 4);
-              o[0] *= s0.x; o[1] *= s0.y; o[2] *= s0.z; o[3] *= s0.w;
-              o[4] *= s1.x; o[5] *= s1.y; o[6] *= s1.z; o[7] *= s1.w;
-            }
-            if (p.shift != nullptr) {
-              const float4 s0 = *reinterpret_cast<const float4*>(p.shift + n0 + 8 * i);
-              const float4 s1 = *reinterpret_cast<const float4*>(p.shift + n0 + 8 * i + 4);
-              o[0] += s0.x; o[1] += s0.y; o[2] += s0.z; o[3] += s0.w;
-              o[4] += s1.x; o[5] += s1.y; o[6] += s1.z; o[7] += s1.w;
-            }
-            if (p.resid != nullptr) {
-              const float4 r0 = *reinterpret_cast<const float4*>(p.resid + off + 8 * i);
-              const float4 r1 = *reinterpret_cast<const float4*>(p.resid + off + 8 * i + 4);
-              float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-              if (p.mask != nullptr) {
-                const float4 m0 = *reinterpret_cast<const float4*>(p.mask + off + 8 * i);
-                const float4 m1 = *reinterpret_cast<const float4*>(p.mask + off + 8 * i + 4);
-                const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) rr[k] = mm[k] > 0.f ? rr[k] : 0.f;
-              }
-#pragma unroll
-              for (int k = 0; k < 8; ++k) o[k] += rr[k];
-            }
-            if (p.resid_h != nullptr) {
-              const uint4 rh = *reinterpret_cast<const uint4*>(p.resid_h + off + 8 * i);
-              const uint4 rl = *reinterpret_cast<const uint4*>(p.resid_l + off + 8 * i);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
-              const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 a = __half22float2(h2[k]), b = __half22float2(l2[k]);
-                o[2 * k] += a.x + b.x;
-                o[2 * k + 1] += a.y + b.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
-            }
-            if (p.out_h != nullptr) {
-              uint4 ph, pl;
-              __half2* h2 = reinterpret_cast<__half2*>(&ph);
-              __half2* l2 = reinterpret_cast<__half2*>(&pl);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) split_f16(o[2 * k], o[2 * k + 1], h2[k], l2[k]);
-              *reinterpret_cast<uint4*>(p.out_h + off + 8 * i) = ph;
-              *reinterpret_cast<uint4*>(p.out_l + off + 8 * i) = pl;
-            }
-            if (p.out != nullptr) {
-              if (p.round_tf32) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = tf32_rn(o[k]);
-              }
-              float4* dst = reinterpret_cast<float4*>(p.out + off + 8 * i);
-              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-            }
+            for (int k = 0; k < 4; ++k) { mine[k] += st_s[k]; mine[L::STATS_C + k] += st_q[k]; }
           }
         }
       }
@@ -388,8 +539,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       // epilogue-only named barrier (warps 2..5 = 128 threads), then flush CTA partials
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = threadIdx.x - 64; c < p.Cout; c += 128) {
-        const float a = s_stats[c] + s_stats[1024 + c] + s_stats[2048 + c] + s_stats[3072 + c];
-        const float b = s_stats[512 + c] + s_stats[1536 + c] + s_stats[2560 + c] + s_stats[3584 + c];
+        constexpr int SC = L::STATS_C;
+        const float a = s_stats[c] + s_stats[2 * SC + c] + s_stats[4 * SC + c] + s_stats[6 * SC + c];
+        const float b = s_stats[SC + c] + s_stats[3 * SC + c] + s_stats[5 * SC + c] + s_stats[7 * SC + c];
         if (a != 0.f || b != 0.f) {
           atomicAdd(&p.stats[c], static_cast<double>(a));
           atomicAdd(&p.stats[p.Cout + c], static_cast<double>(b));

@@ -1,5 +1,6 @@
 // Host launcher for the tcgen05 implicit-GEMM conv kernel (conv_igemm.cuh).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "conv_igemm.cuh"
 #include "launch.h"
@@ -24,10 +25,10 @@ struct ConvMaps {
 
 constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B>;
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
   static bool configured = false;
@@ -46,25 +47,25 @@ static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cuda
 int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (a.Cout % 64 != 0) return set_error("conv: Cout=%d must be a multiple of 64", a.Cout);
   const bool split = a.x_h != nullptr;
+  // bytes of one K row: all of Cin up to 128 B (narrow rows only exist for HALO-capable convs)
+  const int esz = split ? 2 : 4;
+  const int kbytes = a.Cin * esz >= 128 ? 128 : a.Cin * esz;
   if (split) {
     if (!a.x_l || !a.w_h || !a.w_l) return set_error("conv: split mode needs x_h, x_l, w_h, w_l");
-    if (a.Cin % 32 != 0 || (a.Cin % 64 != 0 && a.Cin != 32))
-      return set_error("conv: split mode needs Cin=32 or a multiple of 64 (got %d)", a.Cin);
   } else {
     if (!a.x || !a.w) return set_error("conv: null operand");
-    if (a.Cin % 32 != 0) return set_error("conv: Cin=%d must be a multiple of 32", a.Cin);
   }
+  if ((kbytes != 128 && kbytes != 64 && kbytes != 32) || (a.Cin * esz) % kbytes != 0)
+    return set_error("conv: unsupported Cin=%d (%d-byte elements)", a.Cin, esz);
   if ((a.out_h != nullptr) != (a.out_l != nullptr) || (a.resid_h != nullptr) != (a.resid_l != nullptr))
     return set_error("conv: FP16 pairs need both planes");
   if (!a.out && !a.out_h) return set_error("conv: no output tensor");
-  const int kbytes = (split && a.Cin == 32) ? 64 : 128;
   const TmapDtype dt = split ? kF16 : kF32;
-  const int kelems = kbytes / (split ? 2 : 4);
+  const int kelems = kbytes / esz;
   const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
   const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
   if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("conv: empty output");
   const long long M = 1ll * a.N * P * Q;
-  if (M > 2000000000ll) return set_error("conv: too many output pixels");
   int block_n = a.Cout % 128 == 0 ? 128 : 64;
   // 256-wide tiles halve the activation-operand smem reads per MAC (the SS-mode UMMA operand
   // fetch, not the math, bounds these kernels) when there are enough tiles to fill the GPU
@@ -72,12 +73,32 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (a.force_block_n) block_n = a.force_block_n;
   if (a.Cout % block_n != 0) return set_error("conv: Cout %% BLOCK_N != 0");
 
+  // Tap-sharing HALO variant (conv_igemm.cuh): stride-1 same-width convs whose whole packed
+  // weight matrix stays resident in shared memory (layer1's 3x3 convs, the 4x4 s2d stem).
+  const int ksteps_full = a.R * a.S * (a.Cin / kelems);
+  const bool halo_shape = a.stride == 1 && a.S <= kHaloMaxS && a.pad_w_lo + a.pad_w_hi == a.S - 1 &&
+                          block_n == 64 && a.Cout == 64 && a.o_step == 0 && !a.a_tiled2d &&
+                          !a.no_resident_weights && !a.no_halo && getenv("B2N_NO_HALO") == nullptr;
+  int halo = 0;  // 0 = off, else kbytes of the HALO variant
+  if (halo_shape && kbytes == 128 &&
+      (split ? ConvSmem<64, 128, 2, true, true, true>::total(ksteps_full)
+             : ConvSmem<64, 128, 4, false, true, true>::total(ksteps_full)) <= kMaxDynSmem)
+    halo = 128;
+  if (halo_shape && kbytes == 32 &&
+      (split ? ConvSmem<64, 32, 8, true, true, true>::total(ksteps_full)
+             : ConvSmem<64, 32, 8, false, true, true>::total(ksteps_full)) <= kMaxDynSmem)
+    halo = 32;
+  if (!halo && kbytes == 32) return set_error("conv: 32-byte K rows need the HALO variant");
+  if (!halo && kbytes == 64 && !split) return set_error("conv: Cin=16 needs FP16 pair operands");
+  const long long M_tiles_over = halo ? 1ll * a.N * P * (Q + a.S - 1) : M;  // raster the M tiles cover
+  if (M_tiles_over > 2000000000ll) return set_error("conv: too many output pixels");
+
   ConvParams p;
-  p.M_total = (int)M;
+  p.M_total = (int)M_tiles_over;
   p.P = P; p.Q = Q;
   p.Cout = a.Cout; p.Cin = a.Cin; p.R = a.R; p.S = a.S;
   p.stride = a.stride; p.pad_h = a.pad_h_lo; p.pad_w = a.pad_w_lo;
-  p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.num_m_tiles = (int)((M_tiles_over + kBlockM - 1) / kBlockM);
   p.num_n_tiles = a.Cout / block_n;
   p.kslices = a.Cin / kelems;
   p.out = a.out; p.out_h = a.out_h; p.out_l = a.out_l;
@@ -88,6 +109,8 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.a_tiled2d = a.a_tiled2d;
   p.o_step = a.o_step; p.o_h0 = a.o_h0; p.o_w0 = a.o_w0; p.o_H = a.o_H; p.o_W = a.o_W;
   if (a.o_step != 0 && a.stats != nullptr) return set_error("conv: stats with strided output");
+  if (a.stats != nullptr && (a.scale != nullptr || a.shift != nullptr))
+    return set_error("conv: batch statistics are taken from the raw output (no scale/shift)");
 
   ConvMaps m;
   const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;
@@ -97,14 +120,22 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     if (split || a.R != 1 || a.S != 1 || a.stride != 1) return set_error("conv: a_tiled2d misuse");
     if (make_tiled_map_2d(&m.a, xa, dt, (uint64_t)M, a.Cin, a.Cin, kBlockM, kelems, kbytes))
       return set_error("conv: %s", tmap_last_error());
+  } else if (halo) {
+    // S = 1 with the pad columns inside the bounding box: the traversal is the padded-width
+    // raster (W + S - 1 positions per row), boxes are kBlockM + S - 1 pixels
+    if (make_im2col_map(&m.a, xa, dt, a.N, a.H, a.W, a.Cin, a.R, 1, a.pad_h_lo, a.pad_h_hi, a.pad_w_lo,
+                        a.pad_w_hi, 1, kelems, kBlockM + a.S - 1, kbytes))
+      return set_error("conv: %s", tmap_last_error());
   } else if (make_im2col_map(&m.a, xa, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
                              a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
     return set_error("conv: %s", tmap_last_error());
   if (make_tiled_map_2d(&m.b, wa, dt, a.Cout, ktot, ktot, block_n, kelems, kbytes))
     return set_error("conv: %s", tmap_last_error());
   if (split) {
-    if (make_im2col_map(&m.a_lo, a.x_l, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo,
-                        a.pad_h_hi, a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
+    if (halo ? make_im2col_map(&m.a_lo, a.x_l, dt, a.N, a.H, a.W, a.Cin, a.R, 1, a.pad_h_lo, a.pad_h_hi,
+                               a.pad_w_lo, a.pad_w_hi, 1, kelems, kBlockM + a.S - 1, kbytes)
+             : make_im2col_map(&m.a_lo, a.x_l, dt, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo,
+                               a.pad_h_hi, a.pad_w_lo, a.pad_w_hi, a.stride, kelems, kBlockM, kbytes))
       return set_error("conv: %s", tmap_last_error());
     if (make_tiled_map_2d(&m.b_lo, a.w_l, dt, a.Cout, ktot, ktot, block_n, kelems, kbytes))
       return set_error("conv: %s", tmap_last_error());
@@ -117,6 +148,14 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
 
+  if (halo == 128) {
+    if (split) return launch_variant<64, 128, 2, true, true, true>(m, p, grid, stream);
+    return launch_variant<64, 128, 4, false, true, true>(m, p, grid, stream);
+  }
+  if (halo == 32) {
+    if (split) return launch_variant<64, 32, 8, true, true, true>(m, p, grid, stream);
+    return launch_variant<64, 32, 8, false, true, true>(m, p, grid, stream);
+  }
   // Resident weights when the whole packed matrix fits next to the activation ring.
   const int ksteps = a.R * a.S * p.kslices;
   if (p.num_n_tiles == 1 && block_n == 64 && !a.no_resident_weights) {

@@ -53,6 +53,14 @@ static const Case kCases[] = {
     {"wgrad 1x1 s2 C64->128", 1, 2, 56, 56, 64, 128, 1, 1, 2, 0, 0, 0, 0},
     {"wgrad 3x3 C256->512 7x7 N5 ragged", 1, 5, 14, 14, 256, 512, 3, 3, 2, 1, 1, 0, 0},
     {"wgrad 4x4 pad(2,1) C32->64 (s2d stem)", 1, 2, 20, 20, 32, 64, 4, 4, 1, 2, 1, 0, 0},
+    // force -1: one box per tap (no HALO)
+    {"fwd 3x3 s1 C64->64 56x56 N2 per-tap boxes", 0, 2, 56, 56, 64, 64, 3, 3, 1, 1, 1, 0, -1},
+    {"fwd 3x3 s1 C64->64 7x7 N3 HALO ragged", 0, 3, 7, 7, 64, 64, 3, 3, 1, 1, 1, 0, 0},
+    {"fwd 3x3 s1 C32->64 13x9 N5 HALO odd sizes", 0, 5, 13, 9, 32, 64, 3, 3, 1, 1, 1, 2, 0},
+    {"fwd 3x3 s1 C128->64 14x14 N2 HALO 4 k-slices", 0, 2, 14, 14, 128, 64, 3, 3, 1, 1, 1, 1, 0},
+    {"fwd 4x4 s1 pad(2,1) C32->64 HALO (4 taps/box)", 0, 3, 20, 18, 32, 64, 4, 4, 1, 2, 1, 0, 0},
+    {"fwd 4x4 s1 pad(2,1) C8->64 HALO 32-byte rows", 0, 3, 20, 18, 8, 64, 4, 4, 1, 2, 1, 0, 0},
+    {"fwd 3x3 s1 C8->64 56x56 N2 HALO 32-byte rows", 0, 2, 56, 56, 8, 64, 3, 3, 1, 1, 1, 1, 0},
 };
 static const int kNumCases = sizeof(kCases) / sizeof(kCases[0]);
 
@@ -162,7 +170,8 @@ static int run_conv(const Case& c) {
   a.N = c.N; a.H = c.H; a.W = c.W; a.Cin = c.Cin; a.Cout = c.Cout; a.R = c.R; a.S = c.S;
   a.stride = c.stride;
   a.pad_h_lo = a.pad_w_lo = c.plo; a.pad_h_hi = a.pad_w_hi = c.phi;
-  a.force_block_n = c.force;
+  a.force_block_n = c.force > 0 ? c.force : 0;
+  a.no_halo = c.force == -1;
   if (c.epi == 0) a.stats = dstats;
   if (c.epi == 1) { a.scale = dscale; a.shift = dshift; a.relu = 1; a.round_tf32 = 1; }
   if (c.epi == 2) { a.resid = dresid; a.mask = dmask; }

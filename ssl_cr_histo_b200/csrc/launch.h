@@ -39,6 +39,7 @@ struct ConvArgs {
   int o_step = 0, o_h0 = 0, o_w0 = 0, o_H = 0, o_W = 0;  // strided output placement (0 = dense)
   int a_tiled2d = 0;                  // experiment: 1x1/s1 conv with A loaded in tiled mode
   int no_resident_weights = 0;        // force the streamed-weights variant (tests)
+  int no_halo = 0;                    // force one box per filter tap (tests)
   const int* a_lo_nonzero = nullptr;  // split mode: device flag, 0 => x_l is all zero (skipped)
 };
 int launch_conv(const ConvArgs& a, cudaStream_t stream);

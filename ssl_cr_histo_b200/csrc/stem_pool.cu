@@ -2,11 +2,12 @@
 //
 // The 7x7/stride-2 stem convolution (torchvision resnet.py:197, applied :268) is run on the
 // tensor cores as a 4x4/stride-1 convolution over a 2x2 space-to-depth view of the input:
-//   xs[n, i, j, (dy*2+dx)*3 + c] = x[n, c, 2i+dy, 2j+dx]         (12 real + 20 zero channels)
+//   xs[n, i, j, (dy*2+dx)*3 + c] = x[n, c, 2i+dy, 2j+dx]         (12 real channels, zero padded)
 //   ws[k, tr, ts, (dy*2+dx)*3 + c] = w[k, c, 2tr+dy-1, 2ts+dx-1] (zero when out of the 7x7 window)
 //   out[p, q] = sum xs[p-2+tr, q-2+ts, :] . ws[:, tr, ts, :]      (padding 2 low / 1 high)
-// The channel count is padded to 32 so that the same 128-byte-row TMA boxes / UMMA layouts as
-// every other conv (forward and weight-gradient) apply.
+// The forward operand (hi, lo) FP16 pair is padded to 16 channels (32-byte pixel rows: one K = 16
+// MMA per filter tap, four taps sharing one HALO box); the fp32 copy the weight gradient reads is
+// padded to 32 channels (128-byte rows, the same TMA boxes / UMMA layout as every other wgrad).
 #include <cuda_fp16.h>
 #include <float.h>
 
@@ -15,10 +16,12 @@
 
 namespace b2n {
 
-constexpr int kStemC = 32;
+constexpr int kStemC = 32;   // channels of the fp32 (weight-gradient) copy
+constexpr int kStemC16 = 16; // channels of the FP16 (forward) pair
 
-// x: NCHW fp32 (N,3,H,W), H and W even.  Outputs NHWC (N,H/2,W/2,32): the (hi, lo) FP16 pair for
-// the forward conv and, when xs32 is given, the TF32-rounded fp32 copy the weight gradient reads.
+// x: NCHW fp32 (N,3,H,W), H and W even.  Outputs NHWC: the (hi, lo) FP16 pair (N,H/2,W/2,16) for
+// the forward conv and, when xs32 is given, the TF32-rounded fp32 copy (N,H/2,W/2,32) the weight
+// gradient reads.
 __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __restrict__ xs_h,
                                        uint4* __restrict__ xs_l, float4* __restrict__ xs32,
                                        int* __restrict__ lo_nonzero, int N, int H, int W) {
@@ -53,11 +56,10 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __res
     if (lo_nonzero != nullptr && ((pl[0].x | pl[0].y | pl[0].z | pl[0].w | pl[1].x | pl[1].y |
                                    pl[1].z | pl[1].w) & 0x7fff7fffu) != 0)
       atomicOr(lo_nonzero, 1);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* dh = xs_h + t * (kStemC / 8);
-    uint4* dl = xs_l + t * (kStemC / 8);
-    dh[0] = ph[0]; dh[1] = ph[1]; dh[2] = z; dh[3] = z;
-    dl[0] = pl[0]; dl[1] = pl[1]; dl[2] = z; dl[3] = z;
+    uint4* dh = xs_h + t * (kStemC16 / 8);
+    uint4* dl = xs_l + t * (kStemC16 / 8);
+    dh[0] = ph[0]; dh[1] = ph[1];
+    dl[0] = pl[0]; dl[1] = pl[1];
     if (xs32 != nullptr) {
       float4* d = xs32 + t * (kStemC / 4);
       d[0] = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
@@ -69,14 +71,15 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __res
   }
 }
 
-// w: (K,3,7,7) -> (hi, lo) FP16 pair ws: [K][16 taps][32].  unpack = the transpose map for grads.
+// w: (K,3,7,7) -> (hi, lo) FP16 pair ws: [K][16 taps][16].  unpack = the transpose map for grads
+// (of the 32-channel fp32 layout the weight gradient runs in).
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ ws_h,
                                         __half* __restrict__ ws_l, int K) {
-  const int total = K * 16 * kStemC;
+  const int total = K * 16 * kStemC16;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const int ch = t % kStemC;
-    const int tap = (t / kStemC) % 16;
-    const int k = t / (kStemC * 16);
+    const int ch = t % kStemC16;
+    const int tap = (t / kStemC16) % 16;
+    const int k = t / (kStemC16 * 16);
     float v = 0.f;
     if (ch < 12) {
       const int c = ch % 3, dd = ch / 3, dy = dd >> 1, dx = dd & 1;

@@ -21,7 +21,8 @@ from . import _lib
 from ._lib import call
 
 _LAYER_CFG = [(64, 1), (128, 2), (256, 2), (512, 2)]  # (planes, stride of first block)
-STEM_C = 32  # channels of the space-to-depth stem input (12 real)
+STEM_C = 32    # channels of the fp32 space-to-depth stem input the weight gradient reads (12 real)
+STEM_C16 = 16  # channels of its FP16 (hi, lo) pair, the forward conv's operand
 
 
 class BasicBlock(nn.Module):
@@ -87,7 +88,7 @@ def _pack_dgrad_s2(w):
 
 
 def _pack_stem(w):
-    out = torch.empty(2, w.shape[0], 16 * STEM_C, device=w.device, dtype=torch.float16)
+    out = torch.empty(2, w.shape[0], 16 * STEM_C16, device=w.device, dtype=torch.float16)
     call("b2n_stem_pack_weight", w, out[0], out[1], w.shape[0])
     return out[0], out[1]
 
@@ -239,11 +240,12 @@ class _TrunkFn(torch.autograd.Function):
             return s, stats
 
         saved = {"N": N, "H": H, "W": W, "blocks": []}
-        stem_alg = 147.0 / (16 * STEM_C)
+        stem_alg = 147.0 / (16 * STEM_C16)
 
         # ---- stem: s2d pack -> 4x4 tensor-core conv -> BN+ReLU+maxpool
         H2, W2 = H // 2, W // 2
-        xs = _Act((N, H2, W2, STEM_C), dev, save)
+        xs = _Act((N, H2, W2, STEM_C16), dev, False)
+        xs.f32 = torch.empty(N, H2, W2, STEM_C, device=dev, dtype=torch.float32) if save else None
         lo_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         call("b2n_stem_pack_input", x, xs.hi, xs.lo, xs.f32, lo_flag, N, H, W)
         ws = packs.get("stem", trunk.conv1.weight, _pack_stem)
@@ -251,7 +253,7 @@ class _TrunkFn(torch.autograd.Function):
         PH, PW = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
         a = _Act((N, PH, PW, 64), dev, save)
         if training:
-            y0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg,
+            y0 = _conv(xs, ws, N, H2, W2, STEM_C16, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg,
                        lo_flag=lo_flag)
             bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0)
             idx = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.uint8) if save else None
@@ -261,7 +263,7 @@ class _TrunkFn(torch.autograd.Function):
                 saved.update(xs=xs.f32, y0=y0, bn0=bn0, idx=idx)
         else:
             bn0 = _bn_affine(trunk.bn1, False, None, 0, 0, bufs, s0)
-            z0 = _conv(xs, ws, N, H2, W2, STEM_C, 64, 4, 1, 2, 1, scale=bn0.scale, shift=bn0.shift,
+            z0 = _conv(xs, ws, N, H2, W2, STEM_C16, 64, 4, 1, 2, 1, scale=bn0.scale, shift=bn0.shift,
                        relu=1, alg=stem_alg, lo_flag=lo_flag)
             ones = torch.ones(64, device=dev)
             zeros = torch.zeros(64, device=dev)

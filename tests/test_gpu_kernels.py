@@ -224,22 +224,23 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     x = ints((N, 3, H, W), 0, 255, 31)                       # uint8-valued patches
     w = ints((64, 3, 7, 7), -2, 2, 32, 0.25)
     ref = F.conv2d(x, w, None, 2, 3)
-    xs = torch.empty(N, H // 2, W // 2, 32, device=DEV)
-    xs_h, xs_l = torch.empty_like(xs, dtype=torch.half), torch.empty_like(xs, dtype=torch.half)
+    xs = torch.empty(N, H // 2, W // 2, 32, device=DEV)      # fp32 copy (wgrad): 32 channels
+    xs_h = torch.empty(N, H // 2, W // 2, 16, device=DEV, dtype=torch.half)   # FP16 pair: 16
+    xs_l = torch.empty_like(xs_h)
     flag = torch.zeros(1, device=DEV, dtype=torch.int32)
     call("b2n_stem_pack_input", x.to(DEV), xs_h, xs_l, xs, flag, N, H, W)
     assert int(flag) == 0                                     # uint8-valued input: lo plane is zero
-    ws = torch.empty(2, 64, 16 * 32, device=DEV, dtype=torch.half)
+    ws = torch.empty(2, 64, 16 * 16, device=DEV, dtype=torch.half)
     call("b2n_stem_pack_weight", w.to(DEV), ws[0], ws[1], 64)
-    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1)
+    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 16, 64, 4, 1, 2, 1)
     assert torch.equal(from_nhwc(y.cpu()), ref)
-    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1, lo_flag=flag)
+    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 16, 64, 4, 1, 2, 1, lo_flag=flag)
     assert torch.equal(from_nhwc(y.cpu()), ref)               # lo plane skipped
     xf = x + 0.37                                             # non-integer image: flag raised
     flag.zero_()
     call("b2n_stem_pack_input", xf.to(DEV), xs_h, xs_l, None, flag, N, H, W)
     assert int(flag) == 1
-    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 32, 64, 4, 1, 2, 1, lo_flag=flag)
+    y = conv((xs_h, xs_l), (ws[0], ws[1]), N, H // 2, W // 2, 16, 64, 4, 1, 2, 1, lo_flag=flag)
     ref_f = F.conv2d(xf.double(), w.double(), None, 2, 3)
     assert float((from_nhwc(y.cpu()).double() - ref_f).abs().max()) < 1e-5 * float(ref_f.abs().max())
     dy = ints(tuple(ref.shape), -1, 1, 33)
