@@ -121,15 +121,19 @@ int b2n_bn_apply(const float* y, const float* scale, const float* shift, const f
                  const float* res_scale, const float* res_shift, const b2n_half* res_h,
                  const b2n_half* res_l, float* out32, b2n_half* out_h, b2n_half* out_l,
                  long long rows, int C, int relu, int round_tf32, void* stream);
-/* BatchNorm backward, two passes.  g' = g * [mask > 0] (mask = post-ReLU block output or null).
+/* BatchNorm backward, two passes.  g' = g * [ReLU gate]; the gate is mask > 0 (mask = post-ReLU
+ * block output), or -- when the ReLU input is this BN's own output (bn1 of a BasicBlock) --
+ * fmaf(y, gate_scale, gate_shift) > 0 recomputed from y with the forward affine (saves reading the
+ * mask in both passes), or absent (all three null).
  *   reduce: sums[0][c] += sum g', sums[1][c] += sum g' * xhat        (sums caller-zeroed)
  *   apply : dy = gamma*invstd*(g' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0 */
 int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
-                      const float* invstd, double* sums, long long rows, int C, void* stream);
+                      const float* invstd, const float* gate_scale, const float* gate_shift,
+                      double* sums, long long rows, int C, void* stream);
 int b2n_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
-                     const float* invstd, const float* gamma, const double* sums, float* dy,
-                     float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
-                     void* stream);
+                     const float* invstd, const float* gamma, const float* gate_scale,
+                     const float* gate_shift, const double* sums, float* dy, float* dgamma,
+                     float* dbeta, long long rows, int C, int round_tf32, void* stream);
 /* up[n,2p,2q,:] = dy[n,p,q,:], zero elsewhere: stride-2 data gradient as a stride-1 conv. */
 int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                       void* stream);
@@ -142,6 +146,20 @@ int b2n_bn_relu_maxpool(const float* y, const float* scale, const float* shift,
 int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* argmax_idx, const float* y,
                          const float* scale, const float* shift, float* gz, int N, int H, int W,
                          int C, void* stream);
+/* The stem's tail backward in two sweeps instead of five: the gradient of maxpool+ReLU is rebuilt
+ * on the fly from the pooled gradient `ga` (N,P,Q,C) and the recorded argmax, and fed straight
+ * into the two BatchNorm-backward passes (same formulas as b2n_bn_bwd_reduce / _apply; y is the
+ * raw stem conv output (N,H,W,C), scale/shift the forward BN affine that defines the ReLU gate).
+ * Replaces loss.backward() through tv:269-271 (bn1, relu, maxpool). */
+int b2n_pool_bn_bwd_reduce(const float* ga, const unsigned char* argmax_idx, const float* y,
+                           const float* scale, const float* shift, const float* mean,
+                           const float* invstd, double* sums /* [2][C], caller-zeroed */, int N,
+                           int H, int W, int C, void* stream);
+int b2n_pool_bn_bwd_apply(const float* ga, const unsigned char* argmax_idx, const float* y,
+                          const float* scale, const float* shift, const float* mean,
+                          const float* invstd, const float* gamma, const double* sums, float* dy,
+                          float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
+                          void* stream);
 int b2n_avgpool_fwd(const b2n_half* a_h, const b2n_half* a_l, float* e, int N, int HW, int C,
                     void* stream);
 int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream);

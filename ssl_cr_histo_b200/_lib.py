@@ -31,11 +31,13 @@ _SIGNATURES = {
     "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
     "b2n_bn_apply": [P] * 11 + [LL, I, I, I],
-    "b2n_bn_bwd_reduce": [P] * 6 + [LL, I],
-    "b2n_bn_bwd_apply": [P] * 10 + [LL, I, I],
+    "b2n_bn_bwd_reduce": [P] * 8 + [LL, I],
+    "b2n_bn_bwd_apply": [P] * 12 + [LL, I, I],
     "b2n_upsample_zero": [P, P] + [I] * 6,
     "b2n_bn_relu_maxpool": [P] * 7 + [I] * 4,
     "b2n_maxpool_relu_bwd": [P] * 6 + [I] * 4,
+    "b2n_pool_bn_bwd_reduce": [P] * 8 + [I] * 4,
+    "b2n_pool_bn_bwd_apply": [P] * 12 + [I] * 5,
     "b2n_avgpool_fwd": [P, P, P, I, I, I],
     "b2n_avgpool_bwd": [P, P, I, I, I],
     "b2n_linear_fwd": [P, LL, P, LL, P, P, LL, I, I, I, I, I],

@@ -113,15 +113,17 @@ int b2n_bn_apply(const float* y, const float* scale, const float* shift, const f
                                  round_tf32, S(stream)));
 }
 int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
-                      const float* invstd, double* sums, long long rows, int C, void* stream) {
-  return counted(launch_bn_bwd_reduce(g, mask, y, mean, invstd, sums, rows, C, S(stream)));
+                      const float* invstd, const float* gate_scale, const float* gate_shift,
+                      double* sums, long long rows, int C, void* stream) {
+  return counted(launch_bn_bwd_reduce(g, mask, y, mean, invstd, gate_scale, gate_shift, sums, rows, C,
+                                      S(stream)));
 }
 int b2n_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
-                     const float* invstd, const float* gamma, const double* sums, float* dy,
-                     float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
-                     void* stream) {
-  return counted(launch_bn_bwd_apply(g, mask, y, mean, invstd, gamma, sums, dy, dgamma, dbeta, rows, C,
-                             round_tf32, S(stream)));
+                     const float* invstd, const float* gamma, const float* gate_scale,
+                     const float* gate_shift, const double* sums, float* dy, float* dgamma,
+                     float* dbeta, long long rows, int C, int round_tf32, void* stream) {
+  return counted(launch_bn_bwd_apply(g, mask, y, mean, invstd, gamma, gate_scale, gate_shift, sums, dy,
+                                     dgamma, dbeta, rows, C, round_tf32, S(stream)));
 }
 int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                       void* stream) {
@@ -138,6 +140,21 @@ int b2n_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float*
                          const float* scale, const float* shift, float* gz, int N, int H, int W,
                          int C, void* stream) {
   return counted(launch_maxpool_relu_bwd(ga, idx, y, scale, shift, gz, N, H, W, C, S(stream)));
+}
+int b2n_pool_bn_bwd_reduce(const float* ga, const unsigned char* idx, const float* y,
+                           const float* scale, const float* shift, const float* mean,
+                           const float* invstd, double* sums, int N, int H, int W, int C,
+                           void* stream) {
+  return counted(launch_pool_bn_bwd_reduce(ga, idx, y, scale, shift, mean, invstd, sums, N, H, W, C,
+                                           S(stream)));
+}
+int b2n_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const float* y,
+                          const float* scale, const float* shift, const float* mean,
+                          const float* invstd, const float* gamma, const double* sums, float* dy,
+                          float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
+                          void* stream) {
+  return counted(launch_pool_bn_bwd_apply(ga, idx, y, scale, shift, mean, invstd, gamma, sums, dy,
+                                          dgamma, dbeta, N, H, W, C, round_tf32, S(stream)));
 }
 int b2n_avgpool_fwd(const b2n_half* a_h, const b2n_half* a_l, float* e, int N, int HW, int C,
                     void* stream) {

@@ -174,13 +174,18 @@ int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, 
 }
 
 // ------------------------------------------------------------------ backward
-// g' = g * (mask > 0)   (mask = the block's post-ReLU output; null = no ReLU gate)
+// g' = g * (mask > 0)   (mask = the block's post-ReLU output; null = no ReLU gate).  When the
+// ReLU input is the BN output itself (no residual: bn1 of a BasicBlock) the gate can instead be
+// recomputed from y -- fmaf(y, gate_scale, gate_shift) > 0, the forward's own expression -- which
+// saves reading the mask tensor in both passes.
 // sums[0][c] = sum g',  sums[1][c] = sum g' * xhat,  xhat = (y - mean) * invstd
 //
 // Thread layout: threadIdx.x -> float4 channel group (C/4 of them), threadIdx.y -> row lane.
 __global__ void bn_bwd_reduce_kernel(const float4* __restrict__ g, const float4* __restrict__ mask,
                                      const float4* __restrict__ y, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, double* __restrict__ sums,
+                                     const float* __restrict__ invstd,
+                                     const float* __restrict__ gate_scale,
+                                     const float* __restrict__ gate_shift, double* __restrict__ sums,
                                      long long rows, int C, int rows_per_block) {
   extern __shared__ float red[];  // [blockDim.y][C][2]
   const int cg = threadIdx.x;     // channel group
@@ -192,6 +197,11 @@ __global__ void bn_bwd_reduce_kernel(const float4* __restrict__ g, const float4*
   if (cg < C4) {
     const float4 mu = *reinterpret_cast<const float4*>(mean + 4 * cg);
     const float4 is = *reinterpret_cast<const float4*>(invstd + 4 * cg);
+    float4 gs = make_float4(0, 0, 0, 0), gh = gs;
+    if (gate_scale != nullptr) {
+      gs = *reinterpret_cast<const float4*>(gate_scale + 4 * cg);
+      gh = *reinterpret_cast<const float4*>(gate_shift + 4 * cg);
+    }
     for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
       const size_t i = static_cast<size_t>(r) * C4 + cg;
       float4 gv = g[i];
@@ -201,6 +211,10 @@ __global__ void bn_bwd_reduce_kernel(const float4* __restrict__ g, const float4*
         gv.z = m.z > 0.f ? gv.z : 0.f; gv.w = m.w > 0.f ? gv.w : 0.f;
       }
       const float4 yv = y[i];
+      if (gate_scale != nullptr) {
+        gv.x = fmaf(yv.x, gs.x, gh.x) > 0.f ? gv.x : 0.f; gv.y = fmaf(yv.y, gs.y, gh.y) > 0.f ? gv.y : 0.f;
+        gv.z = fmaf(yv.z, gs.z, gh.z) > 0.f ? gv.z : 0.f; gv.w = fmaf(yv.w, gs.w, gh.w) > 0.f ? gv.w : 0.f;
+      }
       s1.x += gv.x; s1.y += gv.y; s1.z += gv.z; s1.w += gv.w;
       s2.x += gv.x * (yv.x - mu.x) * is.x; s2.y += gv.y * (yv.y - mu.y) * is.y;
       s2.z += gv.z * (yv.z - mu.z) * is.z; s2.w += gv.w * (yv.w - mu.w) * is.w;
@@ -225,6 +239,8 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const float4* __restrict__ y, const float* __restrict__ mean,
                                     const float* __restrict__ invstd,
                                     const float* __restrict__ gamma,
+                                    const float* __restrict__ gate_scale,
+                                    const float* __restrict__ gate_shift,
                                     const double* __restrict__ sums, float4* __restrict__ dy,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, size_t n4,
                                     int C, double inv_count) {
@@ -244,6 +260,12 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
       gv.z = m.z > 0.f ? gv.z : 0.f; gv.w = m.w > 0.f ? gv.w : 0.f;
     }
     const float4 yv = y[i];
+    if (gate_scale != nullptr) {
+      const float4 gs = *reinterpret_cast<const float4*>(gate_scale + c);
+      const float4 gh = *reinterpret_cast<const float4*>(gate_shift + c);
+      gv.x = fmaf(yv.x, gs.x, gh.x) > 0.f ? gv.x : 0.f; gv.y = fmaf(yv.y, gs.y, gh.y) > 0.f ? gv.y : 0.f;
+      gv.z = fmaf(yv.z, gs.z, gh.z) > 0.f ? gv.z : 0.f; gv.w = fmaf(yv.w, gs.w, gh.w) > 0.f ? gv.w : 0.f;
+    }
     const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 is = *reinterpret_cast<const float4*>(invstd + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
@@ -266,8 +288,10 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
 }
 
 int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
-                         const float* invstd, double* sums, long long rows, int C,
-                         cudaStream_t stream) {
+                         const float* invstd, const float* gate_scale, const float* gate_shift,
+                         double* sums, long long rows, int C, cudaStream_t stream) {
+  if ((gate_scale != nullptr) != (gate_shift != nullptr))
+    return set_error("bn_bwd_reduce: gate_scale and gate_shift come as a pair");
   if (C % 4 != 0 || C > 1024) return set_error("bn_bwd_reduce: unsupported C=%d", C);
   const int C4 = C / 4;
   int ty = 256 / C4;
@@ -281,16 +305,19 @@ int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, cons
   const size_t smem = static_cast<size_t>(ty) * C * 2 * sizeof(float);
   bn_bwd_reduce_kernel<<<blocks, block, smem, stream>>>(
       reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(mask),
-      reinterpret_cast<const float4*>(y), mean, invstd, sums, rows, C, static_cast<int>(rpb));
+      reinterpret_cast<const float4*>(y), mean, invstd, gate_scale, gate_shift, sums, rows, C,
+      static_cast<int>(rpb));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_bwd_reduce: %s", cudaGetErrorString(e));
   return 0;
 }
 
 int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
-                        const float* invstd, const float* gamma, const double* sums, float* dy,
-                        float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
-                        cudaStream_t stream) {
+                        const float* invstd, const float* gamma, const float* gate_scale,
+                        const float* gate_shift, const double* sums, float* dy, float* dgamma,
+                        float* dbeta, long long rows, int C, int round_tf32, cudaStream_t stream) {
+  if ((gate_scale != nullptr) != (gate_shift != nullptr))
+    return set_error("bn_bwd_apply: gate_scale and gate_shift come as a pair");
   if (C % 4 != 0) return set_error("bn_bwd_apply: C %% 4 != 0");
   const size_t n4 = static_cast<size_t>(rows) * C / 4;
   const int threads = 256;
@@ -305,10 +332,12 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
   auto d4 = reinterpret_cast<float4*>(dy);
   if (round_tf32)
     bn_bwd_apply_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(
-        g4, m4, y4, mean, invstd, gamma, sums, d4, dgamma, dbeta, n4, C, inv_count);
+        g4, m4, y4, mean, invstd, gamma, gate_scale, gate_shift, sums, d4, dgamma, dbeta, n4, C,
+        inv_count);
   else
     bn_bwd_apply_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(
-        g4, m4, y4, mean, invstd, gamma, sums, d4, dgamma, dbeta, n4, C, inv_count);
+        g4, m4, y4, mean, invstd, gamma, gate_scale, gate_shift, sums, d4, dgamma, dbeta, n4, C,
+        inv_count);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_bwd_apply: %s", cudaGetErrorString(e));
   return 0;

@@ -100,7 +100,18 @@ struct ConvSmem {
   }
 };
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false>
+// Epilogue feature bits.  EPI < 0 (generic) tests the ConvParams pointers at run time; EPI >= 0
+// compiles exactly that combination -- the 64-channel layers are epilogue-instruction bound (a
+// 128 x 64 tile is only ~1-3.5k tensor-pipe cycles), so their launches use specialised kernels.
+enum : int {
+  kEpiStats = 1, kEpiAffine = 2, kEpiResid32 = 4, kEpiMask = 8, kEpiResid16 = 16, kEpiRelu = 32,
+  kEpiOut32 = 64, kEpiOut16 = 128, kEpiRound = 256
+};
+__host__ __device__ constexpr bool epi_on(int epi, int bit, bool runtime) {
+  return epi >= 0 ? (epi & bit) != 0 : runtime;
+}
+
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
@@ -121,8 +132,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   static_assert(!HALO || RES_B, "HALO needs resident weights");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // align by offsetting the __shared__ array itself (not through an integer cast) so the compiler
+  // keeps the shared address space and emits LDS / STS for the staging tile and the statistics
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* s_stats = reinterpret_cast<float*>(base);
   float4* s_stage = reinterpret_cast<float4*>(base + L::STATS_FLOATS * 4);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + L::STATS_FLOATS * 4 + L::STAGING_BYTES);
@@ -348,6 +360,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ========================================================= epilogue
+    const bool f_stats = epi_on(EPI, kEpiStats, p.stats != nullptr);
+    const bool f_affine = epi_on(EPI, kEpiAffine, p.scale != nullptr);
+    const bool f_resid = epi_on(EPI, kEpiResid32, p.resid != nullptr);
+    const bool f_mask = epi_on(EPI, kEpiMask, p.mask != nullptr);
+    const bool f_resid16 = epi_on(EPI, kEpiResid16, p.resid_h != nullptr);
+    const bool f_relu = epi_on(EPI, kEpiRelu, p.relu != 0);
+    const bool f_out32 = epi_on(EPI, kEpiOut32, p.out != nullptr);
+    const bool f_out16 = epi_on(EPI, kEpiOut16, p.out_h != nullptr);
+    const bool f_round = epi_on(EPI, kEpiRound, p.round_tf32 != 0);
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
     float4* stg = s_stage + quad * (16 * 8);
@@ -386,27 +407,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl)
         row4[sl] = __shfl_sync(0xffffffffu, my_row4, (sl >> 2) * 16 + 4 * (sl & 3) + (lane >> 3));
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
-#pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-        float v[32];
-        tmem_ld_32x32(t_addr + ch * 32, v);
-        const int n0 = n_tile * BLOCK_N + ch * 32;
-        // Residual operands of the whole chunk are fetched up front: eight independent loads per
-        // lane in flight (and overlapped with the TMEM read) instead of one load -> use -> store
-        // round trip per row group -- the stores below may alias, so the compiler cannot hoist.
-        const int c4 = n0 + 4 * (lane & 7);
-        float4 pre_r[8], pre_m[8];
-        uint2 pre_h[8], pre_l[8];
-        if (p.resid != nullptr) {
+      // Residual operands are fetched up front -- eight independent loads per lane and chunk in
+      // flight instead of one load -> use -> store round trip per row group (the stores may alias,
+      // so the compiler cannot hoist).  64-wide tiles fetch the whole tile *before* waiting for the
+      // accumulator, hiding the HBM latency behind the tile's MMAs.
+      auto prefetch = [&](int ch, float4(&pre_r)[8], float4(&pre_m)[8], uint2(&pre_h)[8],
+                          uint2(&pre_l)[8]) {
+        const int c4 = n_tile * BLOCK_N + ch * 32 + 4 * (lane & 7);
+        if (f_resid) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl)
             pre_r[sl] = row4[sl] != 0xFFFFFFFFu
                             ? *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(row4[sl]) << 2) + c4)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.mask != nullptr) {
+          if (f_mask) {
 #pragma unroll
             for (int sl = 0; sl < 8; ++sl)
               pre_m[sl] = row4[sl] != 0xFFFFFFFFu
@@ -414,7 +428,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                               : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (p.resid_h != nullptr) {
+        if (f_resid16) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl) {
             const bool ok = row4[sl] != 0xFFFFFFFFu;
@@ -423,16 +437,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             pre_l[sl] = ok ? *reinterpret_cast<const uint2*>(p.resid_l + o) : make_uint2(0u, 0u);
           }
         }
+      };
+      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+      auto process = [&](int ch, const float4(&pre_r)[8], const float4(&pre_m)[8],
+                         const uint2(&pre_h)[8], const uint2(&pre_l)[8]) {
+        float v[32];
+        tmem_ld_32x32(t_addr + ch * 32, v);
+        const int n0 = n_tile * BLOCK_N + ch * 32;
+        const int c4 = n0 + 4 * (lane & 7);
         tmem_ld_wait();
         // per-channel affine while a thread still owns a whole row of the chunk
-        if (p.scale != nullptr) {
+        if (f_affine) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 sc = *reinterpret_cast<const float4*>(p.scale + n0 + 4 * i);
             v[4 * i] *= sc.x; v[4 * i + 1] *= sc.y; v[4 * i + 2] *= sc.z; v[4 * i + 3] *= sc.w;
           }
         }
-        if (p.shift != nullptr) {
+        if (f_affine) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 sh = *reinterpret_cast<const float4*>(p.shift + n0 + 4 * i);
@@ -461,14 +483,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             if (row4[sl] != 0xFFFFFFFFu) {
               const size_t off = (static_cast<size_t>(row4[sl]) << 2) + c4;
               float o[4] = {t.x, t.y, t.z, t.w};
-              if (p.stats != nullptr) {  // BN batch statistics of the raw conv output
+              if (f_stats) {  // BN batch statistics of the raw conv output
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { st_s[k] += o[k]; st_q[k] += o[k] * o[k]; }
               }
-              if (p.resid != nullptr) {
+              if (f_resid) {
                 const float4 r0 = pre_r[sl];
                 float rr[4] = {r0.x, r0.y, r0.z, r0.w};
-                if (p.mask != nullptr) {
+                if (f_mask) {
                   const float4 m0 = pre_m[sl];
                   rr[0] = m0.x > 0.f ? rr[0] : 0.f; rr[1] = m0.y > 0.f ? rr[1] : 0.f;
                   rr[2] = m0.z > 0.f ? rr[2] : 0.f; rr[3] = m0.w > 0.f ? rr[3] : 0.f;
@@ -476,7 +498,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] += rr[k];
               }
-              if (p.resid_h != nullptr) {
+              if (f_resid16) {
                 const uint2 rh = pre_h[sl];
                 const uint2 rl = pre_l[sl];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
@@ -488,11 +510,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   o[2 * k + 1] += a.y + b.y;
                 }
               }
-              if (p.relu) {
+              if (f_relu) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
               }
-              if (p.out_h != nullptr) {
+              if (f_out16) {
                 uint2 ph, pl;
                 __half2* h2 = reinterpret_cast<__half2*>(&ph);
                 __half2* l2 = reinterpret_cast<__half2*>(&pl);
@@ -501,8 +523,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                 *reinterpret_cast<uint2*>(p.out_h + off) = ph;
                 *reinterpret_cast<uint2*>(p.out_l + off) = pl;
               }
-              if (p.out != nullptr) {
-                if (p.round_tf32) {
+              if (f_out32) {
+                if (f_round) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) o[k] = tf32_rn(o[k]);
                 }
@@ -512,7 +534,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           }
           __syncwarp();
         }
-        if (p.stats != nullptr) {
+        if (f_stats) {
           // lanes l, l+8, l+16, l+24 hold the same four channels (different rows); each epilogue
           // warp accumulates into its own smem row (no atomics, no cross-warp contention)
 #pragma unroll
@@ -528,6 +550,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             for (int k = 0; k < 4; ++k) { mine[k] += st_s[k]; mine[L::STATS_C + k] += st_q[k]; }
           }
         }
+      };
+      if constexpr (BLOCK_N == 64 && EPI >= 0) {
+        float4 pr0[8], pm0[8], pr1[8], pm1[8];
+        uint2 ph0[8], pl0[8], ph1[8], pl1[8];
+        prefetch(0, pr0, pm0, ph0, pl0);
+        prefetch(1, pr1, pm1, ph1, pl1);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        process(0, pr0, pm0, ph0, pl0);
+        process(1, pr1, pm1, ph1, pl1);
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          float4 pr[8], pm[8];
+          uint2 ph[8], pl[8];
+          prefetch(ch, pr, pm, ph, pl);
+          process(ch, pr, pm, ph, pl);
+        }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back
       tc_fence_before();
@@ -535,7 +577,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.stats != nullptr) {
+    if (f_stats) {
       // epilogue-only named barrier (warps 2..5 = 128 threads), then flush CTA partials
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = threadIdx.x - 64; c < p.Cout; c += 128) {

@@ -25,10 +25,10 @@ struct ConvMaps {
 
 constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
   using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI>;
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
   static bool configured = false;
@@ -109,6 +109,9 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.a_tiled2d = a.a_tiled2d;
   p.o_step = a.o_step; p.o_h0 = a.o_h0; p.o_w0 = a.o_w0; p.o_H = a.o_H; p.o_W = a.o_W;
   if (a.o_step != 0 && a.stats != nullptr) return set_error("conv: stats with strided output");
+  if ((a.scale != nullptr) != (a.shift != nullptr))
+    return set_error("conv: scale and shift come as a pair");
+  if (a.mask != nullptr && a.resid == nullptr) return set_error("conv: mask without resid");
   if (a.stats != nullptr && (a.scale != nullptr || a.shift != nullptr))
     return set_error("conv: batch statistics are taken from the raw output (no scale/shift)");
 
@@ -148,14 +151,34 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
 
+  // epilogue features of this launch; the combinations the network's 64-channel layers use have
+  // specialised kernels (see the EPI comment in conv_igemm.cuh), everything else runs generic
+  const int epi = (a.stats ? kEpiStats : 0) | (a.scale ? kEpiAffine : 0) | (a.resid ? kEpiResid32 : 0) |
+                  (a.mask ? kEpiMask : 0) | (a.resid_h ? kEpiResid16 : 0) | (a.relu ? kEpiRelu : 0) |
+                  (a.out ? kEpiOut32 : 0) | (a.out_h ? kEpiOut16 : 0) | (a.round_tf32 ? kEpiRound : 0);
+  constexpr int kTrainFwd = kEpiStats | kEpiOut32;                       // raw y + BN statistics
+  constexpr int kEvalAct = kEpiAffine | kEpiRelu | kEpiOut16;            // folded BN + ReLU -> pair
+  constexpr int kEvalActRes = kEvalAct | kEpiResid16;                    // ... + identity shortcut
+  constexpr int kEvalStem = kEpiAffine | kEpiRelu | kEpiOut32;
+  constexpr int kDgrad = kEpiOut32;
+  constexpr int kDgradRes = kEpiOut32 | kEpiResid32 | kEpiMask;          // + gated shortcut gradient
+  if (halo == 128 && split) {
+    if (epi == kTrainFwd) return launch_variant<64, 128, 2, true, true, true, kTrainFwd>(m, p, grid, stream);
+    if (epi == kEvalAct) return launch_variant<64, 128, 2, true, true, true, kEvalAct>(m, p, grid, stream);
+    if (epi == kEvalActRes) return launch_variant<64, 128, 2, true, true, true, kEvalActRes>(m, p, grid, stream);
+    return launch_variant<64, 128, 2, true, true, true>(m, p, grid, stream);
+  }
   if (halo == 128) {
-    if (split) return launch_variant<64, 128, 2, true, true, true>(m, p, grid, stream);
+    if (epi == kDgrad) return launch_variant<64, 128, 4, false, true, true, kDgrad>(m, p, grid, stream);
+    if (epi == kDgradRes) return launch_variant<64, 128, 4, false, true, true, kDgradRes>(m, p, grid, stream);
     return launch_variant<64, 128, 4, false, true, true>(m, p, grid, stream);
   }
-  if (halo == 32) {
-    if (split) return launch_variant<64, 32, 8, true, true, true>(m, p, grid, stream);
-    return launch_variant<64, 32, 8, false, true, true>(m, p, grid, stream);
+  if (halo == 32 && split) {
+    if (epi == kTrainFwd) return launch_variant<64, 32, 8, true, true, true, kTrainFwd>(m, p, grid, stream);
+    if (epi == kEvalStem) return launch_variant<64, 32, 8, true, true, true, kEvalStem>(m, p, grid, stream);
+    return launch_variant<64, 32, 8, true, true, true>(m, p, grid, stream);
   }
+  if (halo == 32) return launch_variant<64, 32, 8, false, true, true>(m, p, grid, stream);
   // Resident weights when the whole packed matrix fits next to the activation ring.
   const int ksteps = a.R * a.S * p.kslices;
   if (p.num_n_tiles == 1 && block_n == 64 && !a.no_resident_weights) {

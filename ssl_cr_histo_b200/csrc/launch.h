@@ -69,12 +69,12 @@ int launch_bn_apply(const float* y, const float* scale, const float* shift, cons
                     const __half* res_l, float* out32, __half* out_h, __half* out_l,
                     long long rows, int C, int relu, int round_tf32, cudaStream_t stream);
 int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, const float* mean,
-                         const float* invstd, double* sums, long long rows, int C,
-                         cudaStream_t stream);
+                         const float* invstd, const float* gate_scale, const float* gate_shift,
+                         double* sums, long long rows, int C, cudaStream_t stream);
 int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
-                        const float* invstd, const float* gamma, const double* sums, float* dy,
-                        float* dgamma, float* dbeta, long long rows, int C, int round_tf32,
-                        cudaStream_t stream);
+                        const float* invstd, const float* gamma, const float* gate_scale,
+                        const float* gate_shift, const double* sums, float* dy, float* dgamma,
+                        float* dbeta, long long rows, int C, int round_tf32, cudaStream_t stream);
 int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                          cudaStream_t stream);
 int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
@@ -88,6 +88,15 @@ int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shif
 int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const float* y,
                             const float* scale, const float* shift, float* gz, int N, int H, int W,
                             int C, cudaStream_t stream);
+int launch_pool_bn_bwd_reduce(const float* ga, const unsigned char* idx, const float* y,
+                              const float* scale, const float* shift, const float* mean,
+                              const float* invstd, double* sums, int N, int H, int W, int C,
+                              cudaStream_t stream);
+int launch_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const float* y,
+                             const float* scale, const float* shift, const float* mean,
+                             const float* invstd, const float* gamma, const double* sums, float* dy,
+                             float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
+                             cudaStream_t stream);
 int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, int HW, int C,
                        cudaStream_t stream);
 int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream);

@@ -195,11 +195,12 @@ __device__ __forceinline__ float tf32_rn(float x) {
 // (hi, lo) FP16 pair of two fp32 values: hi = fp16(v) (saturated to the finite range),
 // lo = fp16(v - hi); hi + lo reproduces v to ~2^-22 (absolute floor 2^-25 from fp16 subnormals).
 __device__ __forceinline__ void split_f16(float a, float b, __half2& hi, __half2& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  hi = __floats2half2_rn(a, b);
-  const float2 h = __half22float2(hi);
-  lo = __floats2half2_rn(a - h.x, b - h.y);
+  uint32_t h, l;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));  // {b : a} -> a low
+  hi = *reinterpret_cast<__half2*>(&h);
+  const float2 hf = __half22float2(hi);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(b - hf.y), "f"(a - hf.x));
+  lo = *reinterpret_cast<__half2*>(&l);
 }
 
 }  // namespace b2n

@@ -351,14 +351,17 @@ class _TrunkFn(torch.autograd.Function):
             return (None, None, None, None) + tuple(None for _ in params)
         min_unit = min(i for i, n in enumerate(unit_need) if n)
 
-        def bn_backward(g, mask, y, st, bn, rows, C):
+        def bn_backward(g, mask, y, st, bn, rows, C, gate_from_y=False):
+            """``mask``: post-ReLU tensor gating g, or None; ``gate_from_y``: the ReLU input is this
+            BN's own output, so the gate is recomputed from y (no mask tensor is read)."""
+            gsc, gsh = (st.scale, st.shift) if gate_from_y else (None, None)
             sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
-            call("b2n_bn_bwd_reduce", g, mask, y, st.mean, st.invstd, sums, rows, C)
+            call("b2n_bn_bwd_reduce", g, mask, y, st.mean, st.invstd, gsc, gsh, sums, rows, C)
             dy = torch.empty_like(y)
             dgamma = torch.empty(C, device=dev)
             dbeta = torch.empty(C, device=dev)
-            call("b2n_bn_bwd_apply", g, mask, y, st.mean, st.invstd, bn.weight, sums, dy, dgamma,
-                 dbeta, rows, C, 1)
+            call("b2n_bn_bwd_apply", g, mask, y, st.mean, st.invstd, bn.weight, gsc, gsh, sums, dy,
+                 dgamma, dbeta, rows, C, 1)
             if need[id(bn.weight)]:
                 grads[id(bn.weight)] = dgamma
             if need[id(bn.bias)]:
@@ -396,7 +399,7 @@ class _TrunkFn(torch.autograd.Function):
             wgrad(blk.conv2, rec["a1"], dy2, ph, pw, 1, 1)
             wd2 = packs.get("b%d.w2d" % bi, blk.conv2.weight, _pack_dgrad)
             da1 = _conv(dy2, wd2, N, ph, pw, cout, cout, 3, 1, 1, 1)
-            dy1 = bn_backward(da1, rec["a1"], rec["y1"], rec["b1"], blk.bn1, rows, cout)
+            dy1 = bn_backward(da1, None, rec["y1"], rec["b1"], blk.bn1, rows, cout, gate_from_y=True)
             wgrad(blk.conv1, rec["a_in"], dy1, h, w, s, 1)
             g_in = None
             if blk.downsample is not None:
@@ -425,10 +428,18 @@ class _TrunkFn(torch.autograd.Function):
         if min_unit == 0:
             H2, W2 = sv["H"] // 2, sv["W"] // 2
             bn0 = sv["bn0"]
-            gz = torch.empty_like(sv["y0"])
-            call("b2n_maxpool_relu_bwd", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, gz, N, H2, W2,
-                 64)
-            dy0 = bn_backward(gz, None, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
+            # maxpool + ReLU + BN backward fused: two sweeps over the stem output instead of five
+            sums = torch.zeros(2 * 64, device=dev, dtype=torch.float64)
+            call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
+                 bn0.invstd, sums, N, H2, W2, 64)
+            dy0 = torch.empty_like(sv["y0"])
+            dgamma, dbeta = torch.empty(64, device=dev), torch.empty(64, device=dev)
+            call("b2n_pool_bn_bwd_apply", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
+                 bn0.invstd, trunk.bn1.weight, sums, dy0, dgamma, dbeta, N, H2, W2, 64, 1)
+            if need[id(trunk.bn1.weight)]:
+                grads[id(trunk.bn1.weight)] = dgamma
+            if need[id(trunk.bn1.bias)]:
+                grads[id(trunk.bn1.bias)] = dbeta
             if need[id(trunk.conv1.weight)]:
                 dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
                 call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,

@@ -296,14 +296,27 @@ def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
     assert torch.allclose(rm.cpu(), bn.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(rv.cpu(), bn.running_var, rtol=1e-5, atol=1e-6)
     sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
-    call("b2n_bn_bwd_reduce", gout.to(DEV), out, yd, mean, invstd, sums, rows, C)
+    call("b2n_bn_bwd_reduce", gout.to(DEV), out, yd, mean, invstd, None, None, sums, rows, C)
     dy, dgamma, dbeta = torch.empty(rows, C, device=DEV), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
-    call("b2n_bn_bwd_apply", gout.to(DEV), out, yd, mean, invstd, gamma.to(DEV), sums, dy, dgamma,
-         dbeta, rows, C, 0)
+    call("b2n_bn_bwd_apply", gout.to(DEV), out, yd, mean, invstd, gamma.to(DEV), None, None, sums, dy,
+         dgamma, dbeta, rows, C, 0)
     scale_t = float(yr.grad.abs().max())
     assert float((dy.cpu() - yr.grad).abs().max()) < 2e-4 * scale_t
     assert torch.allclose(dgamma.cpu(), bn.weight.grad, rtol=1e-3, atol=1e-3)
     assert torch.allclose(dbeta.cpu(), bn.bias.grad, rtol=1e-4, atol=1e-4)
+    # ReLU gate recomputed from y (no residual: bn1 of a block) == gate read from the mask tensor
+    act = torch.empty(rows, C, device=DEV)
+    call("b2n_bn_apply", yd, scale, shift, None, None, None, None, None, act, None, None, rows, C, 1, 0)
+    s_m, s_y = (torch.zeros(2 * C, device=DEV, dtype=torch.float64) for _ in range(2))
+    call("b2n_bn_bwd_reduce", gout.to(DEV), act, yd, mean, invstd, None, None, s_m, rows, C)
+    call("b2n_bn_bwd_reduce", gout.to(DEV), None, yd, mean, invstd, scale, shift, s_y, rows, C)
+    assert torch.equal(s_m, s_y)
+    dy_m, dy_y = torch.empty(rows, C, device=DEV), torch.empty(rows, C, device=DEV)
+    call("b2n_bn_bwd_apply", gout.to(DEV), act, yd, mean, invstd, gamma.to(DEV), None, None, s_m, dy_m,
+         dgamma, dbeta, rows, C, 1)
+    call("b2n_bn_bwd_apply", gout.to(DEV), None, yd, mean, invstd, gamma.to(DEV), scale, shift, s_m, dy_y,
+         dgamma, dbeta, rows, C, 1)
+    assert torch.equal(dy_m, dy_y)
     # eval-mode fold
     call("b2n_bn_fold_eval", gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, C, 1e-5)
     bn.eval()
@@ -338,6 +351,24 @@ def test_bn_relu_maxpool_forward_backward(shape):
     call("b2n_maxpool_relu_bwd", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), gz, N, H,
          W, C)
     assert torch.allclose(from_nhwc(gz.cpu()), z.grad * (z.detach() > 0), rtol=1e-6, atol=1e-7)
+    # fused maxpool + ReLU + BN backward == the three-kernel chain over the materialised gz
+    rows = N * H * W
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    mean = yd.mean((0, 1, 2))
+    invstd = 1.0 / torch.sqrt(yd.var((0, 1, 2), unbiased=False) + 1e-5)
+    s_ref = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    call("b2n_bn_bwd_reduce", gz, None, yd, mean, invstd, None, None, s_ref, rows, C)
+    dy_ref, dg_ref, db_ref = torch.empty_like(yd), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    call("b2n_bn_bwd_apply", gz, None, yd, mean, invstd, gamma, None, None, s_ref, dy_ref, dg_ref, db_ref,
+         rows, C, 1)
+    s_f = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    call("b2n_pool_bn_bwd_reduce", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), mean,
+         invstd, s_f, N, H, W, C)
+    assert torch.allclose(s_f, s_ref, rtol=1e-5, atol=1e-5)
+    dy_f, dg_f, db_f = torch.empty_like(yd), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    call("b2n_pool_bn_bwd_apply", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), mean,
+         invstd, gamma, s_ref, dy_f, dg_f, db_f, N, H, W, C, 1)
+    assert torch.equal(dy_f, dy_ref) and torch.equal(dg_f, dg_ref) and torch.equal(db_f, db_ref)
 
 
 def test_avgpool():

@@ -77,7 +77,9 @@ def trunk_only(N=4, size=64):
     def spy(name, *args):
         orig_call(name, *args)
         if name == "b2n_bn_bwd_apply":
-            trace.append(("dy", args[7].clone(), args[0].clone()))
+            trace.append(("dy", args[9].clone(), args[0].clone()))
+        if name == "b2n_pool_bn_bwd_apply":
+            trace.append(("dy", args[9].clone(), args[0].clone()))
     T.call = spy
     (e * R.cuda()).sum().backward()
     T.call = orig_call
