@@ -208,6 +208,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
 
 // ------------------------------------------------------------------ wgrad
 #include "conv_wgrad.cuh"
+#include "conv_wgrad_halo.cuh"
 
 namespace b2n {
 
@@ -230,6 +231,53 @@ static int launch_wgrad_variant(const CUtensorMap& mx, const CUtensorMap& mdy,
   return 0;
 }
 
+template <int NACC, int STAGES>
+static int launch_wgrad_halo_variant(const CUtensorMap& mx, const CUtensorMap& mdy,
+                                     const WgradHaloParams& p, int grid, cudaStream_t stream) {
+  using L = WgradHaloSmem<NACC, STAGES>;
+  static_assert(L::TOTAL <= kMaxDynSmem, "wgrad halo stage ring too large");
+  auto kern = conv_wgrad_halo_kernel<NACC, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return set_error("wgrad halo: cudaFuncSetAttribute(%d B): %s", L::TOTAL,
+                                           cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, kWgradHaloThreads, L::TOTAL, stream>>>(mx, mdy, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("wgrad halo launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Tap-sharing variant (conv_wgrad_halo.cuh): stride-1 same-width convs with 64 output channels
+// whose R * Cin/32 accumulators fit TMEM -- layer1's 3x3 convs (6) and the 4x4 s2d stem (4).
+static int launch_wgrad_halo(const WgradArgs& a, int P, int Q, cudaStream_t stream) {
+  WgradHaloParams p;
+  p.P = P; p.Q = Q; p.Cin = a.Cin; p.R = a.R; p.S = a.S;
+  p.pad_h = a.pad_h_lo; p.pad_w = a.pad_w_lo;
+  p.Ktot = a.R * a.S * a.Cin;
+  p.nacc = a.R * (a.Cin / 32);
+  const long long positions = 1ll * a.N * P * (Q + a.S - 1);
+  if (positions > 2000000000ll) return set_error("wgrad: too many pixels");
+  p.slabs_total = (int)((positions + kWhPX - 1) / kWhPX);
+  p.dw = a.dw;
+  CUtensorMap mx, mdy;
+  // X: S = 1 with the pad columns inside the bounding box -> traversal = padded-width raster
+  if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.Cin, a.R, 1, a.pad_h_lo, a.pad_h_hi,
+                      a.pad_w_lo, a.pad_w_hi, 1, 32, kWhPX + a.S - 1, kSwizzle128Atom32))
+    return set_error("wgrad: %s", tmap_last_error());
+  // dY on the same raster: S - 1 zero-filled positions after the last column of every row
+  if (make_im2col_map(&mdy, a.dy, kF32, a.N, P, Q, a.Cout, 1, 1, 0, 0, 0, a.S - 1, 1, 32, kWhPX,
+                      kSwizzle128Atom32))
+    return set_error("wgrad: %s", tmap_last_error());
+  int grid = a.force_splits > 0 ? a.force_splits : device_sm_count();
+  if (grid > p.slabs_total) grid = p.slabs_total;
+  if (p.nacc <= 4) return launch_wgrad_halo_variant<4, 4>(mx, mdy, p, grid, stream);
+  return launch_wgrad_halo_variant<6, 3>(mx, mdy, p, grid, stream);
+}
+
 int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   if (a.Cin % 32 != 0) return set_error("wgrad: Cin=%d must be a multiple of 32", a.Cin);
   if (a.Cout % 64 != 0) return set_error("wgrad: Cout=%d must be a multiple of 64", a.Cout);
@@ -238,6 +286,9 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("wgrad: empty problem");
   const long long M = 1ll * a.N * P * Q;
   if (M > 2000000000ll) return set_error("wgrad: too many pixels");
+  if (a.stride == 1 && a.Cout == 64 && a.S >= 2 && a.S <= 4 && a.pad_w_lo + a.pad_w_hi == a.S - 1 &&
+      a.R * (a.Cin / 32) <= 6 && !a.no_halo && getenv("B2N_NO_HALO") == nullptr)
+    return launch_wgrad_halo(a, P, Q, stream);
   const int block_n = a.Cout % 256 == 0 ? 256 : (a.Cout % 128 == 0 ? 128 : 64);
 
   WgradParams p;

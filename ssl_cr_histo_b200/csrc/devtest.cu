@@ -61,6 +61,10 @@ static const Case kCases[] = {
     {"fwd 4x4 s1 pad(2,1) C32->64 HALO (4 taps/box)", 0, 3, 20, 18, 32, 64, 4, 4, 1, 2, 1, 0, 0},
     {"fwd 4x4 s1 pad(2,1) C8->64 HALO 32-byte rows", 0, 3, 20, 18, 8, 64, 4, 4, 1, 2, 1, 0, 0},
     {"fwd 3x3 s1 C8->64 56x56 N2 HALO 32-byte rows", 0, 2, 56, 56, 8, 64, 3, 3, 1, 1, 1, 1, 0},
+    {"wgrad 3x3 s1 C64->64 56x56 N2 per-tap boxes", 1, 2, 56, 56, 64, 64, 3, 3, 1, 1, 1, 0, -1},
+    {"wgrad 3x3 s1 C64->64 13x9 N5 HALO odd sizes", 1, 5, 13, 9, 64, 64, 3, 3, 1, 1, 1, 0, 0},
+    {"wgrad 3x3 s1 C32->64 7x7 N3 HALO one CTA", 1, 3, 7, 7, 32, 64, 3, 3, 1, 1, 1, 0, 1},
+    {"wgrad 4x4 pad(2,1) C32->64 20x18 N3 HALO", 1, 3, 20, 18, 32, 64, 4, 4, 1, 2, 1, 0, 0},
 };
 static const int kNumCases = sizeof(kCases) / sizeof(kCases[0]);
 
@@ -234,7 +238,8 @@ static int run_wgrad(const Case& c) {
   a.N = c.N; a.H = c.H; a.W = c.W; a.Cin = c.Cin; a.Cout = c.Cout; a.R = c.R; a.S = c.S;
   a.stride = c.stride;
   a.pad_h_lo = a.pad_w_lo = c.plo; a.pad_h_hi = a.pad_w_hi = c.phi;
-  a.force_splits = c.force;
+  a.force_splits = c.force > 0 ? c.force : 0;
+  a.no_halo = c.force == -1;
   if (launch_wgrad(a, 0)) { printf("   launch_wgrad error: %s\n", last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("   kernel failed: %s\n", cudaGetErrorString(e)); return 1; }

@@ -53,6 +53,7 @@ struct WgradArgs {
   int N = 0, H = 0, W = 0, Cin = 0, Cout = 0, R = 0, S = 0, stride = 1;
   int pad_h_lo = 0, pad_h_hi = 0, pad_w_lo = 0, pad_w_hi = 0;
   int force_splits = 0;  // 0 = heuristic
+  int no_halo = 0;       // force the one-box-per-tap kernel (tests)
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t stream);
 

@@ -268,144 +268,182 @@ int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const flo
 
 // --------------------------------- fused maxpool + ReLU + BatchNorm backward (the stem's tail)
 // The stem's BN output is 1/3 of all conv-output elements of the trunk, so materialising
-// gz = d(maxpool o relu) first and then running the generic two-pass BN backward over it costs
-// three extra sweeps of that tensor.  These two kernels rebuild gz on the fly from the pooled
-// gradient and the recorded argmax (the same gather as maxpool_relu_bwd_kernel):
-//   reduce: sums[0][c] += sum gz, sums[1][c] += sum gz * xhat
-//   apply : dy = gamma*invstd*(gz - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0
-__device__ __forceinline__ float4 pooled_grad_at(const float4* __restrict__ ga,
-                                                 const uchar4* __restrict__ idx, int n, int h, int w,
-                                                 int P, int Q, int C4, int c4) {
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int p_lo = h >> 1, p_hi = (h + 1) >> 1;  // windows with 2p-1 <= h <= 2p+1
-  const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
-  for (int p = p_lo; p <= p_hi; ++p) {
-    if (p >= P) continue;
-    const int r = h - (2 * p - 1);
-    for (int q = q_lo; q <= q_hi; ++q) {
-      if (q >= Q) continue;
-      const unsigned char code = static_cast<unsigned char>(r * 3 + (w - (2 * q - 1)));
-      const size_t o = ((static_cast<size_t>(n) * P + p) * Q + q) * C4 + c4;
-      const uchar4 id = idx[o];
-      const float4 g = ga[o];
-      if (id.x == code) acc[0] += g.x;
-      if (id.y == code) acc[1] += g.y;
-      if (id.z == code) acc[2] += g.z;
-      if (id.w == code) acc[3] += g.w;
-    }
-  }
-  return make_float4(acc[0], acc[1], acc[2], acc[3]);
-}
+// gz = d(maxpool o relu) and then running the generic two-pass BN backward over it costs three
+// extra sweeps of that tensor.  Here gz never exists in memory: a block owns a band of two image
+// rows (2b, 2b+1), stages the pooled gradients and recorded argmax codes of pooled rows b and b+1
+// (the only rows whose 3x3/s2 windows reach the band) in shared memory, and sweeps the band once
+// against y, rebuilding gz per position from its (at most four) candidate windows in the same
+// order as maxpool_relu_bwd_kernel:
+//   reduce: sums[0][c] += sum gz', sums[1][c] += sum gz' * xhat       (gz' = gz * [scale*y+shift > 0])
+//   apply : dy = gamma*invstd*(gz' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0
+// Blocks are persistent over bands, so the reduce pass issues one atomic per channel per block.
+constexpr int kBandThreads = 256;
 
-// threadIdx.x -> float4 channel group (C/4), threadIdx.y -> pixel lane; one block = a pixel range
-__global__ void pool_bn_bwd_reduce_kernel(const float4* __restrict__ ga, const uchar4* __restrict__ idx,
-                                          const float4* __restrict__ y, const float* __restrict__ scale,
-                                          const float* __restrict__ shift, const float* __restrict__ mean,
-                                          const float* __restrict__ invstd, double* __restrict__ sums,
-                                          int N, int H, int W, int P, int Q, int C,
-                                          long long pix_per_block) {
-  extern __shared__ float red[];  // [blockDim.y][C][2]
-  const int c4 = threadIdx.x, C4 = C >> 2;
-  const long long pixels = static_cast<long long>(N) * H * W;
-  const long long r0 = static_cast<long long>(blockIdx.x) * pix_per_block;
-  long long r1 = r0 + pix_per_block;
-  if (r1 > pixels) r1 = pixels;
-  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+template <bool APPLY, bool ROUND>
+__global__ void __launch_bounds__(kBandThreads, 3)
+pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict__ idx,
+                        const float4* __restrict__ y, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        double* __restrict__ sums, float4* __restrict__ dy, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int N, int H, int W, int P, int Q, int C,
+                        double inv_count) {
+  extern __shared__ float smem_f[];  // pooled gradients [2][Q][C] fp32 | argmax codes [2][Q][C] u8
+  float4* g_s = reinterpret_cast<float4*>(smem_f);
+  uchar4* id_s = reinterpret_cast<uchar4*>(smem_f + 2 * Q * C);
+  const int tid = threadIdx.x;
+  const int C4 = C >> 2;
+  const int c4 = tid % C4;  // constant per thread: kBandThreads % C4 == 0
+  const int HB = (H + 1) >> 1;
+  const int nbands = N * HB;
+
   const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
   const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
   const float4 mu = *reinterpret_cast<const float4*>(mean + 4 * c4);
   const float4 is = *reinterpret_cast<const float4*>(invstd + 4 * c4);
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    const int w = static_cast<int>(r % W);
-    const int h = static_cast<int>((r / W) % H);
-    const int n = static_cast<int>(r / (static_cast<long long>(W) * H));
-    const float4 v = y[static_cast<size_t>(r) * C4 + c4];
-    float4 g = pooled_grad_at(ga, idx, n, h, w, P, Q, C4, c4);
-    g.x = fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
-    g.y = fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
-    g.z = fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
-    g.w = fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
-    s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
-    s2.x += g.x * (v.x - mu.x) * is.x; s2.y += g.y * (v.y - mu.y) * is.y;
-    s2.z += g.z * (v.z - mu.z) * is.z; s2.w += g.w * (v.w - mu.w) * is.w;
+  float4 m1 = make_float4(0, 0, 0, 0), m2 = m1, gi = m1;
+  if (APPLY) {
+    const int c = 4 * c4;
+    m1 = make_float4(static_cast<float>(sums[c] * inv_count), static_cast<float>(sums[c + 1] * inv_count),
+                     static_cast<float>(sums[c + 2] * inv_count), static_cast<float>(sums[c + 3] * inv_count));
+    m2 = make_float4(static_cast<float>(sums[C + c] * inv_count), static_cast<float>(sums[C + c + 1] * inv_count),
+                     static_cast<float>(sums[C + c + 2] * inv_count), static_cast<float>(sums[C + c + 3] * inv_count));
+    const float4 ga4 = *reinterpret_cast<const float4*>(gamma + c);
+    gi = make_float4(ga4.x * is.x, ga4.y * is.y, ga4.z * is.z, ga4.w * is.w);
+    if (blockIdx.x == 0 && dgamma != nullptr) {
+      for (int k = tid; k < C; k += kBandThreads) {
+        dbeta[k] = static_cast<float>(sums[k]);
+        dgamma[k] = static_cast<float>(sums[C + k]);
+      }
+    }
   }
-  float* dst = red + (static_cast<size_t>(threadIdx.y) * C + 4 * c4) * 2;
-  dst[0] = s1.x; dst[1] = s2.x; dst[2] = s1.y; dst[3] = s2.y;
-  dst[4] = s1.z; dst[5] = s2.z; dst[6] = s1.w; dst[7] = s2.w;
-  __syncthreads();
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int j = tid; j < 2 * C; j += blockDim.x * blockDim.y) {
-    float acc = 0.f;
-    for (int ry = 0; ry < blockDim.y; ++ry) acc += red[static_cast<size_t>(ry) * 2 * C + j];
-    atomicAdd(&sums[(j & 1) * C + (j >> 1)], static_cast<double>(acc));
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1;
+
+  for (int band = blockIdx.x; band < nbands; band += gridDim.x) {
+    const int n = band / HB, hb = band - n * HB, h0 = 2 * hb;
+    // stage pooled rows hb and hb + 1 (window rows 2p-1 .. 2p+1); code 255 never matches
+#pragma unroll 4
+    for (int e = tid; e < 2 * Q * C4; e += kBandThreads) {
+      const int pr = e / (Q * C4);
+      const int p = hb + pr;
+      const size_t o = (static_cast<size_t>(n) * P + p) * Q * C4 + (e - pr * Q * C4);
+      g_s[e] = p < P ? ga[o] : make_float4(0, 0, 0, 0);
+      id_s[e] = p < P ? idx[o] : make_uchar4(255, 255, 255, 255);
+    }
+    __syncthreads();
+    const int band_n = (h0 + 1 < H ? 2 : 1) * W * C4;  // float4 elements of this band
+    const size_t t0 = (static_cast<size_t>(n) * H + h0) * W * C4;
+    for (int i0 = tid; i0 < band_n; i0 += 4 * kBandThreads) {
+      // four independent loads of y in flight per thread before any of them is consumed
+      float4 vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kBandThreads;
+        vv[u] = i < band_n ? y[t0 + i] : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kBandThreads;
+      if (i >= band_n) break;
+      const int hh = i / (W * C4);
+      const int w = (i - hh * W * C4) / C4;
+      const size_t t = t0 + i;
+      const float4 v = vv[u];
+      // branch-free gather over the four candidate windows (pr, q) in maxpool_relu_bwd_kernel's
+      // order; candidates that do not exist get a code no recorded argmax can equal
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
+#pragma unroll
+      for (int cand = 0; cand < 4; ++cand) {
+        const int pr = cand >> 1;            // row h0: window row hb only; row h0+1: hb, hb+1
+        const int q = (cand & 1) ? q_hi : q_lo;
+        const bool valid = pr <= hh && (!(cand & 1) || q_hi != q_lo) && q < Q;
+        const int code = valid ? (hh + 1 - 2 * pr) * 3 + (w - (2 * q - 1)) : 254;
+        const int slot = (pr * Q + (q < Q ? q : Q - 1)) * C4 + c4;
+        const uchar4 id = id_s[slot];
+        const float4 gq = g_s[slot];
+        acc[0] += id.x == code ? gq.x : 0.f;
+        acc[1] += id.y == code ? gq.y : 0.f;
+        acc[2] += id.z == code ? gq.z : 0.f;
+        acc[3] += id.w == code ? gq.w : 0.f;
+      }
+      float4 g = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      g.x = fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
+      g.y = fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+      g.z = fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
+      g.w = fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+      const float4 xh = make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z,
+                                    (v.w - mu.w) * is.w);
+      if (APPLY) {
+        float4 o = make_float4(gi.x * (g.x - m1.x - xh.x * m2.x), gi.y * (g.y - m1.y - xh.y * m2.y),
+                               gi.z * (g.z - m1.z - xh.z * m2.z), gi.w * (g.w - m1.w - xh.w * m2.w));
+        if (ROUND) o = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
+        dy[t] = o;
+      } else {
+        s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+        s2.x += g.x * xh.x; s2.y += g.y * xh.y; s2.z += g.z * xh.z; s2.w += g.w * xh.w;
+      }
+      }
+    }
+    __syncthreads();
+  }
+  if (!APPLY) {
+    // block reduction over the kBandThreads / C4 threads that share a channel group
+    float* red = smem_f;  // [kBandThreads][8]
+    float* dst = red + tid * 8;
+    dst[0] = s1.x; dst[1] = s1.y; dst[2] = s1.z; dst[3] = s1.w;
+    dst[4] = s2.x; dst[5] = s2.y; dst[6] = s2.z; dst[7] = s2.w;
+    __syncthreads();
+    for (int j = tid; j < 2 * C; j += kBandThreads) {
+      const int which = j / C, c = j - which * C;
+      float acc = 0.f;
+      for (int t = c >> 2; t < kBandThreads; t += C4) acc += red[t * 8 + which * 4 + (c & 3)];
+      atomicAdd(&sums[which * C + c], static_cast<double>(acc));
+    }
   }
 }
 
-template <bool ROUND>
-__global__ void pool_bn_bwd_apply_kernel(const float4* __restrict__ ga, const uchar4* __restrict__ idx,
-                                         const float4* __restrict__ y, const float* __restrict__ scale,
-                                         const float* __restrict__ shift, const float* __restrict__ mean,
-                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                         const double* __restrict__ sums, float4* __restrict__ dy,
-                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
-                                         int H, int W, int P, int Q, int C, double inv_count) {
-  if (blockIdx.x == 0 && dgamma != nullptr) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] = static_cast<float>(sums[c]);
-      dgamma[c] = static_cast<float>(sums[C + c]);
-    }
+template <bool APPLY, bool ROUND>
+static int launch_band(const float* ga, const unsigned char* idx, const float* y, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, const float* gamma,
+                       double* sums, float* dy, float* dgamma, float* dbeta, int N, int H, int W,
+                       int C, cudaStream_t stream) {
+  const int C4 = C / 4;
+  if (C % 4 != 0 || kBandThreads % C4 != 0)
+    return set_error("pool_bn_bwd: unsupported C=%d", C);
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  size_t smem = static_cast<size_t>(2) * Q * C * (sizeof(float) + 1);
+  if (smem < kBandThreads * 8 * sizeof(float)) smem = kBandThreads * 8 * sizeof(float);
+  if (smem > 200 * 1024) return set_error("pool_bn_bwd: image row too wide (W=%d, C=%d)", W, C);
+  auto kern = pool_bn_bwd_band_kernel<APPLY, ROUND>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("pool_bn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
   }
-  const int C4 = C >> 2;
-  const size_t total = static_cast<size_t>(N) * H * W * C4;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += stride) {
-    const int c4 = static_cast<int>(t % C4);
-    size_t u = t / C4;
-    const int w = static_cast<int>(u % W); u /= W;
-    const int h = static_cast<int>(u % H);
-    const int n = static_cast<int>(u / H);
-    const float4 v = y[t];
-    const float4 g = pooled_grad_at(ga, idx, n, h, w, P, Q, C4, c4);
-    const int c = 4 * c4;
-    const float gg[4] = {g.x, g.y, g.z, g.w};
-    const float yy[4] = {v.x, v.y, v.z, v.w};
-    float o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gk = fmaf(yy[k], scale[c + k], shift[c + k]) > 0.f ? gg[k] : 0.f;
-      const float m1 = static_cast<float>(sums[c + k] * inv_count);
-      const float m2 = static_cast<float>(sums[C + c + k] * inv_count);
-      const float xh = (yy[k] - mean[c + k]) * invstd[c + k];
-      const float r = gamma[c + k] * invstd[c + k] * (gk - m1 - xh * m2);
-      o[k] = ROUND ? tf32_rn(r) : r;
-    }
-    dy[t] = make_float4(o[0], o[1], o[2], o[3]);
-  }
+  const int nbands = N * ((H + 1) / 2);
+  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int grid = device_sm_count() * per_sm;
+  if (grid > nbands) grid = nbands;
+  const double inv_count = 1.0 / (static_cast<double>(N) * H * W);
+  kern<<<grid, kBandThreads, smem, stream>>>(
+      reinterpret_cast<const float4*>(ga), reinterpret_cast<const uchar4*>(idx),
+      reinterpret_cast<const float4*>(y), scale, shift, mean, invstd, gamma, sums,
+      reinterpret_cast<float4*>(dy), dgamma, dbeta, N, H, W, P, Q, C, inv_count);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("pool_bn_bwd: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int launch_pool_bn_bwd_reduce(const float* ga, const unsigned char* idx, const float* y,
                               const float* scale, const float* shift, const float* mean,
                               const float* invstd, double* sums, int N, int H, int W, int C,
                               cudaStream_t stream) {
-  if (C % 4 != 0 || C > 1024) return set_error("pool_bn_bwd_reduce: unsupported C=%d", C);
-  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  const int C4 = C / 4;
-  int ty = 256 / C4;
-  if (ty < 1) ty = 1;
-  if (ty > 16) ty = 16;
-  const long long pixels = static_cast<long long>(N) * H * W;
-  const int target_blocks = device_sm_count() * 8;
-  long long ppb = (pixels + target_blocks - 1) / target_blocks;
-  if (ppb < 4LL * ty) ppb = 4LL * ty;
-  const int blocks = static_cast<int>((pixels + ppb - 1) / ppb);
-  pool_bn_bwd_reduce_kernel<<<blocks, dim3(C4, ty), static_cast<size_t>(ty) * C * 2 * sizeof(float),
-                              stream>>>(
-      reinterpret_cast<const float4*>(ga), reinterpret_cast<const uchar4*>(idx),
-      reinterpret_cast<const float4*>(y), scale, shift, mean, invstd, sums, N, H, W, P, Q, C, ppb);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("pool_bn_bwd_reduce: %s", cudaGetErrorString(e));
-  return 0;
+  return launch_band<false, false>(ga, idx, y, scale, shift, mean, invstd, nullptr, sums, nullptr,
+                                   nullptr, nullptr, N, H, W, C, stream);
 }
 
 int launch_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const float* y,
@@ -413,25 +451,12 @@ int launch_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const fl
                              const float* invstd, const float* gamma, const double* sums, float* dy,
                              float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
                              cudaStream_t stream) {
-  if (C % 4 != 0) return set_error("pool_bn_bwd_apply: C %% 4 != 0");
-  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  const size_t total = static_cast<size_t>(N) * H * W * (C / 4);
-  const double inv_count = 1.0 / (static_cast<double>(N) * H * W);
-  auto a4 = reinterpret_cast<const float4*>(ga);
-  auto i4 = reinterpret_cast<const uchar4*>(idx);
-  auto y4 = reinterpret_cast<const float4*>(y);
-  auto d4 = reinterpret_cast<float4*>(dy);
+  double* s = const_cast<double*>(sums);  // only read when APPLY
   if (round_tf32)
-    pool_bn_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(
-        a4, i4, y4, scale, shift, mean, invstd, gamma, sums, d4, dgamma, dbeta, N, H, W, P, Q, C,
-        inv_count);
-  else
-    pool_bn_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(
-        a4, i4, y4, scale, shift, mean, invstd, gamma, sums, d4, dgamma, dbeta, N, H, W, P, Q, C,
-        inv_count);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("pool_bn_bwd_apply: %s", cudaGetErrorString(e));
-  return 0;
+    return launch_band<true, true>(ga, idx, y, scale, shift, mean, invstd, gamma, s, dy, dgamma, dbeta,
+                                   N, H, W, C, stream);
+  return launch_band<true, false>(ga, idx, y, scale, shift, mean, invstd, gamma, s, dy, dgamma, dbeta,
+                                  N, H, W, C, stream);
 }
 
 // ------------------------------------------------------------ global avg-pool

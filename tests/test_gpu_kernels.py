@@ -368,7 +368,11 @@ def test_bn_relu_maxpool_forward_backward(shape):
     dy_f, dg_f, db_f = torch.empty_like(yd), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
     call("b2n_pool_bn_bwd_apply", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), mean,
          invstd, gamma, s_ref, dy_f, dg_f, db_f, N, H, W, C, 1)
-    assert torch.equal(dy_f, dy_ref) and torch.equal(dg_f, dg_ref) and torch.equal(db_f, db_ref)
+    # (a position picked by 3-4 windows sums their gradients in scatter order: a last-bit
+    # difference there can move the TF32 rounding of dy by one TF32 ulp = 2^-11 relative)
+    assert torch.allclose(dy_f, dy_ref, rtol=1e-3, atol=1e-6 * float(dy_ref.abs().max()))
+    assert float((dy_f != dy_ref).float().mean()) < 1e-3
+    assert torch.equal(dg_f, dg_ref) and torch.equal(db_f, db_ref)
 
 
 def test_avgpool():
