@@ -45,10 +45,13 @@ int b2n_device_ok(void);
  *   - error-compensated forward mode (x_h, x_l, w_h, w_l given; x = w_packed = NULL): both
  *     operands are (hi, lo) pairs of FP16 tensors, hi = fp16(v), lo = fp16(v - hi); the kernel
  *     accumulates hi*hi + lo*hi + hi*lo (kind::f16) -- FP32-grade results.  Cin = 32 or a
- *     multiple of 64.
+ *     multiple of 64; Cin = 16 for stride-1 same-width convs with Cout = 64 (the stem).
  *   - plain mode (x, w_packed given; halves NULL): one TF32 pass over fp32 containers (data
  *     gradients, with a b2n_pack_weight_dgrad pack).  Cin a multiple of 32.
- * epilogue: v = acc; v = v*scale[k] (if scale); v += shift[k] (if shift);
+ * Stride-1 same-width convs with Cout = 64 whose packed weights fit in shared memory (layer1's
+ * 3x3 convs, the 4x4 stem) run a tap-sharing variant: one activation box per filter row, the
+ * horizontal taps read through row-shifted UMMA descriptors (same results, ~3x less L2 traffic).
+ * epilogue: v = acc; v = v*scale[k] + shift[k] (scale and shift come as a pair);
  *           v += resid[..] (fp32; only where mask[..] > 0 if mask); v += resid_h + resid_l (FP16
  *           pair); relu; then y (fp32, TF32-rounded if round_tf32) and / or the (hi, lo) FP16 pair
  *           y_h / y_l are stored.
@@ -56,8 +59,9 @@ int b2n_device_ok(void);
  * goes to (o_h0 + i*o_step, o_w0 + j*o_step) of an [N,o_H,o_W,Cout] tensor (resid / mask are
  * addressed the same way; pixels outside are dropped) -- the parity classes of a stride-2 data
  * gradient (b2n_pack_weight_dgrad_s2).
- * stats (optional, [2][Cout] doubles, caller-zeroed): += per-channel sum / sum of squares of
- * the raw accumulator -- the BatchNorm batch statistics.  Cout a multiple of 64.
+ * stats (optional, [2][Cout] doubles, caller-zeroed; not together with scale/shift): += per-channel
+ * sum / sum of squares of the raw accumulator -- the BatchNorm batch statistics.  Cout a multiple
+ * of 64.
  * Replaces: tv:92,96,100 (conv3x3 / downsample conv in BasicBlock.forward), tv:268 (stem, via
  * the space-to-depth view), and the conv dgrad reached from loss.backward()
  * (pretrain_BreastPathQ.py:60, eval_BreastPathQ_SSL_CR.py:99). */
@@ -72,7 +76,9 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
 
 /* Weight gradient, split-K over pixels, accumulated atomically:
  *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
- * dw_packed must be zeroed by the caller.  Replaces cudnnConvolutionBackwardFilter reached from
+ * dw_packed must be zeroed by the caller.  Cin a multiple of 32, Cout a multiple of 64.  Stride-1
+ * same-width convs with Cout = 64 and R*Cin/32 <= 6 (layer1, the stem) run the tap-sharing kernel
+ * in which one CTA owns all of dW for a slab of pixels.  Replaces cudnnConvolutionBackwardFilter reached from
  * loss.backward() (pretrain_BreastPathQ.py:60). */
 int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
                    int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,

@@ -122,7 +122,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
   constexpr uint32_t SBO = 8 * KBYTES;  // 8 rows of one swizzle atom
-  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // STACK: the hi and lo weight tiles sit back to back in shared memory, so hi*hi and hi*lo are ONE
+  // MMA of width 2*BLOCK_N over [W_hi ; W_lo] into two accumulator halves (summed by the epilogue)
+  // and lo*hi a second one into the first half.  The activation tile is then fetched twice instead
+  // of three times per K step -- UMMA operand reads share the SM's 128 B/clk shared-memory port
+  // with the TMA writes, and that port, not the tensor pipe, bounds the narrow (N <= 128) tiles.
+  constexpr bool STACK = SPLIT && BLOCK_N <= 128;
+  constexpr int ACC_COLS = STACK ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns of one accumulator stage
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   // streamed stage layout: A_hi | A_lo | B_hi | B_lo   (B part absent when RES_B)
   constexpr int OFF_A_LO = L::A_BYTES;
   constexpr int OFF_B = L::PLANES * L::A_BYTES;
@@ -144,7 +151,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* bres_bar = tempty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   uint8_t* smem = base + L::CTRL_BYTES;            // activation (+ weight) ring
-  uint8_t* resb = smem + L::RING_BYTES;          // resident weights: [plane][k step][B tile]
+  uint8_t* resb = smem + L::RING_BYTES;          // resident weights: [k step][plane][B tile]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,9 +194,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       // whole weight matrix (num_n_tiles == 1), one barrier for all of it
       mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(num_k_steps) * L::PLANES * L::B_BYTES);
       for (int ks = 0; ks < num_k_steps; ++ks) {
-        tma_load_2d(resb + ks * L::B_BYTES, &map_b, bres_bar, ks * KELEMS, 0);
+        tma_load_2d(resb + ks * L::PLANES * L::B_BYTES, &map_b, bres_bar, ks * KELEMS, 0);
         if (SPLIT)
-          tma_load_2d(resb + (num_k_steps + ks) * L::B_BYTES, &map_b_lo, bres_bar, ks * KELEMS, 0);
+          tma_load_2d(resb + (ks * L::PLANES + 1) * L::B_BYTES, &map_b_lo, bres_bar, ks * KELEMS, 0);
       }
     }
     __syncwarp();
@@ -277,6 +284,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     // registers) and a descriptor is one 32-bit add on a precomputed template.
     constexpr uint32_t idesc =
         SPLIT ? make_idesc_f16(kBlockM, BLOCK_N) : make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc_f16(kBlockM, STACK ? 2 * BLOCK_N : BLOCK_N);
     const uint64_t desc0 = make_smem_desc(0, 16, SBO, SWZ);  // address field filled per MMA
     const uint32_t ring16 = smem_u32(smem) >> 4;             // all offsets in 16-byte units
     const uint32_t resb16 = smem_u32(resb) >> 4;
@@ -288,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       if (HALO) {
         const int nstages = p.R * p.kslices;
         int r = 0, cs = 0;
@@ -304,14 +312,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               // 128B swizzle is a function of the absolute smem address (measured: the shifted
               // descriptor reads correctly with base_offset = 0, not with base_offset = s).
               const int ks = (r * p.S + s) * p.kslices + cs;
-              const uint32_t b16 = resb16 + ks * (L::B_BYTES >> 4);
-              const uint32_t bl16 = resb16 + (num_k_steps + ks) * (L::B_BYTES >> 4);
+              const uint32_t b16 = resb16 + ks * (L::PLANES * L::B_BYTES >> 4);
+              const uint32_t bl16 = b16 + (L::B_BYTES >> 4);
 #pragma unroll
               for (int j = 0; j < MMAS_PER_STAGE; ++j) {
                 const uint64_t da = desc0 + (a16 + (KBYTES / 16) * s + 2 * j);
                 const uint64_t db = desc0 + (b16 + 2 * j);
                 const uint32_t accum = (si | s | j) != 0 ? 1u : 0u;
-                if (SPLIT) {
+                if (STACK) {
+                  umma_f16(d_tmem, da, db, idesc2, accum);  // [hi*hi | hi*lo]
+                  if (!skip_a_lo)
+                    umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + (KBYTES / 16) * s + 2 * j), db, idesc, 1u);
+                } else if (SPLIT) {
                   umma_f16(d_tmem, da, db, idesc, accum);
                   umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
                   if (!skip_a_lo)
@@ -334,14 +346,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
-          const uint32_t b16 = RES_B ? resb16 + ks * (L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
-          const uint32_t bl16 = RES_B ? resb16 + (num_k_steps + ks) * (L::B_BYTES >> 4)
-                                      : a16 + (OFF_B_LO >> 4);
+          const uint32_t b16 =
+              RES_B ? resb16 + ks * (L::PLANES * L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
+          const uint32_t bl16 = b16 + (L::B_BYTES >> 4);  // lo tile follows hi in both layouts
 #pragma unroll
           for (int j = 0; j < MMAS_PER_STAGE; ++j) {
             const uint64_t da = desc0 + (a16 + 2 * j);
             const uint64_t db = desc0 + (b16 + 2 * j);
-            if (SPLIT) {
+            if (STACK) {
+              umma_f16(d_tmem, da, db, idesc2, (ks | j) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
+              if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
+            } else if (SPLIT) {
               umma_f16(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
               umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
               if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
@@ -438,13 +453,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
       };
-      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
       auto process = [&](int ch, const float4(&pre_r)[8], const float4(&pre_m)[8],
                          const uint2(&pre_h)[8], const uint2(&pre_l)[8]) {
         float v[32];
         tmem_ld_32x32(t_addr + ch * 32, v);
         const int n0 = n_tile * BLOCK_N + ch * 32;
         const int c4 = n0 + 4 * (lane & 7);
+        if (STACK) {  // second accumulator half: the hi * W_lo products
+          float v2[32];
+          tmem_ld_32x32(t_addr + BLOCK_N + ch * 32, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        }
         tmem_ld_wait();
         // per-channel affine while a thread still owns a whole row of the chunk
         if (f_affine) {
