@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--e2e-fp32", action="store_true",
+                    help="e2e arm ships fp32 patches (the reference loop's format) instead of uint8")
     return ap.parse_args()
 
 
@@ -173,10 +175,19 @@ def run_b200(args):
         g = torch.Generator().manual_seed(sd)
         return torch.randint(0, 256, (n, 3, S, S), dtype=torch.uint8, generator=g).float()
 
-    host = [patches_u8(n, seed + i).pin_memory() for i, n in enumerate((nx, nu, nu))]
+    host = [patches_u8(n, seed + i) for i, n in enumerate((nx, nu, nu))]
     host_t = torch.rand(nx, generator=torch.Generator().manual_seed(seed + 7)).pin_memory()
+    # `value`: fp32 patches resident in HBM, exactly what the reference's loop holds after its
+    # .float() / .cuda() (eval_BreastPathQ_SSL_CR.py:68-71)
     resident = [h.to(dev) for h in host] + [host_t.to(dev)]
-    h2d_bytes = sum(h.numel() * 4 for h in host) + host_t.numel() * 4
+    # `e2e`: the patches travel as the uint8 pixels the dataset holds (dataset.py:65-67); the
+    # trunk's stem pack kernel does the cast on the device (4x fewer PCIe bytes than shipping the
+    # loop's fp32 copy).  --e2e-fp32 ships fp32 instead.
+    if args.e2e_fp32:
+        host = [h.pin_memory() for h in host]
+    else:
+        host = [h.to(torch.uint8).pin_memory() for h in host]
+    h2d_bytes = sum(h.numel() * h.element_size() for h in host) + host_t.numel() * 4
 
     def step(ix, iw, is_, tx):
         with torch.no_grad():
@@ -198,7 +209,7 @@ def run_b200(args):
     # the copy of step i+1 is issued on a side stream while step i computes (two device-side
     # input slots); the loss of every step is read back on the host (:103).
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [[torch.empty_like(r) for r in resident] for _ in range(2)]
+    slots = [[torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host + [host_t]] for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"i": 0, "primed": False}
@@ -302,7 +313,9 @@ def run_b200(args):
                    "unique_patches_per_step_per_rank": nx + nu, "optimizer": "Adam(1e-4, wd 1e-4)",
                    "parallelism": "dp%d, one NCCL all-reduce of %.1f MB grads/step" % (
                        world, reducer.nbytes / 1e6) if reducer else "single GPU",
-                   "l2": "inputs (%.0f MB/step) larger than the 126 MB L2" % (h2d_bytes / 1e6)},
+                   "l2": "inputs (%.0f MB/step fp32) larger than the 126 MB L2"
+                         % (sum(r.numel() * 4 for r in resident) / 1e6),
+                   "e2e_input_format": "fp32 NCHW" if args.e2e_fp32 else "uint8 NCHW (cast in the stem kernel)"},
         "algorithmic_tflops": alg_flops * args.steps / (ms * 1e-3) / 1e12,
         "e2e": {"value": patches * args.steps / (ms_e2e * 1e-3), "unit": "patches/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -102,6 +102,11 @@ int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int
 int b2n_stem_pack_input(const float* x_nchw, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
                         int* xs_l_nonzero /* optional, caller-zeroed: set to 1 if any lo != 0 */,
                         int N, int H, int W, void* stream);
+/* Same for uint8 pixels (the patches as the dataset holds them, dataset.py:65-67, before the
+ * loop's .float()): 4x fewer host->device bytes.  uint8 values are exact in FP16, so there is no
+ * lo plane: pass the conv a zeroed x_l_nonzero flag and any valid pointer as x_l. */
+int b2n_stem_pack_input_u8(const unsigned char* x_nchw, b2n_half* xs_h, float* xs32, int N, int H,
+                           int W, void* stream);
 /* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16 taps * 16];  packed gradient [K][16 taps * 32] ->
  * (K,3,7,7). */
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream);

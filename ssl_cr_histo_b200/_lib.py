@@ -26,6 +26,7 @@ _SIGNATURES = {
     "b2n_pack_weight_dgrad_s2": [P, P, I, I],
     "b2n_unpack_wgrad": [P, P, I, I, I, I],
     "b2n_stem_pack_input": [P, P, P, P, P, I, I, I],
+    "b2n_stem_pack_input_u8": [P, P, P, I, I, I],
     "b2n_stem_pack_weight": [P, P, P, I],
     "b2n_stem_unpack_wgrad": [P, P, I],
     "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],

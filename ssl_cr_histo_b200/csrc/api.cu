@@ -87,6 +87,10 @@ int b2n_stem_pack_input(const float* x, b2n_half* xs_h, b2n_half* xs_l, float* x
   return counted(launch_stem_pack_input(x, H16(xs_h), H16(xs_l), xs32, xs_l_nonzero, N, H, W,
                                         S(stream)));
 }
+int b2n_stem_pack_input_u8(const unsigned char* x, b2n_half* xs_h, float* xs32, int N, int H, int W,
+                           void* stream) {
+  return counted(launch_stem_pack_input_u8(x, H16(xs_h), xs32, N, H, W, S(stream)));
+}
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream) {
   return counted(launch_stem_pack_weight(w, H16(ws_h), H16(ws_l), K, S(stream)));
 }

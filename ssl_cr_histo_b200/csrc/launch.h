@@ -80,6 +80,8 @@ int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H,
                          cudaStream_t stream);
 int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
                            int* lo_nonzero, int N, int H, int W, cudaStream_t stream);
+int launch_stem_pack_input_u8(const unsigned char* x, __half* xs_h, float* xs32, int N, int H, int W,
+                              cudaStream_t stream);
 int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
                             cudaStream_t stream);
 int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream);

@@ -19,12 +19,27 @@ namespace b2n {
 constexpr int kStemC = 32;   // channels of the fp32 (weight-gradient) copy
 constexpr int kStemC16 = 16; // channels of the FP16 (forward) pair
 
-// x: NCHW fp32 (N,3,H,W), H and W even.  Outputs NHWC: the (hi, lo) FP16 pair (N,H/2,W/2,16) for
-// the forward conv and, when xs32 is given, the TF32-rounded fp32 copy (N,H/2,W/2,32) the weight
-// gradient reads.
-__global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __restrict__ xs_h,
+// x: NCHW (N,3,H,W), H and W even, fp32 or uint8 pixels.  Outputs NHWC: the (hi, lo) FP16 pair
+// (N,H/2,W/2,16) for the forward conv and, when xs32 is given, the TF32-rounded fp32 copy
+// (N,H/2,W/2,32) the weight gradient reads.  uint8 pixels are exact in fp16: their lo plane is
+// identically zero and is neither written nor (lo_nonzero stays 0) read by the conv.
+template <typename T>
+__device__ __forceinline__ float2 load_px2(const T* p);
+template <>
+__device__ __forceinline__ float2 load_px2<float>(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
+template <>
+__device__ __forceinline__ float2 load_px2<unsigned char>(const unsigned char* p) {
+  const uchar2 v = *reinterpret_cast<const uchar2*>(p);
+  return make_float2(static_cast<float>(v.x), static_cast<float>(v.y));
+}
+
+template <typename T>
+__global__ void stem_pack_input_kernel(const T* __restrict__ x, uint4* __restrict__ xs_h,
                                        uint4* __restrict__ xs_l, float4* __restrict__ xs32,
                                        int* __restrict__ lo_nonzero, int N, int H, int W) {
+  constexpr bool kExact = sizeof(T) == 1;
   const int H2 = H >> 1, W2 = W >> 1;
   const size_t total = static_cast<size_t>(N) * H2 * W2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -38,10 +53,10 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __res
     for (int k = 12; k < 16; ++k) v[k] = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float* plane = x + (static_cast<size_t>(n) * 3 + c) * H * W;
+      const T* plane = x + (static_cast<size_t>(n) * 3 + c) * H * W;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
-        const float2 p = *reinterpret_cast<const float2*>(plane + static_cast<size_t>(2 * i + dy) * W + 2 * j);
+        const float2 p = load_px2<T>(plane + static_cast<size_t>(2 * i + dy) * W + 2 * j);
         v[(dy * 2 + 0) * 3 + c] = p.x;
         v[(dy * 2 + 1) * 3 + c] = p.y;
       }
@@ -51,15 +66,17 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, uint4* __res
     __half2* l2 = reinterpret_cast<__half2*>(pl);
 #pragma unroll
     for (int k = 0; k < 8; ++k) split_f16(v[2 * k], v[2 * k + 1], h2[k], l2[k]);
-    // integer-valued images (uint8 patches cast to float, dataset.py:65-67) are exact in fp16:
-    // tell the stem conv it may skip the all-zero lo plane
-    if (lo_nonzero != nullptr && ((pl[0].x | pl[0].y | pl[0].z | pl[0].w | pl[1].x | pl[1].y |
-                                   pl[1].z | pl[1].w) & 0x7fff7fffu) != 0)
-      atomicOr(lo_nonzero, 1);
     uint4* dh = xs_h + t * (kStemC16 / 8);
-    uint4* dl = xs_l + t * (kStemC16 / 8);
     dh[0] = ph[0]; dh[1] = ph[1];
-    dl[0] = pl[0]; dl[1] = pl[1];
+    if (!kExact) {
+      // integer-valued images (uint8 patches cast to float, dataset.py:65-67) are exact in fp16:
+      // tell the stem conv it may skip the all-zero lo plane
+      if (lo_nonzero != nullptr && ((pl[0].x | pl[0].y | pl[0].z | pl[0].w | pl[1].x | pl[1].y |
+                                     pl[1].z | pl[1].w) & 0x7fff7fffu) != 0)
+        atomicOr(lo_nonzero, 1);
+      uint4* dl = xs_l + t * (kStemC16 / 8);
+      dl[0] = pl[0]; dl[1] = pl[1];
+    }
     if (xs32 != nullptr) {
       float4* d = xs32 + t * (kStemC / 4);
       d[0] = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
@@ -101,20 +118,30 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* _
   }
 }
 
-int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
-                           int* lo_nonzero, int N, int H, int W, cudaStream_t stream) {
+template <typename T>
+static int launch_stem_pack_input_t(const T* x, __half* xs_h, __half* xs_l, float* xs32,
+                                    int* lo_nonzero, int N, int H, int W, cudaStream_t stream) {
   if ((H | W) & 1) return set_error("stem_pack_input: H and W must be even (got %dx%d)", H, W);
+  if (sizeof(T) != 1 && xs_l == nullptr) return set_error("stem_pack_input: xs_l is null");
   const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2);
   size_t blocks = (total + 127) / 128;
   const size_t cap = static_cast<size_t>(device_sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  stem_pack_input_kernel<<<(unsigned)blocks, 128, 0, stream>>>(
+  stem_pack_input_kernel<T><<<(unsigned)blocks, 128, 0, stream>>>(
       x, reinterpret_cast<uint4*>(xs_h), reinterpret_cast<uint4*>(xs_l),
       reinterpret_cast<float4*>(xs32), lo_nonzero, N, H, W);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_pack_input: %s", cudaGetErrorString(e));
   return 0;
+}
+int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
+                           int* lo_nonzero, int N, int H, int W, cudaStream_t stream) {
+  return launch_stem_pack_input_t<float>(x, xs_h, xs_l, xs32, lo_nonzero, N, H, W, stream);
+}
+int launch_stem_pack_input_u8(const unsigned char* x, __half* xs_h, float* xs32, int N, int H, int W,
+                              cudaStream_t stream) {
+  return launch_stem_pack_input_t<unsigned char>(x, xs_h, nullptr, xs32, nullptr, N, H, W, stream);
 }
 int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
                             cudaStream_t stream) {

@@ -310,3 +310,28 @@ def test_large_batch_properties():
     for (k, u), (_, v) in zip(a.named_buffers(), b.named_buffers()):
         if u.dtype != torch.long and "running_mean" in k:
             assert max_rel(u, v) <= 1e-4, k
+
+
+def test_uint8_patches_equal_their_float_cast():
+    """The trunk takes the patches as uint8 (what the dataset holds before the loop's .float(),
+    dataset.py:65-67): features, gradients and BN buffers are bit-identical to the fp32 path --
+    the uint8 values are exact in the stem's FP16 operand, whose lo plane is zero either way."""
+    _, _, gm, gh = pair("finetune", ("finetune", 9))
+    gm2, gh2 = copy.deepcopy(gm), copy.deepcopy(gh)
+    xf = O.synthetic_patches(6, 96, seed=70)
+    xu = xf.to(torch.uint8)
+    assert torch.equal(xu.float(), xf)
+    target = torch.tensor([0, 3, 8, 1, 5, 2], device=DEV)
+    gm.train(); gm2.train()
+    lf = F.cross_entropy(gh(gm(xf.to(DEV))), target)
+    lu = F.cross_entropy(gh2(gm2(xu.to(DEV))), target)
+    assert torch.equal(lf, lu)
+    lf.backward(); lu.backward()
+    for (k, p), (_, q) in zip(gm.named_parameters(), gm2.named_parameters()):
+        if k == "model.conv1.weight":       # split-K atomics: summation order varies run to run
+            assert rel_l2(q.grad, p.grad) < 1e-5, k
+    for (k, u), (_, v) in zip(gm.named_buffers(), gm2.named_buffers()):
+        assert torch.equal(u, v), k
+    gm.eval(); gm2.eval()
+    with torch.no_grad():
+        assert torch.equal(gm(xf.to(DEV)), gm2(xu.to(DEV)))
