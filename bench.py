@@ -124,7 +124,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -275,29 +275,47 @@ def run_b200(args):
         except Exception:
             pass
         bf16 = peaks.get("bf16_tflops_sustained")
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 issues at half the bf16 rate)"
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step); "
+                    "TF32 = half of it (TF32 issues at half the bf16 rate, the file has no TF32 line)")
         if bf16 is None:
-            bf16, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) / 2"
-        peak = bf16 / 2.0
+            bf16, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md); TF32 = half"
+        peak16, peak32 = float(bf16), float(bf16) / 2.0
         if os.environ.get("B2N_PROF_DUMP"):
             with open(os.environ["B2N_PROF_DUMP"], "w") as f:
-                json.dump({n: [(round(a.elapsed_time(c) * 1e3, 1), w) for a, c, w in ev]
+                json.dump({n: [(round(a.elapsed_time(c) * 1e3, 1), w[0]) for a, c, w in ev]
                            for n, ev in prof.items()}, f)
-        kern = {}
+        # per group (forward convs / data gradients / weight gradients): time, algorithmic TFLOP/s,
+        # and tensor-pipe utilisation = executed MMA FLOPs of each kind / that kind's peak
+        grp = {}
         for name, ev in prof.items():
-            t = sum(a.elapsed_time(c) for a, c, _ in ev)
-            w = sum(x for _, _, x in ev)
-            kern[name] = {"launches_per_step": len(ev) / 2, "ms_per_step": t / 2,
-                          "tflops": w / (t * 1e-3) / 1e12 if t > 0 else None}
-        dom = kern["b2n_conv_fwd"]
+            for a, c, w in ev:
+                g = grp.setdefault(w[3], {"ms": 0.0, "alg": 0.0, "pipe_s": 0.0, "n": 0})
+                g["ms"] += a.elapsed_time(c)
+                g["alg"] += w[0]
+                g["pipe_s"] += w[1] / (peak16 * 1e12) + w[2] / (peak32 * 1e12)
+                g["n"] += 1
+        step_ms = t_ms / 2
+
+        def summary(keys):
+            ms = sum(grp[k]["ms"] for k in keys)
+            alg = sum(grp[k]["alg"] for k in keys)
+            pipe = sum(grp[k]["pipe_s"] for k in keys)
+            return {"launches_per_step": sum(grp[k]["n"] for k in keys) / 2, "ms_per_step": ms / 2,
+                    "algorithmic_tflops": alg / (ms * 1e-3) / 1e12,
+                    "tensor_pipe_util": pipe / (ms * 1e-3), "share_of_step": (ms / 2) / step_ms}
+
+        dom = summary(["fwd", "dgrad"])
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
-                "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": dom["tflops"] / peak if dom["tflops"] else None, "traffic": None,
-                "peak_source": peak_src, "share_of_step": dom["ms_per_step"] / (t_ms / 2),
+                "achieved": dom["algorithmic_tflops"], "peak": peak32, "unit": "TFLOP/s",
+                "frac": dom["algorithmic_tflops"] / peak32, "traffic": None,
+                "peak_source": peak_src, "share_of_step": dom["share_of_step"],
                 "launches_per_step": dom["launches_per_step"],
-                "wgrad": {"tflops": kern["b2n_conv_wgrad"]["tflops"],
-                          "frac": (kern["b2n_conv_wgrad"]["tflops"] or 0) / peak,
-                          "share_of_step": kern["b2n_conv_wgrad"]["ms_per_step"] / (t_ms / 2)}}
+                # executed MMA math / peak of the MMA kind: the forward issues 3 FP16 MMAs per
+                # product (error compensation), which `frac` (algorithmic FLOPs vs the TF32 peak)
+                # counts once
+                "tensor_pipe_util": dom["tensor_pipe_util"],
+                "forward": summary(["fwd"]), "dgrad": summary(["dgrad"]), "wgrad": summary(["wgrad"]),
+                "peaks_tflops": {"fp16_mma": peak16, "tf32_mma": peak32}}
 
     patches = (nx + nu) * world
     alg_flops = world * (nu * FLOP_FWD + (nx + nu) * (FLOP_FWD + FLOP_BWD))
@@ -305,7 +323,8 @@ def run_b200(args):
         "metric": "224x224 histo patches/sec (consistency step)", "unit": "patches/s",
         "value": patches * args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage and accumulate)",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 (hi,lo) error-compensated forward MMAs + tf32 backward MMAs, fp32 accumulate / storage",
         "data": "synthetic",
         "config": {"workload": "SSL_CR consistency step (eval_BreastPathQ_SSL_CR.py:76-100), MSE/MSE, "
                                "modules_student=0, BASELINE configs[2] per rank",

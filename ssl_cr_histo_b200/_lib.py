@@ -88,11 +88,12 @@ def _conv(a):
 
 # Optional per-kernel timing (bench.py): when PROFILE is a dict, calls whose entry-point name
 # is a key get bracketed by CUDA events on the launching stream; `work` (algorithmic FLOPs or
-# bytes of that launch, supplied by the caller) is accumulated next to them.
+# bytes of that launch -- or a tuple (algorithmic FLOPs, executed FP16-MMA FLOPs, executed
+# TF32-MMA FLOPs, tag) -- supplied by the caller) is recorded next to them.
 PROFILE = None
 
 
-def call(name: str, *args, work: float = 0.0) -> None:
+def call(name: str, *args, work=0.0) -> None:
     """Invoke an entry point on the current CUDA stream; raise on a non-zero return code."""
     lib = load()
     stream = torch.cuda.current_stream().cuda_stream

@@ -189,8 +189,8 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
     """One conv launch.  ``x`` / ``wp`` are either an ``_Act`` and an FP16 (hi, lo) weight pair
     (error-compensated forward) or plain fp32 tensors (single TF32 pass: data gradients).
     ``alg``: algorithmic / executed FLOP ratio of this launch (the stem runs 147 real taps in a
-    512-wide padded reduction; a zero-stuffed stride-2 data gradient executes 4x the useful
-    MACs) -- only used for the roofline accounting in bench.py."""
+    256-wide padded reduction) -- only used for the roofline accounting in bench.py, which gets
+    (algorithmic FLOPs, executed FP16-MMA FLOPs, executed TF32-MMA FLOPs, tag) per launch."""
     S = R if R_w is None else R_w                 # taps / upper padding may differ per axis
     phw = pad_hi if pad_hi_w is None else pad_hi_w
     P = (H + pad_lo + pad_hi - R) // stride + 1
@@ -203,9 +203,14 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
         out = torch.empty(N, P, Q, Cout, device=dev, dtype=torch.float32)
     oh, ol = (out_pair.hi, out_pair.lo) if out_pair is not None else (None, None)
     rh, rl = (resid_pair.hi, resid_pair.lo) if resid_pair is not None else (None, None)
+    nominal = 2.0 * N * P * Q * Cout * R * S * Cin
+    if isinstance(x, _Act):   # hi*hi + hi*lo + lo*hi (the lo plane of integer images is skipped)
+        work = (nominal * alg, nominal * (2.0 if lo_flag is not None else 3.0), 0.0, "fwd")
+    else:
+        work = (nominal * alg, 0.0, nominal, "dgrad")
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, S, stride,
          pad_lo, pad_hi, pad_lo, phw, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
-         lo_flag, *placement, work=2.0 * N * P * Q * Cout * R * S * Cin * alg)
+         lo_flag, *placement, work=work)
     return out
 
 
@@ -384,8 +389,9 @@ class _TrunkFn(torch.autograd.Function):
             K, C, R, S = conv.weight.shape
             dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
             P, Q = dy.shape[1], dy.shape[2]
+            wflops = 2.0 * N * P * Q * K * R * S * C
             call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
-                 work=2.0 * N * P * Q * K * R * S * C)
+                 work=(wflops, 0.0, wflops, "wgrad"))
             dw = torch.empty_like(conv.weight)
             call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
             grads[id(conv.weight)] = dw
@@ -453,7 +459,8 @@ class _TrunkFn(torch.autograd.Function):
             if need[id(trunk.conv1.weight)]:
                 dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
                 call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
-                     work=2.0 * N * H2 * W2 * 64 * 147)
+                     work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
+                           "wgrad"))
                 dw = torch.empty_like(trunk.conv1.weight)
                 call("b2n_stem_unpack_wgrad", dws, dw, 64)
                 grads[id(trunk.conv1.weight)] = dw
