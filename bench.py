@@ -294,7 +294,7 @@ def run_b200(args):
                 g["alg"] += w[0]
                 g["pipe_s"] += w[1] / (peak16 * 1e12) + w[2] / (peak32 * 1e12)
                 g["n"] += 1
-        step_ms = t_ms / 2
+        step_ms = ms / args.steps   # the timed run (the profiled pass is slowed by its own events)
 
         def summary(keys):
             ms = sum(grp[k]["ms"] for k in keys)

@@ -134,7 +134,7 @@ int launch_bn_apply(const float* y, const float* scale, const float* shift, cons
   if (n8 == 0) return 0;
   const int threads = 256;
   size_t blocks = (n8 + threads - 1) / threads;
-  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * elementwise_blocks_per_sm();
   if (blocks > cap) blocks = cap;
 #define B2N_LAUNCH(R, T)                                                                        \
   bn_apply_kernel<R, T><<<(unsigned)blocks, threads, 0, stream>>>(                              \
@@ -322,7 +322,7 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
   const size_t n4 = static_cast<size_t>(rows) * C / 4;
   const int threads = 256;
   size_t blocks = (n4 + threads - 1) / threads;
-  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * elementwise_blocks_per_sm();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const double inv_count = 1.0 / static_cast<double>(rows);
@@ -369,7 +369,7 @@ int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H,
   if (C % 4 != 0) return set_error("upsample_zero: C %% 4 != 0");
   const size_t total = static_cast<size_t>(N) * H * W * (C / 4);
   size_t blocks = (total + 255) / 256;
-  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * elementwise_blocks_per_sm();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   upsample_zero_kernel<<<(unsigned)blocks, 256, 0, stream>>>(

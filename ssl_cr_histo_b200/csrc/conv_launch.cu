@@ -8,6 +8,19 @@
 
 namespace b2n {
 
+// Blocks per SM the grid-stride element-wise kernels are capped at (256 threads each).  Below the
+// 8 that fill an SM's thread slots on purpose: the weight-gradient kernels run on a side stream
+// and can only overlap an HBM-bound element-wise kernel if their 192-thread CTA still finds room.
+int elementwise_blocks_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B2N_EW_BLOCKS_PER_SM");
+    v = e != nullptr ? atoi(e) : 16;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

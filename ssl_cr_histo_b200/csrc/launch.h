@@ -11,6 +11,7 @@ namespace b2n {
 int set_error(const char* fmt, ...);
 const char* last_error();
 int device_sm_count();
+int elementwise_blocks_per_sm();
 
 // Forward-style convolution: out[n,p,q,:] = sum_taps x[n, p*stride - pad_lo + r, ...] * w.
 // x is NHWC fp32 [N,H,W,Cin]; w is packed K-major [Cout][R*S*Cin]; out is NHWC [N,P,Q,Cout].

@@ -257,7 +257,7 @@ __global__ void maxpool_relu_bwd_kernel(const float4* __restrict__ ga, const uch
 
 static unsigned grid_for(size_t total, int threads) {
   size_t blocks = (total + threads - 1) / threads;
-  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * elementwise_blocks_per_sm();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<unsigned>(blocks);

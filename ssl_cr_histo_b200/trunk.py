@@ -12,6 +12,7 @@ next conv's tensor-core operand) are kept for the backward pass.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -148,6 +149,24 @@ class ResNet18Trunk(nn.Module):
 
 
 # ====================================================================== execution
+
+
+# Weight gradients are off the backward pass' critical path (nothing downstream reads them until
+# the optimizer), so they can be enqueued on a side stream where the tensor-core wgrad kernels
+# overlap the HBM-bound BatchNorm-backward kernels of the layers below.  Opt-in
+# (B2N_OVERLAP_WGRAD=1): on the power-capped B200s measured here it gained 0.3-0.9 ms of a 39 ms
+# step on average but produced occasional +3..+20 ms outliers (two persistent 1-CTA/SM kernels
+# contending for the SMs), so the default keeps the whole step on one stream.
+_SIDE_STREAMS = {}
+OVERLAP_WGRAD = os.environ.get("B2N_OVERLAP_WGRAD", "0") not in ("", "0")
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return s
 
 
 class _BNState:
@@ -383,17 +402,46 @@ class _TrunkFn(torch.autograd.Function):
                 grads[id(bn.bias)] = dbeta
             return dy
 
+        main = torch.cuda.current_stream(dev)
+        # (per-launch timing for bench.py's roofline keeps everything on one stream)
+        side = _side_stream(dev) if OVERLAP_WGRAD and _lib.PROFILE is None else None
+
+        class _on_side:
+            """Run the enclosed launches on the side stream once everything enqueued on the main
+            stream so far (the operands) is complete; ``uses``: main-stream tensors they read."""
+
+            def __init__(self, *uses):
+                self.uses = uses
+
+            def __enter__(self):
+                if side is None:
+                    return
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                for t in self.uses:
+                    t.record_stream(side)
+                self.ctx = torch.cuda.stream(side)
+                self.ctx.__enter__()
+
+            def __exit__(self, *exc):
+                if side is not None:
+                    self.ctx.__exit__(*exc)
+
         def wgrad(conv, x_in, dy, H, W, stride, pad):
             if not need[id(conv.weight)]:
                 return
             K, C, R, S = conv.weight.shape
-            dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
             P, Q = dy.shape[1], dy.shape[2]
             wflops = 2.0 * N * P * Q * K * R * S * C
-            call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
-                 work=(wflops, 0.0, wflops, "wgrad"))
-            dw = torch.empty_like(conv.weight)
-            call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
+            with _on_side(x_in, dy):
+                dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
+                call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
+                     work=(wflops, 0.0, wflops, "wgrad"))
+                dw = torch.empty_like(conv.weight)
+                call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
+            if side is not None:
+                dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
             grads[id(conv.weight)] = dw
 
         last = sv["blocks"][-1]
@@ -457,12 +505,17 @@ class _TrunkFn(torch.autograd.Function):
             if need[id(trunk.bn1.bias)]:
                 grads[id(trunk.bn1.bias)] = dbeta
             if need[id(trunk.conv1.weight)]:
-                dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
-                call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
-                     work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
-                           "wgrad"))
-                dw = torch.empty_like(trunk.conv1.weight)
-                call("b2n_stem_unpack_wgrad", dws, dw, 64)
+                with _on_side(sv["xs"], dy0):
+                    dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
+                    call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
+                         work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
+                               "wgrad"))
+                    dw = torch.empty_like(trunk.conv1.weight)
+                    call("b2n_stem_unpack_wgrad", dws, dw, 64)
+                if side is not None:
+                    dw.record_stream(main)
                 grads[id(trunk.conv1.weight)] = dw
 
+        if side is not None:
+            main.wait_stream(side)   # all weight gradients are complete before anyone reads them
         return (None, None, None, None) + tuple(grads[id(p)] for p in params)
