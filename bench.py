@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--torch-optim", action="store_true",
+                    help="step torch.optim.Adam instead of the multi-tensor ssl_cr_histo_b200.optim.Adam")
     ap.add_argument("--e2e-fp32", action="store_true",
                     help="e2e arm ships fp32 patches (the reference loop's format) instead of uint8")
     return ap.parse_args()
@@ -139,7 +141,7 @@ class ClockSampler(threading.Thread):
 def run_b200(args):
     import torch.distributed as dist
     import ssl_cr_histo_b200.net as net
-    from ssl_cr_histo_b200 import _lib, ddp, losses
+    from ssl_cr_histo_b200 import _lib, ddp, losses, optim
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,7 +168,12 @@ def run_b200(args):
     student, cls_s, teacher, cls_t = (m.to(dev) for m in (student, cls_s, teacher, cls_t))
     teacher.eval(); cls_t.eval(); student.train(); cls_s.train()
     params = list(student.parameters()) + list(cls_s.parameters())
-    opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4)       # :481
+    # eval_BreastPathQ_SSL_CR.py:481 -- Adam(lr 1e-4, wd 1e-4); the multi-tensor drop-in by default
+    if args.torch_optim:
+        opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4)
+    else:
+        opt = optim.Adam(params, lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4)
+        opt.grad_scale = 1.0 / world          # folds the all-reduce averaging into the step
     reducer = ddp.GradAllReducer(params) if world > 1 else None
 
     # synthetic inputs: host copies in pinned memory (e2e) and resident device copies (value)
@@ -200,7 +207,7 @@ def run_b200(args):
             opt.zero_grad(set_to_none=True)
         loss.backward()
         if reducer is not None:
-            reducer.all_reduce()
+            reducer.all_reduce(average=args.torch_optim)
         opt.step()
         return loss
 
@@ -329,7 +336,7 @@ def run_b200(args):
         "config": {"workload": "SSL_CR consistency step (eval_BreastPathQ_SSL_CR.py:76-100), MSE/MSE, "
                                "modules_student=0, BASELINE configs[2] per rank",
                    "labeled": nx, "unlabeled_weak": nu, "unlabeled_strong": nu, "image": S,
-                   "unique_patches_per_step_per_rank": nx + nu, "optimizer": "Adam(1e-4, wd 1e-4)",
+                   "unique_patches_per_step_per_rank": nx + nu, "optimizer": "Adam(1e-4, wd 1e-4), " + ("torch.optim" if args.torch_optim else "multi-tensor kernel"),
                    "parallelism": "dp%d, one NCCL all-reduce of %.1f MB grads/step" % (
                        world, reducer.nbytes / 1e6) if reducer else "single GPU",
                    "l2": "inputs (%.0f MB/step fp32) larger than the 126 MB L2"

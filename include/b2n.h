@@ -206,6 +206,25 @@ int b2n_fused_loss(int mode, const float* logits_x, const long long* targets_i,
 int b2n_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
                    float alpha, int write_back, void* stream);
 
+/* ---- multi-tensor optimizer steps (torch.optim formulas term by term) -- */
+/* Host arrays of n device pointers / element counts (as b2n_lerp_multi).  grad_scale multiplies
+ * every gradient first (1/world after a summing all-reduce, else 1).
+ * Adam with L2 weight decay, bias correction for `step` >= 1:
+ *   replaces optimizer.step() of torch.optim.Adam (eval_BreastPathQ_SSL_CR.py:481,100;
+ *   eval_Kather_SSL.py:419,72). */
+int b2n_adam_multi(float* const* p, const float* const* g, float* const* exp_avg,
+                   float* const* exp_avg_sq, const long long* numel, int n, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, long long step,
+                   double grad_scale,
+                   void* stream);
+/* SGD with momentum (dampening 0), optional Nesterov, L2 weight decay; first_step != 0
+ * initialises the momentum buffer with the gradient:
+ *   replaces torch.optim.SGD(nesterov=True) (pretrain_BreastPathQ.py:245,61;
+ *   eval_Camelyon_SSL_CR.py:514). */
+int b2n_sgd_multi(float* const* p, const float* const* g, float* const* momentum_buf,
+                  const long long* numel, int n, double lr, double momentum, double weight_decay,
+                  int nesterov, int first_step, double grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

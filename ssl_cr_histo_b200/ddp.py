@@ -39,15 +39,18 @@ class GradAllReducer:
         """Use instead of optimizer.zero_grad(): keeps .grad aliased into the arena."""
         self.flat.zero_()
 
-    def all_reduce(self) -> None:
-        """Average gradients over ranks (sum -> /world), in place, one collective."""
+    def all_reduce(self, average: bool = True) -> None:
+        """Sum gradients over ranks in place with one collective and (``average``) divide by the
+        world size; pass ``average=False`` when the optimizer folds 1/world into its step
+        (``optim.Adam.grad_scale``)."""
         for p in self.params:  # a backward pass may have re-bound .grad to a fresh tensor
             if p.grad is not None and p.grad.data_ptr() != self._slot(p).data_ptr():
                 self._slot(p).copy_(p.grad)
                 p.grad = self._slot(p)
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(self.world)
+            if average:
+                self.flat.div_(self.world)
 
     def _slot(self, p):
         if not hasattr(self, "_slots"):

@@ -489,3 +489,55 @@ def test_lerp_handoff_bitwise_and_lookahead_golden():
     many_s = [torch.full((5,), float(i), device=DEV) for i in range(130)]
     weights.lerp_(many_d, many_s, 0.25)
     assert all(torch.allclose(d, s * 0.25) for d, s in zip(many_d, many_s))
+
+
+@pytest.mark.parametrize("kind", ["adam", "sgd_nesterov", "sgd_plain"])
+def test_fused_optimizers_match_torch_optim(kind):
+    """b2n_adam_multi / b2n_sgd_multi follow torch.optim's formulas term by term: three steps over a
+    ragged list of 70 tensors (> one 64-tensor launch), a frozen parameter, weight decay, an LR
+    change in between, and grad_scale == pre-scaled gradients."""
+    from ssl_cr_histo_b200 import optim as fused
+    g = torch.Generator().manual_seed(11)
+    shapes = [(64, 3, 7, 7), (64,), (128, 64, 3, 3), (1,), (512, 1024)] + [(5 + i, 3) for i in range(65)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    mine = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    ref = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    if kind == "adam":
+        om = fused.Adam(mine, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+        orf = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    else:
+        kw = dict(lr=0.05, momentum=0.9 if kind == "sgd_nesterov" else 0.0, weight_decay=1e-4,
+                  nesterov=kind == "sgd_nesterov")
+        om, orf = fused.SGD(mine, **kw), torch.optim.SGD(ref, **kw)
+    om.grad_scale = 0.25
+    for step in range(3):
+        for i, (a, b) in enumerate(zip(mine, ref)):
+            if i == 3:
+                continue                                     # a parameter that never gets a grad
+            gr = torch.randn(a.shape, generator=g).to(DEV)
+            a.grad, b.grad = gr * 4.0, gr.clone()            # grad_scale 0.25 undoes the x4 exactly
+        om.step(); orf.step()
+        if step == 0:
+            om.param_groups[0]["lr"] *= 0.1; orf.param_groups[0]["lr"] *= 0.1
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (kind, i, float((a - b).abs().max()))
+    assert torch.equal(mine[3], ref[3])
+    if kind == "adam":
+        assert om.state[mine[0]]["step"] == 3
+        assert torch.allclose(om.state[mine[0]]["exp_avg_sq"], orf.state[ref[0]]["exp_avg_sq"], rtol=2e-6)
+
+
+def test_fused_optimizer_invalidates_packed_weights():
+    """A step writes parameters behind autograd's version counters: the trunk must re-pack."""
+    import ssl_cr_histo_b200.net as net
+    from ssl_cr_histo_b200 import optim as fused
+    torch.manual_seed(0)
+    m = net.TripletNet_Finetune("resnet18").to(DEV).train()
+    x = ints((2, 3, 32, 32), 0, 255, 5).to(DEV)
+    opt = fused.SGD(m.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    out0 = m(x)
+    out0.square().mean().backward()
+    opt.step()
+    with torch.no_grad():
+        out1 = m(x)
+    assert not torch.equal(out0, out1)

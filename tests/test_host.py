@@ -180,3 +180,29 @@ def test_shard_rejects_ragged_batches():
     with pytest.raises(RuntimeError, match="does not divide"):
         ddp.shard(torch.zeros(7, 2), 0, 2)
     assert ddp.shard(torch.arange(8), 1, 4).tolist() == [2, 3]
+
+
+def test_fused_optimizers_keep_the_torch_optim_contract():
+    """Constructor validation, param_groups / LR-scheduler / state_dict compatibility (no launch)."""
+    import pytest
+    import torch
+    from ssl_cr_histo_b200 import optim as fused
+
+    p = [torch.nn.Parameter(torch.zeros(4))]
+    adam = fused.Adam(p, lr=1e-4, weight_decay=1e-4)                   # eval_BreastPathQ_SSL_CR.py:481
+    ref_defaults = torch.optim.Adam(p, lr=1e-4, weight_decay=1e-4).defaults
+    assert all(ref_defaults[k] == v for k, v in adam.defaults.items())   # same names, same values
+    sched = torch.optim.lr_scheduler.MultiStepLR(adam, milestones=[30, 60], gamma=0.1)   # :482
+    assert sched.get_last_lr() == [1e-4]
+    sgd = fused.SGD(p, lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)   # pretrain_BreastPathQ.py:245
+    assert sgd.param_groups[0]["nesterov"] is True
+    assert set(adam.state_dict().keys()) == {"state", "param_groups"}
+    with pytest.raises(ValueError):
+        fused.Adam(p, lr=-1.0)
+    with pytest.raises(ValueError):
+        fused.SGD(p, lr=0.1, nesterov=True)                             # Nesterov needs momentum
+    with pytest.raises(NotImplementedError):
+        fused.SGD(p, lr=0.1, momentum=0.9, dampening=0.5)
+    p[0].grad = torch.zeros(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        adam.step()                                                     # CPU tensors fail loudly
