@@ -74,12 +74,15 @@ struct ConvParams {
                             // (integer-valued images) and its loads / MMAs are skipped
 };
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;   // producer warp + MMA warp + 4 epilogue warps
+// 64-wide tiles whose epilogue, not their MMAs, sets the pace (the stem: K = 256 only) run with 8
+// epilogue warps -- two per TMEM lane quadrant, one per 32-column chunk.
+__host__ __device__ constexpr int conv_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 constexpr int kBlockM = 128;
 constexpr int kHaloMaxS = 4;                       // widest filter row the HALO variant handles
 constexpr int kHaloRows = kBlockM + kHaloMaxS - 1;  // pixels of the largest HALO activation box
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI_WARPS = 4>
 struct ConvSmem {
   static constexpr int PLANES = SPLIT ? 2 : 1;
   // HALO boxes hold kBlockM + S - 1 pixels; every plane stays 1024-byte aligned
@@ -89,8 +92,11 @@ struct ConvSmem {
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   // one private [sum | sumsq] row per epilogue warp; resident-weight launches have one N tile
   static constexpr int STATS_C = RES_B ? BLOCK_N : 512;
-  static constexpr int STATS_FLOATS = 4 * 2 * STATS_C;
-  static constexpr int STAGING_BYTES = 4 * 16 * 128;  // per epilogue warp: 16 rows x 32 floats
+  static constexpr int STATS_FLOATS = EPI_WARPS * 2 * STATS_C;
+  // per epilogue warp: SROWS rows x 32 floats.  Two 16-row half rounds where shared memory is
+  // scarce; the 8-warp (stem) variant stages all 32 rows at once -- one barrier, twice the ILP
+  static constexpr int SROWS = EPI_WARPS == 8 ? 32 : 16;
+  static constexpr int STAGING_BYTES = EPI_WARPS * SROWS * 128;
   // stats | staging | barriers | tmem pointer, rounded up to keep the ring 1024-byte aligned
   static constexpr int CTRL_BYTES =
       (STATS_FLOATS * 4 + STAGING_BYTES + (2 * STAGES + 5) * 8 + 16 + 1023) / 1024 * 1024;
@@ -111,13 +117,15 @@ __host__ __device__ constexpr bool epi_on(int epi, int bit, bool runtime) {
   return epi >= 0 ? (epi & bit) != 0 : runtime;
 }
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
+          int EPI_WARPS = 4>
+__global__ void __launch_bounds__(conv_threads(EPI_WARPS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
+  static_assert(EPI_WARPS == 4 || (EPI_WARPS == 8 && BLOCK_N == 64), "8 epilogue warps: one per chunk of a 64-wide tile");
   constexpr int KELEMS = KBYTES / (SPLIT ? 2 : 4);  // fp16 pairs (split) or tf32-in-fp32
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
@@ -172,7 +180,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -181,7 +189,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < L::STATS_FLOATS; i += kConvThreads) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < L::STATS_FLOATS; i += conv_threads(EPI_WARPS)) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -385,8 +393,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     const bool f_out16 = epi_on(EPI, kEpiOut16, p.out_h != nullptr);
     const bool f_round = epi_on(EPI, kEpiRound, p.round_tf32 != 0);
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;    // epilogue warp index (its private staging tile / statistics row)
     const int row_in_tile = quad * 32 + lane;
-    float4* stg = s_stage + quad * (16 * 8);
+    float4* stg = s_stage + ew * (L::SROWS * 8);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -488,20 +497,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         // 128 contiguous bytes of one output row -- 4 lines per warp instruction instead of 32.
         float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if ((lane >> 4) == h) {
-            const int r = lane & 15;
+        for (int h = 0; h < 32 / L::SROWS; ++h) {
+          if (lane / L::SROWS == h) {
+            const int r = lane % L::SROWS;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               stg[r * 8 + (c ^ (r & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < L::SROWS / 4; ++i) {
             const int r = 4 * i + (lane >> 3);
             const int c = lane & 7;
             const float4 t = stg[r * 8 + (c ^ (r & 7))];
-            const int sl = 4 * h + i;
+            const int sl = (L::SROWS / 4) * h + i;
             if (row4[sl] != 0xFFFFFFFFu) {
               const size_t off = (static_cast<size_t>(row4[sl]) << 2) + c4;
               float o[4] = {t.x, t.y, t.z, t.w};
@@ -567,13 +576,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 16);
           }
           if (lane < 8) {
-            float* mine = s_stats + quad * (2 * L::STATS_C) + n0 + 4 * lane;
+            float* mine = s_stats + ew * (2 * L::STATS_C) + n0 + 4 * lane;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { mine[k] += st_s[k]; mine[L::STATS_C + k] += st_q[k]; }
           }
         }
       };
-      if constexpr (BLOCK_N == 64 && EPI >= 0) {
+      if constexpr (EPI_WARPS == 8) {
+        // one chunk per warp: warps 2..5 take columns 0..31, warps 6..9 columns 32..63
+        const int ch = ew >> 2;
+        float4 pr[8], pm[8];
+        uint2 ph[8], pl[8];
+        prefetch(ch, pr, pm, ph, pl);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        process(ch, pr, pm, ph, pl);
+      } else if constexpr (BLOCK_N == 64 && EPI >= 0) {
         float4 pr0[8], pm0[8], pr1[8], pm1[8];
         uint2 ph0[8], pl0[8], ph1[8], pl1[8];
         prefetch(0, pr0, pm0, ph0, pl0);
@@ -601,11 +619,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     if (f_stats) {
       // epilogue-only named barrier (warps 2..5 = 128 threads), then flush CTA partials
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < p.Cout; c += 128) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * EPI_WARPS) {
         constexpr int SC = L::STATS_C;
-        const float a = s_stats[c] + s_stats[2 * SC + c] + s_stats[4 * SC + c] + s_stats[6 * SC + c];
-        const float b = s_stats[SC + c] + s_stats[3 * SC + c] + s_stats[5 * SC + c] + s_stats[7 * SC + c];
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < EPI_WARPS; ++w) {
+          a += s_stats[2 * w * SC + c];
+          b += s_stats[(2 * w + 1) * SC + c];
+        }
         if (a != 0.f || b != 0.f) {
           atomicAdd(&p.stats[c], static_cast<double>(a));
           atomicAdd(&p.stats[p.Cout + c], static_cast<double>(b));

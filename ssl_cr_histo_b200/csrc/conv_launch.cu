@@ -38,10 +38,11 @@ struct ConvMaps {
 
 constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1>
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
+          int EPI_WARPS = 4>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI>;
+  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS>;
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
   static bool configured = false;
@@ -51,7 +52,7 @@ static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cuda
     if (e != cudaSuccess) return set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, kConvThreads, smem, stream>>>(m.a, m.b, m.a_lo, m.b_lo, p);
+  kern<<<grid, conv_threads(EPI_WARPS), smem, stream>>>(m.a, m.b, m.a_lo, m.b_lo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("conv launch: %s", cudaGetErrorString(e));
   return 0;
@@ -186,9 +187,9 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     if (epi == kDgradRes) return launch_variant<64, 128, 4, false, true, true, kDgradRes>(m, p, grid, stream);
     return launch_variant<64, 128, 4, false, true, true>(m, p, grid, stream);
   }
-  if (halo == 32 && split) {
-    if (epi == kTrainFwd) return launch_variant<64, 32, 8, true, true, true, kTrainFwd>(m, p, grid, stream);
-    if (epi == kEvalStem) return launch_variant<64, 32, 8, true, true, true, kEvalStem>(m, p, grid, stream);
+  if (halo == 32 && split) {  // the stem: epilogue-paced, 8 epilogue warps
+    if (epi == kTrainFwd) return launch_variant<64, 32, 8, true, true, true, kTrainFwd, 8>(m, p, grid, stream);
+    if (epi == kEvalStem) return launch_variant<64, 32, 8, true, true, true, kEvalStem, 8>(m, p, grid, stream);
     return launch_variant<64, 32, 8, true, true, true>(m, p, grid, stream);
   }
   if (halo == 32) return launch_variant<64, 32, 8, false, true, true>(m, p, grid, stream);

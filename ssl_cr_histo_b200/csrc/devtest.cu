@@ -286,7 +286,88 @@ static int run_tma_mode_timing() {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA delivery-rate microbenchmark: one thread per CTA streams boxes of `rows` x `row_bytes` from
+// an L2-resident tensor into a 4-deep shared-memory ring and only waits for their arrival (no
+// MMA, no stores).  Compares tiled-mode with im2col-mode boxes: is the im2col unit row-rate bound?
+#include "ptx.cuh"
+#include "tmap.h"
+
+__global__ void __launch_bounds__(64, 1)
+tma_rate_kernel(const __grid_constant__ CUtensorMap map, int im2col, int boxes, int rows,
+                int row_bytes, int W, int HW_imgs, int DEPTH, long long* clocks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int box_bytes = rows * row_bytes;
+  const int slot_bytes = (box_bytes + 1023) / 1024 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + DEPTH * slot_bytes);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DEPTH; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int i = 0; i < boxes + DEPTH; ++i) {
+      const int slot = i % DEPTH;
+      if (i >= DEPTH) mbar_wait(&bar[slot], ((i / DEPTH) - 1) & 1);
+      if (i < boxes) {
+        // each CTA walks its own region of the tensor, box after box along the pixel raster
+        const int pix = (blockIdx.x * boxes + i) * rows % (HW_imgs - rows - 2 * W);
+        mbar_arrive_expect_tx(&bar[slot], box_bytes);
+        if (im2col)
+          tma_load_im2col_4d(smem + slot * slot_bytes, &map, &bar[slot], 0, pix % W - 1,
+                             (pix / W) % W - 1, pix / (W * W), 0, 1);
+        else
+          tma_load_2d(smem + slot * slot_bytes, &map, &bar[slot], 0, pix);
+      }
+    }
+    clocks[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static int run_tma_rate() {
+  const int N = 32, H = 56, W = 56;  // 32 x 56 x 56 pixels, L2 resident for every row width below
+  struct Cfg { int row_bytes, rows; };
+  for (Cfg cfg : {Cfg{128, 64}, Cfg{128, 130}, Cfg{32, 131}}) {
+    const int row_bytes = cfg.row_bytes, rows = cfg.rows;
+    const int C = row_bytes / 4;  // fp32 channels per pixel == one K row
+    const size_t pixels = (size_t)N * H * W;
+    float* dx;
+    CK(cudaMalloc(&dx, pixels * C * 4));
+    CK(cudaMemset(dx, 0, pixels * C * 4));
+    long long* dclk;
+    CK(cudaMalloc(&dclk, 148 * 8));
+    for (int depth : {1, 2, 4, 8, 12}) {
+      for (int mode = 0; mode < 2; ++mode) {
+        CUtensorMap map;
+        int rc = mode ? make_im2col_map(&map, dx, kF32, N, H, W, C, 3, 1, 1, 1, 1, 1, 1, C, rows, row_bytes)
+                      : make_tiled_map_2d(&map, dx, kF32, pixels, C, C, rows, C, row_bytes);
+        if (rc) { printf("map error %s\n", tmap_last_error()); return 1; }
+        const int boxes = 2000;
+        const int smem = depth * ((rows * row_bytes + 1023) / 1024 * 1024) + 128 + 1024;
+        cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int it = 0; it < 2; ++it)
+          tma_rate_kernel<<<148, 64, smem>>>(map, mode, boxes, rows, row_bytes, W, (int)pixels, depth, dclk);
+        CK(cudaDeviceSynchronize());
+        long long h[148];
+        CK(cudaMemcpy(h, dclk, sizeof h, cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int i = 0; i < 148; ++i) avg += (double)h[i];
+        avg /= 148;
+        printf("row %3d B, box %3d rows, depth %2d, %-6s: %7.1f clk/box  %5.2f clk/row  %6.1f B/clk/SM\n",
+               row_bytes, rows, depth, mode ? "im2col" : "tiled", avg / boxes, avg / boxes / rows,
+               (double)rows * row_bytes * boxes / avg);
+      }
+    }
+    cudaFree(dx);
+    cudaFree(dclk);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && !strcmp(argv[1], "tmarate")) return run_tma_rate();
   if (argc >= 2 && !strcmp(argv[1], "tma")) return run_tma_mode_timing();
   if (argc < 2 || !strcmp(argv[1], "list")) { printf("%d\n", kNumCases); return 0; }
   const int id = atoi(argv[1]);
