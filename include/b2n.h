@@ -198,6 +198,10 @@ int b2n_fused_loss(int mode, const float* logits_x, const long long* targets_i,
                    int rows_x, int rows_u, int C, float lambda_u, float* losses, float* dlogits_x,
                    float* dlogits_u, long long* argmax_x, long long* pseudo_labels, void* stream);
 
+/* out[i] = softmax(logits[i, :])[C-1]: the tumour-probability column of the WSI heat-map
+ * inference loop (test_Camelyon16.py:57-58). */
+int b2n_softmax_last(const float* logits, float* out, int rows, int C, void* stream);
+
 /* ---- multi-tensor weight lerp ("EMA") -----------------------------------------------------
  * dst[i] <- alpha*src[i] + (1-alpha)*dst[i]; write_back also stores the result into src[i].
  * dst/src/numel are HOST arrays of n device pointers / element counts.

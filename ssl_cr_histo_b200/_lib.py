@@ -45,6 +45,7 @@ _SIGNATURES = {
     "b2n_linear_bwd_data": [P, LL, P, LL, P, LL, P, I, I, I, I],
     "b2n_linear_bwd_weight": [P, LL, P, LL, P, LL, P, I, I, I, I],
     "b2n_fused_loss": [I, P, P, P, P, P, I, I, I, F, P, P, P, P, P],
+    "b2n_softmax_last": [P, P, I, I],
     "b2n_lerp_multi": [P, P, P, I, F, I],
     "b2n_adam_multi": [P, P, P, P, P, I, D, D, D, D, D, LL, D],
     "b2n_sgd_multi": [P, P, P, P, I, D, D, D, I, I, D],

@@ -199,6 +199,10 @@ int b2n_fused_loss(int mode, const float* logits_x, const long long* targets_i,
                            pseudo_labels, S(stream)));
 }
 
+int b2n_softmax_last(const float* logits, float* out, int rows, int C, void* stream) {
+  return counted(launch_softmax_last(logits, out, rows, C, S(stream)));
+}
+
 int b2n_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
                    float alpha, int write_back, void* stream) {
   if (n < 0 || (n > 0 && (!dst || !src || !numel))) return set_error("b2n_lerp_multi: bad args");

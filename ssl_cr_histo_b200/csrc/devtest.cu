@@ -326,6 +326,71 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap map, int im2col, int boxes, 
   }
 }
 
+// batches of B boxes on one barrier: issue B loads back to back, wait for all, repeat
+__global__ void __launch_bounds__(64, 1)
+tma_batch_kernel(const __grid_constant__ CUtensorMap map, int im2col, int batches, int B, int rows,
+                 int row_bytes, int W, int HW_imgs, long long* clocks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int box_bytes = rows * row_bytes;
+  const int slot_bytes = (box_bytes + 1023) / 1024 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + B * slot_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int i = 0; i < batches; ++i) {
+      mbar_arrive_expect_tx(bar, box_bytes * B);
+      for (int b = 0; b < B; ++b) {
+        const int pix = ((blockIdx.x * batches + i) * B + b) * rows % (HW_imgs - rows - 2 * W);
+        if (im2col)
+          tma_load_im2col_4d(smem + b * slot_bytes, &map, bar, 0, pix % W - 1, (pix / W) % W - 1,
+                             pix / (W * W), 0, 1);
+        else
+          tma_load_2d(smem + b * slot_bytes, &map, bar, 0, pix);
+      }
+      mbar_wait(bar, i & 1);
+    }
+    clocks[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static int run_tma_batch() {
+  const int N = 32, H = 56, W = 56, rows = 130, row_bytes = 128, C = 32;
+  const size_t pixels = (size_t)N * H * W;
+  float* dx;
+  CK(cudaMalloc(&dx, pixels * C * 4));
+  CK(cudaMemset(dx, 0, pixels * C * 4));
+  long long* dclk;
+  CK(cudaMalloc(&dclk, 148 * 8));
+  for (int B : {1, 2, 4, 8, 12}) {
+    for (int mode = 0; mode < 2; ++mode) {
+      CUtensorMap map;
+      int rc = mode ? make_im2col_map(&map, dx, kF32, N, H, W, C, 3, 1, 1, 1, 1, 1, 1, C, rows, row_bytes)
+                    : make_tiled_map_2d(&map, dx, kF32, pixels, C, C, rows, C, row_bytes);
+      if (rc) { printf("map error %s\n", tmap_last_error()); return 1; }
+      const int batches = 1000;
+      const int smem = B * ((rows * row_bytes + 1023) / 1024 * 1024) + 128 + 1024;
+      cudaFuncSetAttribute(tma_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      for (int it = 0; it < 2; ++it)
+        tma_batch_kernel<<<148, 64, smem>>>(map, mode, batches, B, rows, row_bytes, W, (int)pixels, dclk);
+      CK(cudaDeviceSynchronize());
+      long long h[148];
+      CK(cudaMemcpy(h, dclk, sizeof h, cudaMemcpyDeviceToHost));
+      double avg = 0;
+      for (int i = 0; i < 148; ++i) avg += (double)h[i];
+      avg /= 148;
+      printf("batch of %2d boxes (130 x 128 B), %-6s: %7.1f clk/batch  %6.1f clk/box  %5.1f B/clk/SM\n", B,
+             mode ? "im2col" : "tiled", avg / batches, avg / batches / B,
+             (double)rows * row_bytes * B * batches / avg);
+    }
+  }
+  return 0;
+}
+
 static int run_tma_rate() {
   const int N = 32, H = 56, W = 56;  // 32 x 56 x 56 pixels, L2 resident for every row width below
   struct Cfg { int row_bytes, rows; };
@@ -368,6 +433,7 @@ static int run_tma_rate() {
 
 int main(int argc, char** argv) {
   if (argc >= 2 && !strcmp(argv[1], "tmarate")) return run_tma_rate();
+  if (argc >= 2 && !strcmp(argv[1], "tmabatch")) return run_tma_batch();
   if (argc >= 2 && !strcmp(argv[1], "tma")) return run_tma_mode_timing();
   if (argc < 2 || !strcmp(argv[1], "list")) { printf("%d\n", kNumCases); return 0; }
   const int id = atoi(argv[1]);

@@ -127,6 +127,7 @@ int launch_fused_loss(int mode, const float* logits_x, const long long* targets_
                       int rows_x, int rows_u, int C, float lambda_u, float* losses,
                       float* dlogits_x, float* dlogits_u, long long* argmax_x,
                       long long* pseudo_out, cudaStream_t stream);
+int launch_softmax_last(const float* logits, float* out, int rows, int C, cudaStream_t stream);
 int launch_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
                       float alpha, int write_back, cudaStream_t stream);
 

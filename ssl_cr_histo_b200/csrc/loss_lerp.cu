@@ -119,6 +119,29 @@ int launch_fused_loss(int mode, const float* logits_x, const long long* targets_
   return 0;
 }
 
+// ------------------------------------------------- softmax probability of the last class
+// out[i] = softmax(logits[i, :])[C-1]  -- the 'tumor' column of test_Camelyon16.py:57-58.
+__global__ void softmax_last_kernel(const float* __restrict__ logits, float* __restrict__ out,
+                                    int rows, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* l = logits + static_cast<size_t>(i) * C;
+  float mx = l[0];
+  for (int c = 1; c < C; ++c) mx = fmaxf(mx, l[c]);
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) den += expf(l[c] - mx);
+  out[i] = expf(l[C - 1] - mx) / den;
+}
+
+int launch_softmax_last(const float* logits, float* out, int rows, int C, cudaStream_t stream) {
+  if (rows < 0 || C < 1) return set_error("softmax_last: bad shape (%d, %d)", rows, C);
+  if (rows == 0) return 0;
+  softmax_last_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(logits, out, rows, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("softmax_last: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---------------------------------------------------------------- multi lerp
 constexpr int kLerpMaxTensors = 96;
 struct LerpTable {

@@ -335,3 +335,29 @@ def test_uint8_patches_equal_their_float_cast():
     gm.eval(); gm2.eval()
     with torch.no_grad():
         assert torch.equal(gm(xf.to(DEV)), gm2(xu.to(DEV)))
+
+
+def test_wsi_heatmap_inference_matches_reference_loop():
+    """test_Camelyon16.py:30-70 restated on both sides: eval-mode TripletNet_Finetune +
+    FinetuneResNet(2), softmax 'tumor' column scattered into the slide's probability map."""
+    from ssl_cr_histo_b200 import infer
+    om, oh, gm, gh = pair("finetune", ("finetune", 2))
+    # a few train-mode passes first so the running statistics are not the 0 / 1 defaults
+    warm = O.synthetic_patches(8, 64, seed=80)
+    om.train(); gm.train()
+    with torch.no_grad():
+        om(warm); gm(warm.to(DEV))
+    xs = [O.synthetic_patches(5, 64, seed=81 + i) for i in range(3)]
+    coords = [(np.arange(5) + 5 * i, (np.arange(5) * 2 + i) % 7) for i in range(3)]
+    om.eval(); oh.eval()
+    ref_map = np.zeros((15, 7))
+    with torch.no_grad():
+        for x, (xm, ym) in zip(xs, coords):
+            ref_map[xm, ym] = torch.softmax(oh(om(x)), dim=1)[:, -1].numpy()
+    got = infer.probability_map(gm, gh, [(x, torch.from_numpy(xm), torch.from_numpy(ym))
+                                         for x, (xm, ym) in zip(xs, coords)], (15, 7))
+    assert not gm.training and not gh.training
+    assert np.abs(got - ref_map).max() <= 1e-3, np.abs(got - ref_map).max()
+    assert got[ref_map == 0].max() == 0
+    u8 = infer.tumor_probabilities(gm, gh, xs[0].to(torch.uint8).to(DEV))
+    assert torch.equal(u8, infer.tumor_probabilities(gm, gh, xs[0].to(DEV)))
