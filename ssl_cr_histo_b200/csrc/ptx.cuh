@@ -80,6 +80,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion
+// counted on an mbarrier like the tensor loads.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 // im2col-mode load of a (channels x pixels) box.  (c, w, h, n) is the base pixel
 // (already offset by the lower bounding-box corner), (off_w, off_h) the filter tap.
 __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map,

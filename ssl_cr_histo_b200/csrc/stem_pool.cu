@@ -296,18 +296,19 @@ int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const flo
 // --------------------------------- fused maxpool + ReLU + BatchNorm backward (the stem's tail)
 // The stem's BN output is 1/3 of all conv-output elements of the trunk, so materialising
 // gz = d(maxpool o relu) and then running the generic two-pass BN backward over it costs three
-// extra sweeps of that tensor.  Here gz never exists in memory: a block owns a band of two image
-// rows (2b, 2b+1), stages the pooled gradients and recorded argmax codes of pooled rows b and b+1
-// (the only rows whose 3x3/s2 windows reach the band) in shared memory, and sweeps the band once
-// against y, rebuilding gz per position from its (at most four) candidate windows in the same
-// order as maxpool_relu_bwd_kernel:
+// extra sweeps of that tensor.  Here gz never exists in memory: a persistent block walks bands of
+// two image rows (2b, 2b+1); for every band one thread issues three 1-D bulk copies (TMA) into a
+// double-buffered shared-memory slot -- the band of y, and the pooled gradients and recorded
+// argmax codes of pooled rows b and b+1 (the only rows whose 3x3/s2 windows reach the band) --
+// so the next band's ~100 KB are in flight while this one is swept.  gz is rebuilt per position
+// from its (at most four) candidate windows in maxpool_relu_bwd_kernel's order:
 //   reduce: sums[0][c] += sum gz', sums[1][c] += sum gz' * xhat       (gz' = gz * [scale*y+shift > 0])
 //   apply : dy = gamma*invstd*(gz' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0
-// Blocks are persistent over bands, so the reduce pass issues one atomic per channel per block.
-constexpr int kBandThreads = 256;
+// The reduce pass issues one atomic per channel per block.
+constexpr int kBandThreads = 512;
 
 template <bool APPLY, bool ROUND>
-__global__ void __launch_bounds__(kBandThreads, 3)
+__global__ void __launch_bounds__(kBandThreads, 1)
 pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict__ idx,
                         const float4* __restrict__ y, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ mean,
@@ -315,14 +316,17 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
                         double* __restrict__ sums, float4* __restrict__ dy, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int N, int H, int W, int P, int Q, int C,
                         double inv_count) {
-  extern __shared__ float smem_f[];  // pooled gradients [2][Q][C] fp32 | argmax codes [2][Q][C] u8
-  float4* g_s = reinterpret_cast<float4*>(smem_f);
-  uchar4* id_s = reinterpret_cast<uchar4*>(smem_f + 2 * Q * C);
+  extern __shared__ uint8_t band_smem_raw[];
+  uint8_t* smem = band_smem_raw + ((128u - (smem_u32(band_smem_raw) & 127u)) & 127u);
   const int tid = threadIdx.x;
   const int C4 = C >> 2;
   const int c4 = tid % C4;  // constant per thread: kBandThreads % C4 == 0
   const int HB = (H + 1) >> 1;
   const int nbands = N * HB;
+  // slot layout: y band [2][W][C] fp32 | pooled gradients [2][Q][C] fp32 | argmax codes [2][Q][C] u8
+  const uint32_t y_bytes = 2u * W * C * 4, g_bytes = 2u * Q * C * 4, i_bytes = 2u * Q * C;
+  const uint32_t slot_bytes = y_bytes + g_bytes + i_bytes;  // multiple of 16 (C % 4 == 0, checked)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * slot_bytes);
 
   const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
   const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
@@ -346,36 +350,45 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
   }
   float4 s1 = make_float4(0, 0, 0, 0), s2 = s1;
 
-  for (int band = blockIdx.x; band < nbands; band += gridDim.x) {
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // one thread streams a band into a slot; rows / pooled rows beyond the image are not copied
+  auto issue = [&](int band, int slot) {
     const int n = band / HB, hb = band - n * HB, h0 = 2 * hb;
-    // stage pooled rows hb and hb + 1 (window rows 2p-1 .. 2p+1); code 255 never matches
-#pragma unroll 4
-    for (int e = tid; e < 2 * Q * C4; e += kBandThreads) {
-      const int pr = e / (Q * C4);
-      const int p = hb + pr;
-      const size_t o = (static_cast<size_t>(n) * P + p) * Q * C4 + (e - pr * Q * C4);
-      g_s[e] = p < P ? ga[o] : make_float4(0, 0, 0, 0);
-      id_s[e] = p < P ? idx[o] : make_uchar4(255, 255, 255, 255);
-    }
-    __syncthreads();
+    const uint32_t rows = h0 + 1 < H ? 2u : 1u, prow = hb + 1 < P ? 2u : 1u;
+    uint8_t* dst = smem + slot * slot_bytes;
+    const size_t po = (static_cast<size_t>(n) * P + hb) * Q * C;
+    mbar_arrive_expect_tx(&full_bar[slot], rows * (y_bytes / 2) + prow * (g_bytes / 2) + prow * (i_bytes / 2));
+    bulk_load_1d(dst, reinterpret_cast<const float*>(y) + (static_cast<size_t>(n) * H + h0) * W * C,
+                 rows * (y_bytes / 2), &full_bar[slot]);
+    bulk_load_1d(dst + y_bytes, reinterpret_cast<const float*>(ga) + po, prow * (g_bytes / 2), &full_bar[slot]);
+    bulk_load_1d(dst + y_bytes + g_bytes, reinterpret_cast<const unsigned char*>(idx) + po,
+                 prow * (i_bytes / 2), &full_bar[slot]);
+  };
+
+  int k = 0;
+  if (tid == 0 && static_cast<int>(blockIdx.x) < nbands) issue(blockIdx.x, 0);
+  for (int band = blockIdx.x; band < nbands; band += gridDim.x, ++k) {
+    const int slot = k & 1;
+    // slot ^ 1 was released by the __syncthreads that ended the previous iteration
+    if (tid == 0 && band + static_cast<int>(gridDim.x) < nbands) issue(band + gridDim.x, slot ^ 1);
+    mbar_wait(&full_bar[slot], (k >> 1) & 1);
+    const int n = band / HB, hb = band - n * HB, h0 = 2 * hb;
+    const float4* y_s = reinterpret_cast<const float4*>(smem + slot * slot_bytes);
+    const float4* g_s = reinterpret_cast<const float4*>(smem + slot * slot_bytes + y_bytes);
+    const uchar4* id_s = reinterpret_cast<const uchar4*>(smem + slot * slot_bytes + y_bytes + g_bytes);
     const int band_n = (h0 + 1 < H ? 2 : 1) * W * C4;  // float4 elements of this band
     const size_t t0 = (static_cast<size_t>(n) * H + h0) * W * C4;
-    for (int i0 = tid; i0 < band_n; i0 += 4 * kBandThreads) {
-      // four independent loads of y in flight per thread before any of them is consumed
-      float4 vv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kBandThreads;
-        vv[u] = i < band_n ? y[t0 + i] : make_float4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kBandThreads;
-      if (i >= band_n) break;
+#pragma unroll 2
+    for (int i = tid; i < band_n; i += kBandThreads) {
       const int hh = i / (W * C4);
       const int w = (i - hh * W * C4) / C4;
-      const size_t t = t0 + i;
-      const float4 v = vv[u];
+      const float4 v = y_s[i];
       // branch-free gather over the four candidate windows (pr, q) in maxpool_relu_bwd_kernel's
       // order; candidates that do not exist get a code no recorded argmax can equal
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -384,11 +397,11 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
       for (int cand = 0; cand < 4; ++cand) {
         const int pr = cand >> 1;            // row h0: window row hb only; row h0+1: hb, hb+1
         const int q = (cand & 1) ? q_hi : q_lo;
-        const bool valid = pr <= hh && (!(cand & 1) || q_hi != q_lo) && q < Q;
+        const bool valid = pr <= hh && hb + pr < P && (!(cand & 1) || q_hi != q_lo) && q < Q;
         const int code = valid ? (hh + 1 - 2 * pr) * 3 + (w - (2 * q - 1)) : 254;
-        const int slot = (pr * Q + (q < Q ? q : Q - 1)) * C4 + c4;
-        const uchar4 id = id_s[slot];
-        const float4 gq = g_s[slot];
+        const int sidx = ((valid ? pr : 0) * Q + (q < Q ? q : Q - 1)) * C4 + c4;
+        const uchar4 id = id_s[sidx];
+        const float4 gq = g_s[sidx];
         acc[0] += id.x == code ? gq.x : 0.f;
         acc[1] += id.y == code ? gq.y : 0.f;
         acc[2] += id.z == code ? gq.z : 0.f;
@@ -405,18 +418,17 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
         float4 o = make_float4(gi.x * (g.x - m1.x - xh.x * m2.x), gi.y * (g.y - m1.y - xh.y * m2.y),
                                gi.z * (g.z - m1.z - xh.z * m2.z), gi.w * (g.w - m1.w - xh.w * m2.w));
         if (ROUND) o = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
-        dy[t] = o;
+        dy[t0 + i] = o;
       } else {
         s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
         s2.x += g.x * xh.x; s2.y += g.y * xh.y; s2.z += g.z * xh.z; s2.w += g.w * xh.w;
       }
-      }
     }
-    __syncthreads();
+    __syncthreads();  // everyone is done with this slot before it is refilled
   }
   if (!APPLY) {
     // block reduction over the kBandThreads / C4 threads that share a channel group
-    float* red = smem_f;  // [kBandThreads][8]
+    float* red = reinterpret_cast<float*>(smem);  // [kBandThreads][8]
     float* dst = red + tid * 8;
     dst[0] = s1.x; dst[1] = s1.y; dst[2] = s1.z; dst[3] = s1.w;
     dst[4] = s2.x; dst[5] = s2.y; dst[6] = s2.z; dst[7] = s2.w;
@@ -436,12 +448,16 @@ static int launch_band(const float* ga, const unsigned char* idx, const float* y
                        double* sums, float* dy, float* dgamma, float* dbeta, int N, int H, int W,
                        int C, cudaStream_t stream) {
   const int C4 = C / 4;
-  if (C % 4 != 0 || kBandThreads % C4 != 0)
+  if (C % 16 != 0 || kBandThreads % C4 != 0)
     return set_error("pool_bn_bwd: unsupported C=%d", C);
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  size_t smem = static_cast<size_t>(2) * Q * C * (sizeof(float) + 1);
-  if (smem < kBandThreads * 8 * sizeof(float)) smem = kBandThreads * 8 * sizeof(float);
-  if (smem > 200 * 1024) return set_error("pool_bn_bwd: image row too wide (W=%d, C=%d)", W, C);
+  // bulk copies need 16-byte sizes: one image row of y, one pooled row of gradients / codes
+  if ((W * C * 4) % 16 != 0 || (Q * C) % 16 != 0)
+    return set_error("pool_bn_bwd: row sizes must be multiples of 16 bytes (W=%d, C=%d)", W, C);
+  const size_t slot = static_cast<size_t>(2) * W * C * 4 + static_cast<size_t>(2) * Q * C * 5;
+  size_t smem = 2 * slot + 16 + 128;
+  if (smem < kBandThreads * 8 * sizeof(float) + 128) smem = kBandThreads * 8 * sizeof(float) + 128;
+  if (smem > 227 * 1024) return set_error("pool_bn_bwd: image row too wide (W=%d, C=%d)", W, C);
   auto kern = pool_bn_bwd_band_kernel<APPLY, ROUND>;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -450,8 +466,8 @@ static int launch_band(const float* ga, const unsigned char* idx, const float* y
     configured = smem;
   }
   const int nbands = N * ((H + 1) / 2);
-  int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
-  if (per_sm > 8) per_sm = 8;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   int grid = device_sm_count() * per_sm;
   if (grid > nbands) grid = nbands;
