@@ -296,7 +296,8 @@ def run_b200(args):
         grp = {}
         for name, ev in prof.items():
             for a, c, w in ev:
-                g = grp.setdefault(w[3], {"ms": 0.0, "alg": 0.0, "pipe_s": 0.0, "n": 0})
+                g = grp.setdefault(w[3], {"ms": 0.0, "alg": 0.0, "pipe_s": 0.0, "n": 0, "bytes": 0.0})
+                g["bytes"] += w[4]
                 g["ms"] += a.elapsed_time(c)
                 g["alg"] += w[0]
                 g["pipe_s"] += w[1] / (peak16 * 1e12) + w[2] / (peak32 * 1e12)
@@ -308,13 +309,27 @@ def run_b200(args):
             alg = sum(grp[k]["alg"] for k in keys)
             pipe = sum(grp[k]["pipe_s"] for k in keys)
             return {"launches_per_step": sum(grp[k]["n"] for k in keys) / 2, "ms_per_step": ms / 2,
+                    "algorithmic_dram_bytes_per_step": sum(grp[k]["bytes"] for k in keys) / 2,
                     "algorithmic_tflops": alg / (ms * 1e-3) / 1e12,
                     "tensor_pipe_util": pipe / (ms * 1e-3), "share_of_step": (ms / 2) / step_ms}
 
         dom = summary(["fwd", "dgrad"])
+        # measured DRAM traffic of the same launches: one ncu pass over a step of this exact
+        # configuration, committed under profiles/ (bytes per step, summed over the launches)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")))
+            if tr["config"] == {"batch_size": b, "mu": mu, "size": S}:
+                k = tr["per_step"]["conv_igemm_kernel"]
+                traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
+                traffic_src = "profiles/r1_conv_traffic.json (ncu dram__bytes_read+write, per step, %d launches)" % k["launches"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
                 "achieved": dom["algorithmic_tflops"], "peak": peak32, "unit": "TFLOP/s",
-                "frac": dom["algorithmic_tflops"] / peak32, "traffic": None,
+                "frac": dom["algorithmic_tflops"] / peak32, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "algorithmic_dram_bytes_per_step": dom["algorithmic_dram_bytes_per_step"],
                 "peak_source": peak_src, "share_of_step": dom["share_of_step"],
                 "launches_per_step": dom["launches_per_step"],
                 # executed MMA math / peak of the MMA kind: the forward issues 3 FP16 MMAs per

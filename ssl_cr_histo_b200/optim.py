@@ -30,6 +30,13 @@ def _tables(tensors_by_role):
     return out, n
 
 
+def _touch(params) -> None:
+    """The kernels write parameters behind autograd's version counters: mark exactly these tensors
+    as changed so cached weight packs of *other* modules (a frozen teacher) stay valid."""
+    for p in params:
+        p._b2n_epoch = getattr(p, "_b2n_epoch", 0) + 1
+
+
 def _check(p: torch.Tensor, g: torch.Tensor) -> None:
     _lib.require_device(p, "parameter")
     if p.dtype != torch.float32 or g.dtype != torch.float32:
@@ -85,7 +92,7 @@ class Adam(torch.optim.Optimizer):
                 call("b2n_adam_multi", pt, gt, mt, vt, numel, n, float(group["lr"]), float(b1),
                      float(b2), float(group["eps"]), float(group["weight_decay"]), int(step),
                      float(self.grad_scale))
-        _lib.WEIGHT_EPOCH += 1  # parameters changed behind autograd's version counters
+                _touch(ps)
         return loss
 
 
@@ -134,5 +141,5 @@ class SGD(torch.optim.Optimizer):
                 call("b2n_sgd_multi", pt, gt, bt, numel, n, float(group["lr"]),
                      float(group["momentum"]), float(group["weight_decay"]),
                      1 if group["nesterov"] else 0, first, float(self.grad_scale))
-        _lib.WEIGHT_EPOCH += 1
+                _touch(ps)
         return loss

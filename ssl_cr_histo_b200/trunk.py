@@ -52,7 +52,10 @@ class _PackCache:
         return _PackCache()
 
     def get(self, key: str, param: torch.Tensor, maker):
-        tag = (param.data_ptr(), param._version, _lib.WEIGHT_EPOCH, param.device)
+        # _b2n_epoch: bumped by kernels that write this parameter behind autograd's version counter
+        # (optim.Adam / optim.SGD); WEIGHT_EPOCH: bumped by whole-model writes (weights.lerp_)
+        tag = (param.data_ptr(), param._version, getattr(param, "_b2n_epoch", 0), _lib.WEIGHT_EPOCH,
+               param.device)
         hit = self.entries.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -223,10 +226,16 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
     oh, ol = (out_pair.hi, out_pair.lo) if out_pair is not None else (None, None)
     rh, rl = (resid_pair.hi, resid_pair.lo) if resid_pair is not None else (None, None)
     nominal = 2.0 * N * P * Q * Cout * R * S * Cin
+    # algorithmic DRAM bytes of the launch: every operand / result tensor touched once
+    n_out = float(N) * P * Q * Cout if placement[0] == 0 else float(N) * P * Q * Cout
+    byt = n_out * (4.0 * (out is not None) + 4.0 * (out_pair is not None) + 4.0 * (resid is not None)
+                   + 4.0 * (mask is not None) + 4.0 * (resid_pair is not None))
     if isinstance(x, _Act):   # hi*hi + hi*lo + lo*hi (the lo plane of integer images is skipped)
-        work = (nominal * alg, nominal * (2.0 if lo_flag is not None else 3.0), 0.0, "fwd")
+        byt += float(N) * H * W * Cin * (2.0 if lo_flag is not None else 4.0)
+        work = (nominal * alg, nominal * (2.0 if lo_flag is not None else 3.0), 0.0, "fwd", byt)
     else:
-        work = (nominal * alg, 0.0, nominal, "dgrad")
+        byt += float(N) * H * W * Cin * 4.0
+        work = (nominal * alg, 0.0, nominal, "dgrad", byt)
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, S, stride,
          pad_lo, pad_hi, pad_lo, phw, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
          lo_flag, *placement, work=work)
@@ -437,7 +446,7 @@ class _TrunkFn(torch.autograd.Function):
             with _on_side(x_in, dy):
                 dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
                 call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
-                     work=(wflops, 0.0, wflops, "wgrad"))
+                     work=(wflops, 0.0, wflops, "wgrad", 4.0 * N * (H * W * C + P * Q * K)))
                 dw = torch.empty_like(conv.weight)
                 call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
             if side is not None:
@@ -509,7 +518,7 @@ class _TrunkFn(torch.autograd.Function):
                     dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
                     call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
                          work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
-                               "wgrad"))
+                               "wgrad", 4.0 * N * H2 * W2 * (STEM_C + 64)))
                     dw = torch.empty_like(trunk.conv1.weight)
                     call("b2n_stem_unpack_wgrad", dws, dw, 64)
                 if side is not None:
