@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--workload", default="cr", choices=["cr", "rsp"],
+                    help="cr: SSL_CR consistency step (BASELINE configs[2], the headline metric); "
+                         "rsp: RSP pretext step, --rsp-batch triples (BASELINE configs[1])")
+    ap.add_argument("--rsp-batch", type=int, default=256, help="triples per rank for --workload rsp")
     ap.add_argument("--torch-optim", action="store_true",
                     help="step torch.optim.Adam instead of the multi-tensor ssl_cr_histo_b200.optim.Adam")
     ap.add_argument("--e2e-fp32", action="store_true",
@@ -160,6 +164,8 @@ def run_b200(args):
     b, mu, S = args.batch_size, args.mu, args.size
     nx, nu = 3 * b, b * mu
     torch.manual_seed(42)
+    if args.workload == "rsp":
+        return run_rsp(args, net, losses, optim, ddp, dist, dev, rank, world, local)
     student, cls_s = net.TripletNet_Finetune("resnet18"), net.FinetuneResNet(1)
     import copy
     teacher, cls_t = copy.deepcopy(student), copy.deepcopy(cls_s)
@@ -370,6 +376,91 @@ def run_b200(args):
         r = cpu_reference_step_rate(3, 1, size=S)
         line["cpu_baseline"] = {"value": r["value"], "unit": "patches/s", "cores": r["cores"],
                                 "kind": "port", "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rsp(args, net, losses, optim, ddp, dist, dev, rank, world, local):
+    """BASELINE configs[1]: the RSP pretext step of pretrain_BreastPathQ.py:42-68 -- TripletNet over a
+    resolution triple (three trunk passes, shared weights, per-pass BN statistics), Classifier(768,6),
+    cross-entropy over the 6 orders, SGD-Nesterov(lr .01, momentum .9, wd 1e-4).  One step = 3 * batch
+    patches.  Secondary workload: prints the same JSON line without roofline / cpu_baseline."""
+    from ssl_cr_histo_b200 import _lib
+    nb, S = args.rsp_batch, args.size
+    model, cls = net.TripletNet("resnet18").to(dev).train(), net.Classifier(768, 6).to(dev).train()
+    params = list(model.parameters()) + list(cls.parameters())
+    opt = (torch.optim.SGD if args.torch_optim else optim.SGD)(
+        params, lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True)       # :245
+    if not args.torch_optim:
+        opt.grad_scale = 1.0 / world
+    reducer = ddp.GradAllReducer(params) if world > 1 else None
+    g = torch.Generator().manual_seed(1000 * rank)
+    host = [torch.randint(0, 256, (nb, 3, S, S), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    host_t = torch.randint(0, 6, (nb,), generator=g).pin_memory()
+    resident = [h.to(dev).float() for h in host] + [host_t.to(dev)]
+
+    def step(i1, i2, i3, target):
+        loss, pred = losses.cross_entropy(cls(model(i1, i2, i3)), target)       # :54-56,66
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if reducer is not None:
+            reducer.all_reduce(average=args.torch_optim)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        dev_in = [h.to(dev, non_blocking=True) for h in host] + [host_t.to(dev, non_blocking=True)]
+        return float(step(*dev_in).detach())
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), _lib.launch_count() - n0
+
+    for _ in range(max(args.warmup, 3)):
+        step(*resident)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(lambda: step(*resident), args.steps)
+    sampler.stop_flag = True
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    patches = 3 * nb * world
+    line = {
+        "metric": "224x224 histo patches/sec (RSP pretext step)", "unit": "patches/s",
+        "value": patches * args.steps / (ms * 1e-3), "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 (hi,lo) error-compensated forward MMAs + tf32 backward MMAs, fp32 accumulate / storage",
+        "data": "synthetic",
+        "config": {"workload": "RSP pretext step (pretrain_BreastPathQ.py:42-68), BASELINE configs[1] per rank",
+                   "triples": nb, "image": S, "patches_per_step_per_rank": 3 * nb,
+                   "optimizer": "SGD-Nesterov(.01, .9, wd 1e-4), " + ("torch.optim" if args.torch_optim else "multi-tensor kernel"),
+                   "l2": "inputs (%.0f MB/step fp32) larger than the 126 MB L2" % (3 * nb * 3 * S * S * 4 / 1e6)},
+        "algorithmic_tflops": patches * (FLOP_FWD + FLOP_BWD) * args.steps / (ms * 1e-3) / 1e12,
+        "e2e": {"value": patches * args.steps / (ms_e2e * 1e-3), "unit": "patches/s",
+                "h2d_bytes_per_step": sum(h.numel() for h in host) + host_t.numel() * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+    }
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

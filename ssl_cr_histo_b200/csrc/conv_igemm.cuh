@@ -242,47 +242,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     } else {
-    const int PQ = p.P * p.Q;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
-      const int m0 = m_tile * kBlockM;
-      const int img = m0 / PQ;
-      const int rem = m0 - img * PQ;
-      const int op = rem / p.Q;
-      const int oq = rem - op * p.Q;
-      const int base_w = oq * p.stride - p.pad_w;
-      const int base_h = op * p.stride - p.pad_h;
-      // (r, s, channel slice) advance as nested counters: no division per k step
-      int r = 0, s = 0, cs = 0, kcoord = 0;
-      for (int ks = 0; ks < num_k_steps; ++ks) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          uint8_t* st = smem + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          if (p.a_tiled2d)
-            tma_load_2d(st, &map_a, &full_bar[stage], cs * KELEMS, m0);
-          else
-            tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
-                               static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          if (SPLIT && !skip_a_lo)
-            tma_load_im2col_4d(st + OFF_A_LO, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w,
-                               base_h, img, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          if (!RES_B) {
-            tma_load_2d(st + OFF_B, &map_b, &full_bar[stage], kcoord, n_tile * BLOCK_N);
-            if (SPLIT)
-              tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+      const int PQ = p.P * p.Q;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int m0 = m_tile * kBlockM;
+        const int img = m0 / PQ;
+        const int rem = m0 - img * PQ;
+        const int op = rem / p.Q;
+        const int oq = rem - op * p.Q;
+        const int base_w = oq * p.stride - p.pad_w;
+        const int base_h = op * p.stride - p.pad_h;
+        // (r, s, channel slice) advance as nested counters: no division per k step
+        int r = 0, s = 0, cs = 0, kcoord = 0;
+        for (int ks = 0; ks < num_k_steps; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* st = smem + stage * L::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            if (p.a_tiled2d)
+              tma_load_2d(st, &map_a, &full_bar[stage], cs * KELEMS, m0);
+            else
+              tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
+                                 static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+            if (SPLIT && !skip_a_lo)
+              tma_load_im2col_4d(st + OFF_A_LO, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w,
+                                 base_h, img, static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+            if (!RES_B) {
+              tma_load_2d(st + OFF_B, &map_b, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+              if (SPLIT)
+                tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          kcoord += KELEMS;
+          if (++cs == p.kslices) {
+            cs = 0;
+            if (++s == p.S) { s = 0; ++r; }
           }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        kcoord += KELEMS;
-        if (++cs == p.kslices) {
-          cs = 0;
-          if (++s == p.S) { s = 0; ++r; }
-        }
       }
-    }
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer
@@ -349,35 +349,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           if (++cs == p.kslices) { cs = 0; ++r; }
         }
       } else {
-      for (int ks = 0; ks < num_k_steps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
-          const uint32_t b16 =
-              RES_B ? resb16 + ks * (L::PLANES * L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
-          const uint32_t bl16 = b16 + (L::B_BYTES >> 4);  // lo tile follows hi in both layouts
-#pragma unroll
-          for (int j = 0; j < MMAS_PER_STAGE; ++j) {
-            const uint64_t da = desc0 + (a16 + 2 * j);
-            const uint64_t db = desc0 + (b16 + 2 * j);
-            if (STACK) {
-              umma_f16(d_tmem, da, db, idesc2, (ks | j) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
-              if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
-            } else if (SPLIT) {
-              umma_f16(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
-              if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
+        for (int ks = 0; ks < num_k_steps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
+            const uint32_t b16 =
+                RES_B ? resb16 + ks * (L::PLANES * L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
+            const uint32_t bl16 = b16 + (L::B_BYTES >> 4);  // lo tile follows hi in both layouts
+  #pragma unroll
+            for (int j = 0; j < MMAS_PER_STAGE; ++j) {
+              const uint64_t da = desc0 + (a16 + 2 * j);
+              const uint64_t db = desc0 + (b16 + 2 * j);
+              if (STACK) {
+                umma_f16(d_tmem, da, db, idesc2, (ks | j) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
+                if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
+              } else if (SPLIT) {
+                umma_f16(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
+                if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
+              }
             }
+            tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (ks == num_k_steps - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (ks == num_k_steps - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
