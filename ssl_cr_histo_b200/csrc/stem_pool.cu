@@ -10,6 +10,7 @@
 // padded to 32 channels (128-byte rows, the same TMA boxes / UMMA layout as every other wgrad).
 #include <cuda_fp16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "launch.h"
 #include "ptx.cuh"
@@ -209,6 +210,89 @@ __global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float
   }
 }
 
+// Same computation as a bulk-copy pipeline: a persistent block walks pooled rows (n, p); one
+// thread streams the (up to) three rows of y the row's windows cover into a double-buffered
+// shared-memory slot with a single 1-D bulk copy (TMA), so the next row's ~86 KB are in flight
+// while this one is reduced.  Adjacent pooled rows share one y row: it is re-read from L2.
+constexpr int kPoolRowThreads = 512;
+
+__global__ void __launch_bounds__(kPoolRowThreads, 1)
+bn_relu_maxpool_rows_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                            const float* __restrict__ shift, float4* __restrict__ a32,
+                            uint2* __restrict__ a_h, uint2* __restrict__ a_l,
+                            uchar4* __restrict__ idx, int N, int H, int W, int P, int Q, int C) {
+  extern __shared__ uint8_t pool_smem_raw[];
+  uint8_t* smem = pool_smem_raw + ((128u - (smem_u32(pool_smem_raw) & 127u)) & 127u);
+  const int tid = threadIdx.x;
+  const int C4 = C >> 2;
+  const uint32_t row_bytes = static_cast<uint32_t>(W) * C * 4;
+  const uint32_t slot_bytes = 3 * row_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * slot_bytes);
+  const int nbands = N * P;
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int band, int slot) {
+    const int n = band / P, p = band - n * P;
+    const int h_lo = 2 * p - 1 < 0 ? 0 : 2 * p - 1;
+    const int h_hi = 2 * p + 1 > H - 1 ? H - 1 : 2 * p + 1;
+    const uint32_t bytes = static_cast<uint32_t>(h_hi - h_lo + 1) * row_bytes;
+    mbar_arrive_expect_tx(&full_bar[slot], bytes);
+    bulk_load_1d(smem + slot * slot_bytes, y + (static_cast<size_t>(n) * H + h_lo) * W * C, bytes,
+                 &full_bar[slot]);
+  };
+  int k = 0;
+  if (tid == 0 && static_cast<int>(blockIdx.x) < nbands) issue(blockIdx.x, 0);
+  for (int band = blockIdx.x; band < nbands; band += gridDim.x, ++k) {
+    const int slot = k & 1;
+    if (tid == 0 && band + static_cast<int>(gridDim.x) < nbands) issue(band + gridDim.x, slot ^ 1);
+    mbar_wait(&full_bar[slot], (k >> 1) & 1);
+    const int n = band / P, p = band - n * P;
+    const int h_lo = 2 * p - 1 < 0 ? 0 : 2 * p - 1;
+    const float4* ys = reinterpret_cast<const float4*>(smem + slot * slot_bytes);
+    for (int i = tid; i < Q * C4; i += kPoolRowThreads) {
+      const int q = i / C4, c4 = i - q * C4;
+      const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
+      const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
+      float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+      unsigned char bi[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int h = 2 * p - 1 + r;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+          const int w = 2 * q - 1 + sx;
+          if (w < 0 || w >= W) continue;
+          const float4 v = ys[((h - h_lo) * W + w) * C4 + c4];
+          const float z[4] = {fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), fmaxf(fmaf(v.y, sc.y, sh.y), 0.f),
+                              fmaxf(fmaf(v.z, sc.z, sh.z), 0.f), fmaxf(fmaf(v.w, sc.w, sh.w), 0.f)};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (z[kk] > best[kk]) { best[kk] = z[kk]; bi[kk] = static_cast<unsigned char>(r * 3 + sx); }
+        }
+      }
+      const size_t t = (static_cast<size_t>(band) * Q) * C4 + i;
+      if (a_h != nullptr) {
+        uint2 ph, pl;
+        __half2* h2 = reinterpret_cast<__half2*>(&ph);
+        __half2* l2 = reinterpret_cast<__half2*>(&pl);
+        split_f16(best[0], best[1], h2[0], l2[0]);
+        split_f16(best[2], best[3], h2[1], l2[1]);
+        a_h[t] = ph;
+        a_l[t] = pl;
+      }
+      if (a32 != nullptr)
+        a32[t] = make_float4(tf32_rn(best[0]), tf32_rn(best[1]), tf32_rn(best[2]), tf32_rn(best[3]));
+      if (idx != nullptr) idx[t] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+    }
+    __syncthreads();  // everyone is done with this slot before it is refilled
+  }
+}
+
 // Gradient of maxpool + ReLU w.r.t. the BN output: gz[n,h,w,c] = [scale*y+shift > 0] *
 // sum over the (<= 4) windows whose recorded argmax is (h,w) of ga.
 __global__ void maxpool_relu_bwd_kernel(const float4* __restrict__ ga, const uchar4* __restrict__ idx,
@@ -269,6 +353,27 @@ int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shif
   if (C % 4 != 0) return set_error("bn_relu_maxpool: C %% 4 != 0");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 4);
+  // pipelined variant when two slots of three y rows fit in shared memory
+  const size_t smem = 2 * 3 * static_cast<size_t>(W) * C * 4 + 16 + 128;
+  if ((static_cast<size_t>(W) * C * 4) % 16 == 0 && smem <= 227 * 1024 && getenv("B2N_NO_POOL_PIPE") == nullptr) {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_rows_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return set_error("bn_relu_maxpool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured = smem;
+    }
+    int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;
+    int grid = device_sm_count() * per_sm;
+    if (grid > N * P) grid = N * P;
+    bn_relu_maxpool_rows_kernel<<<grid, kPoolRowThreads, smem, stream>>>(
+        y, scale, shift, reinterpret_cast<float4*>(a32), reinterpret_cast<uint2*>(a_h),
+        reinterpret_cast<uint2*>(a_l), reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("bn_relu_maxpool: %s", cudaGetErrorString(e));
+    return 0;
+  }
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
       reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a32),
       reinterpret_cast<uint2*>(a_h), reinterpret_cast<uint2*>(a_l), reinterpret_cast<uchar4*>(idx),
