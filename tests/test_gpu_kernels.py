@@ -541,3 +541,31 @@ def test_fused_optimizer_invalidates_packed_weights():
     with torch.no_grad():
         out1 = m(x)
     assert not torch.equal(out0, out1)
+
+
+@pytest.mark.parametrize("case", [(2, 56, 56, 64, 64, 3, 1, 1), (3, 13, 9, 64, 64, 3, 1, 1)])
+def test_tap_sharing_kernels_equal_the_per_tap_kernels(case, monkeypatch):
+    """The HALO variants (one TMA box per filter row, taps through row-shifted descriptors) and the
+    generic one-box-per-tap kernels compute the same sums: forward (both operand modes) and weight
+    gradient, bit for bit on exactly representable data (B2N_NO_HALO selects the generic path)."""
+    N, H, W, Cin, Cout, R, s, p = case
+    x = ints((N, Cin, H, W), -4, 4, 21)
+    w = ints((Cout, Cin, R, R), -2, 2, 22, 0.25)
+    dy = ints((N, Cout, H, W), -2, 2, 23, 0.5)
+    xh, xl = split_pair(to_nhwc(x))
+
+    def run():
+        y1 = conv(to_nhwc(x).to(DEV), pack_fwd(w), N, H, W, Cin, Cout, R, s, p, p)
+        y2 = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, p, p)
+        dwp = torch.zeros(Cout, R * R * Cin, device=DEV)
+        call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
+             p, p, p, p)
+        return y1, y2, dwp
+
+    halo = run()
+    monkeypatch.setenv("B2N_NO_HALO", "1")
+    plain = run()
+    ref = F.conv2d(x, w, None, s, p)
+    assert torch.equal(from_nhwc(halo[0].cpu()), ref)
+    for a, b in zip(halo, plain):
+        assert torch.equal(a, b)
