@@ -234,6 +234,8 @@ __global__ void bn_bwd_reduce_kernel(const float4* __restrict__ g, const float4*
 }
 
 // dy = gamma*invstd * (g' - sum_g/M - xhat * sum_gx/M); block 0 also emits dgamma / dbeta.
+// The per-channel constants (gamma*invstd, sum_g/M, sum_gx/M from the FP64 sums, mean, invstd, the
+// optional gate affine) are formed once per block in shared memory -- not per element.
 template <bool ROUND>
 __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* __restrict__ mask,
                                     const float4* __restrict__ y, const float* __restrict__ mean,
@@ -244,12 +246,30 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const double* __restrict__ sums, float4* __restrict__ dy,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, size_t n4,
                                     int C, double inv_count) {
-  if (blockIdx.x == 0 && dgamma != nullptr) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  extern __shared__ float chan[];  // [7][C]: gi, m1, m2, mean, invstd, gate scale, gate shift
+  float* s_gi = chan;
+  float* s_m1 = chan + C;
+  float* s_m2 = chan + 2 * C;
+  float* s_mu = chan + 3 * C;
+  float* s_is = chan + 4 * C;
+  float* s_gs = chan + 5 * C;
+  float* s_gh = chan + 6 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    s_gi[c] = gamma[c] * is;
+    s_m1[c] = static_cast<float>(sums[c] * inv_count);
+    s_m2[c] = static_cast<float>(sums[C + c] * inv_count);
+    s_mu[c] = mean[c];
+    s_is[c] = is;
+    s_gs[c] = gate_scale != nullptr ? gate_scale[c] : 0.f;
+    s_gh[c] = gate_shift != nullptr ? gate_shift[c] : 0.f;
+    if (blockIdx.x == 0 && dgamma != nullptr) {
       dbeta[c] = static_cast<float>(sums[c]);
       dgamma[c] = static_cast<float>(sums[C + c]);
     }
   }
+  __syncthreads();
+  const bool gated = gate_scale != nullptr;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const int c = static_cast<int>((i * 4) % C);
@@ -260,27 +280,29 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
       gv.z = m.z > 0.f ? gv.z : 0.f; gv.w = m.w > 0.f ? gv.w : 0.f;
     }
     const float4 yv = y[i];
-    if (gate_scale != nullptr) {
-      const float4 gs = *reinterpret_cast<const float4*>(gate_scale + c);
-      const float4 gh = *reinterpret_cast<const float4*>(gate_shift + c);
+    if (gated) {
+      const float4 gs = *reinterpret_cast<const float4*>(s_gs + c);
+      const float4 gh = *reinterpret_cast<const float4*>(s_gh + c);
       gv.x = fmaf(yv.x, gs.x, gh.x) > 0.f ? gv.x : 0.f; gv.y = fmaf(yv.y, gs.y, gh.y) > 0.f ? gv.y : 0.f;
       gv.z = fmaf(yv.z, gs.z, gh.z) > 0.f ? gv.z : 0.f; gv.w = fmaf(yv.w, gs.w, gh.w) > 0.f ? gv.w : 0.f;
     }
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
-    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 mu = *reinterpret_cast<const float4*>(s_mu + c);
+    const float4 is = *reinterpret_cast<const float4*>(s_is + c);
+    const float4 gi = *reinterpret_cast<const float4*>(s_gi + c);
+    const float4 m1 = *reinterpret_cast<const float4*>(s_m1 + c);
+    const float4 m2 = *reinterpret_cast<const float4*>(s_m2 + c);
     float o[4];
     const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
     const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
     const float mm[4] = {mu.x, mu.y, mu.z, mu.w};
     const float ii[4] = {is.x, is.y, is.z, is.w};
-    const float aa[4] = {ga.x, ga.y, ga.z, ga.w};
+    const float aa[4] = {gi.x, gi.y, gi.z, gi.w};
+    const float a1[4] = {m1.x, m1.y, m1.z, m1.w};
+    const float a2[4] = {m2.x, m2.y, m2.z, m2.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float m1 = static_cast<float>(sums[c + k] * inv_count);
-      const float m2 = static_cast<float>(sums[C + c + k] * inv_count);
       const float xh = (yy[k] - mm[k]) * ii[k];
-      float v = aa[k] * ii[k] * (gg[k] - m1 - xh * m2);
+      const float v = aa[k] * (gg[k] - a1[k] - xh * a2[k]);
       o[k] = ROUND ? tf32_rn(v) : v;
     }
     dy[i] = make_float4(o[0], o[1], o[2], o[3]);
@@ -330,12 +352,14 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
   auto m4 = reinterpret_cast<const float4*>(mask);
   auto y4 = reinterpret_cast<const float4*>(y);
   auto d4 = reinterpret_cast<float4*>(dy);
+  const size_t smem = static_cast<size_t>(7) * C * sizeof(float);
+  if (smem > 48 * 1024) return set_error("bn_bwd_apply: C=%d too large", C);
   if (round_tf32)
-    bn_bwd_apply_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(
+    bn_bwd_apply_kernel<true><<<(unsigned)blocks, threads, smem, stream>>>(
         g4, m4, y4, mean, invstd, gamma, gate_scale, gate_shift, sums, d4, dgamma, dbeta, n4, C,
         inv_count);
   else
-    bn_bwd_apply_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(
+    bn_bwd_apply_kernel<false><<<(unsigned)blocks, threads, smem, stream>>>(
         g4, m4, y4, mean, invstd, gamma, gate_scale, gate_shift, sums, d4, dgamma, dbeta, n4, C,
         inv_count);
   cudaError_t e = cudaGetLastError();
