@@ -20,15 +20,19 @@ struct GemmArgs {
   int accumulate;
 };
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TN = 64, TK = 16;
 
+// RM = rows of the micro-tile (4: 64 x 64 block tile; 2: 32 x 64, for launches whose 64-row grid
+// would leave most of the 148 SMs idle -- the heads' GEMMs have only 704 x 256..1024 outputs)
+template <int RM>
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  constexpr int TM = 16 * RM;
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a 4 x 4 micro-tile
-  float acc[4][4] = {};
+  float acc[RM][4] = {};
   const bool a_kfast = g.sak == 1;  // choose the smem fill order that keeps gmem reads coalesced
   const bool b_kfast = g.sbk == 1;
   for (int k0 = 0; k0 < g.K; k0 += TK) {
@@ -51,21 +55,21 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      float av[4], bv[4];
+      float av[RM], bv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < RM; ++i) av[i] = As[kk][ty * RM + i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= g.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -84,8 +88,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 
 static int run_gemm(const GemmArgs& g, cudaStream_t stream, const char* who) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM);
-  sgemm_kernel<<<grid, 256, 0, stream>>>(g);
+  const long long blocks64 = 1ll * ((g.N + TN - 1) / TN) * ((g.M + 63) / 64);
+  if (blocks64 < 2ll * device_sm_count()) {
+    dim3 grid((g.N + TN - 1) / TN, (g.M + 31) / 32);
+    sgemm_kernel<2><<<grid, 256, 0, stream>>>(g);
+  } else {
+    dim3 grid((g.N + TN - 1) / TN, (g.M + 63) / 64);
+    sgemm_kernel<4><<<grid, 256, 0, stream>>>(g);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s: %s", who, cudaGetErrorString(e));
   return 0;
