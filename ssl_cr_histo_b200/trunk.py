@@ -501,18 +501,27 @@ class _TrunkFn(torch.autograd.Function):
         if min_unit == 0:
             H2, W2 = sv["H"] // 2, sv["W"] // 2
             bn0 = sv["bn0"]
-            # maxpool + ReLU + BN backward fused: two sweeps over the stem output instead of five
-            sums = torch.zeros(2 * 64, device=dev, dtype=torch.float64)
-            call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
-                 bn0.invstd, sums, N, H2, W2, 64)
-            dy0 = torch.empty_like(sv["y0"])
-            dgamma, dbeta = torch.empty(64, device=dev), torch.empty(64, device=dev)
-            call("b2n_pool_bn_bwd_apply", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
-                 bn0.invstd, trunk.bn1.weight, sums, dy0, dgamma, dbeta, N, H2, W2, 64, 1)
-            if need[id(trunk.bn1.weight)]:
-                grads[id(trunk.bn1.weight)] = dgamma
-            if need[id(trunk.bn1.bias)]:
-                grads[id(trunk.bn1.bias)] = dbeta
+            # two double-buffered band slots (2 rows of y + 2 pooled rows of gradients / codes) must
+            # fit in shared memory: patches up to ~300 px wide; wider ones take the unfused chain
+            q2 = (W2 - 1) // 2 + 1
+            if 2 * (2 * W2 * 64 * 4 + 2 * q2 * 64 * 5) + 1024 <= 227 * 1024:
+                # maxpool + ReLU + BN backward fused: two sweeps over the stem output instead of five
+                sums = torch.zeros(2 * 64, device=dev, dtype=torch.float64)
+                call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
+                     bn0.invstd, sums, N, H2, W2, 64)
+                dy0 = torch.empty_like(sv["y0"])
+                dgamma, dbeta = torch.empty(64, device=dev), torch.empty(64, device=dev)
+                call("b2n_pool_bn_bwd_apply", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
+                     bn0.invstd, trunk.bn1.weight, sums, dy0, dgamma, dbeta, N, H2, W2, 64, 1)
+                if need[id(trunk.bn1.weight)]:
+                    grads[id(trunk.bn1.weight)] = dgamma
+                if need[id(trunk.bn1.bias)]:
+                    grads[id(trunk.bn1.bias)] = dbeta
+            else:
+                gz = torch.empty_like(sv["y0"])
+                call("b2n_maxpool_relu_bwd", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, gz, N, H2,
+                     W2, 64)
+                dy0 = bn_backward(gz, None, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
             if need[id(trunk.conv1.weight)]:
                 with _on_side(sv["xs"], dy0):
                     dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)

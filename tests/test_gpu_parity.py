@@ -363,9 +363,10 @@ def test_wsi_heatmap_inference_matches_reference_loop():
     assert torch.equal(u8, infer.tumor_probabilities(gm, gh, xs[0].to(DEV)))
 
 
-@pytest.mark.parametrize("N,H,W", [(1, 64, 96), (3, 34, 46)])
+@pytest.mark.parametrize("N,H,W", [(1, 64, 96), (3, 34, 46), (2, 32, 640)])
 def test_single_patch_and_non_square_train_step(N, H, W):
-    """Edge shapes through the whole path: a batch of one / odd pooled sizes / non-square patches,
+    """Edge shapes through the whole path: a batch of one / odd pooled sizes / non-square patches /
+    a patch too wide for the fused stem backward's shared-memory bands (unfused chain instead);
     full fine-tune step (forward, CE-9 loss, backward) against the oracle."""
     om, oh, gm, gh = pair("finetune", ("finetune", 9))
     g = torch.Generator().manual_seed(90 + N)
