@@ -206,3 +206,45 @@ def test_fused_optimizers_keep_the_torch_optim_contract():
     p[0].grad = torch.zeros(4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         adam.step()                                                     # CPU tensors fail loudly
+
+
+def test_python_binding_argument_counts_match_the_header():
+    """Every ctypes signature in _lib.py has exactly the parameters include/b2n.h declares (the last
+    one being `void* stream`) -- a drifted binding would silently shift arguments."""
+    header = open(os.path.join(ROOT, "include", "b2n.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)          # strip comments
+    for name, sig in _lib._SIGNATURES.items():
+        m = re.search(r"\bint\s+%s\s*\((.*?)\)\s*;" % name, header, flags=re.S)
+        assert m, "no declaration of %s in b2n.h" % name
+        params = [p.strip() for p in m.group(1).split(",")]
+        assert params[-1].replace(" ", "") == "void*stream", name
+        assert len(params) == len(sig) + 1, "%s: header has %d parameters, binding %d" % (
+            name, len(params), len(sig) + 1)
+        for decl, ct in zip(params, sig):                            # pointers vs scalars line up
+            is_ptr = "*" in decl
+            assert is_ptr == (ct is ctypes.c_void_p), "%s: `%s` bound as %s" % (name, decl, ct.__name__)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the CUDA arm) exits 0 and
+    prints one JSON line with the contract's keys; non-zero ranks stay silent."""
+    import json
+    import subprocess
+
+    env = dict(os.environ, RANK="0", OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0", "--size", "64"], capture_output=True,
+                         text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline",
+                "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "patches/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
+    silent = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                             "--steps", "1", "--warmup", "0", "--size", "64"], capture_output=True,
+                            text=True, env=dict(env, RANK="1"), timeout=600)
+    assert silent.returncode == 0 and silent.stdout.strip() == ""
