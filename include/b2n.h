@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 1
+#define B2N_ABI_VERSION 2
 
 /* IEEE binary16 storage (the FP16 operand planes of the forward convolutions). */
 typedef uint16_t b2n_half;
@@ -59,9 +59,16 @@ int b2n_device_ok(void);
  * goes to (o_h0 + i*o_step, o_w0 + j*o_step) of an [N,o_H,o_W,Cout] tensor (resid / mask are
  * addressed the same way; pixels outside are dropped) -- the parity classes of a stride-2 data
  * gradient (b2n_pack_weight_dgrad_s2).
+ *           then (data-gradient launches, both optional): the result is zeroed where
+ *           gate[..] <= 0 (the ReLU gate of the activation this gradient belongs to; addressed like
+ *           the output; not together with mask), and -- bnb_y given -- it is treated as the gradient
+ *           g w.r.t. relu(bn(y)) of the BatchNorm whose raw input is bnb_y: with bnb_scale/shift the
+ *           gate fmaf(y, scale, shift) > 0 is applied to g, and stats[0][k] += sum g,
+ *           stats[1][k] += sum g * (y - bnb_mean[k]) * bnb_invstd[k] (b2n_bn_bwd_reduce's sums,
+ *           taken while the tile is still on chip; dense fp32 result only).
  * stats (optional, [2][Cout] doubles, caller-zeroed; not together with scale/shift): += per-channel
- * sum / sum of squares of the raw accumulator -- the BatchNorm batch statistics.  Cout a multiple
- * of 64.
+ * sum / sum of squares of the raw accumulator -- the BatchNorm batch statistics (without bnb_y).
+ * Cout a multiple of 64.
  * Replaces: tv:92,96,100 (conv3x3 / downsample conv in BasicBlock.forward), tv:268 (stem, via
  * the space-to-depth view), and the conv dgrad reached from loss.backward()
  * (pretrain_BreastPathQ.py:60, eval_BreastPathQ_SSL_CR.py:99). */
@@ -72,7 +79,9 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
                  const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
                  const float* mask, int relu, int round_tf32, double* stats,
                  const int* x_l_nonzero /* optional device flag: 0 => x_l is all zero, skip it */,
-                 int o_step, int o_h0, int o_w0, int o_H, int o_W, void* stream);
+                 int o_step, int o_h0, int o_w0, int o_H, int o_W, const float* gate,
+                 const float* bnb_y, const float* bnb_mean, const float* bnb_invstd,
+                 const float* bnb_scale, const float* bnb_shift, void* stream);
 
 /* Weight gradient, split-K over pixels, accumulated atomically:
  *   dw_packed[k][(r*S+s)*Cin + c] += sum_{n,p,q} dy[n,p,q,k] * x[n, p*stride-pad+r, q*stride-pad+s, c]
@@ -93,7 +102,10 @@ int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, 
  * over dY, packs stored back to back [C][ntaps*K] in class order (0,0), (0,1), (1,0), (1,1);
  * 9*C*K floats. */
 int b2n_pack_weight_dgrad_s2(const float* w, float* w_packed, int K, int C, void* stream);
-int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, void* stream);
+/* accumulate != 0: dw += (several passes over shared weights feed one gradient slot, e.g. the
+ * three trunk passes of TripletNet.forward or a flat all-reduce arena). */
+int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, int accumulate,
+                     void* stream);
 
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
 /* x NCHW fp32 (N,3,H,W), H and W even -> NHWC space-to-depth views (12 real channels): the
@@ -110,7 +122,7 @@ int b2n_stem_pack_input_u8(const unsigned char* x_nchw, b2n_half* xs_h, float* x
 /* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16 taps * 16];  packed gradient [K][16 taps * 32] ->
  * (K,3,7,7). */
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream);
-int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream);
+int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, void* stream);
 
 /* ---- BatchNorm / ReLU / residual (tv:93-103,269-270; nn.BatchNorm2d train + eval) -------- */
 /* Batch statistics -> per-channel affine (scale = gamma*invstd, shift = beta - mean*scale),
@@ -144,7 +156,8 @@ int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const f
 int b2n_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
                      const float* invstd, const float* gamma, const float* gate_scale,
                      const float* gate_shift, const double* sums, float* dy, float* dgamma,
-                     float* dbeta, long long rows, int C, int round_tf32, void* stream);
+                     float* dbeta, long long rows, int C, int round_tf32,
+                     int accumulate /* dgamma / dbeta += instead of = */, void* stream);
 /* up[n,2p,2q,:] = dy[n,p,q,:], zero elsewhere: stride-2 data gradient as a stride-1 conv. */
 int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                       void* stream);
@@ -170,10 +183,13 @@ int b2n_pool_bn_bwd_apply(const float* ga, const unsigned char* argmax_idx, cons
                           const float* scale, const float* shift, const float* mean,
                           const float* invstd, const float* gamma, const double* sums, float* dy,
                           float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
-                          void* stream);
+                          int accumulate /* dgamma / dbeta += instead of = */, void* stream);
 int b2n_avgpool_fwd(const b2n_half* a_h, const b2n_half* a_l, float* e, int N, int HW, int C,
                     void* stream);
-int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream);
+/* g[n,i,c] = ge[n,c] / HW, zeroed where gate[n,i,c] <= 0 (gate optional: the pooled activation,
+ * whose ReLU gate is applied here so that no consumer of g reads a mask). */
+int b2n_avgpool_bwd(const float* ge, const float* gate, float* g, int N, int HW, int C,
+                    void* stream);
 
 /* ---- fully-connected heads, exact FP32 (models/net.py:12-15,36-37,60-62,110) ------------- */
 int b2n_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,

@@ -19,28 +19,28 @@ P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 
 # name -> argument ctypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
-    "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P, P] + [I] * 5,
+    "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P, P] + [I] * 5 + [P] * 6,
     "b2n_conv_wgrad": [P, P, P] + [I] * 12,
     "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
     "b2n_pack_weight_dgrad_s2": [P, P, I, I],
-    "b2n_unpack_wgrad": [P, P, I, I, I, I],
+    "b2n_unpack_wgrad": [P, P, I, I, I, I, I],
     "b2n_stem_pack_input": [P, P, P, P, P, I, I, I],
     "b2n_stem_pack_input_u8": [P, P, P, I, I, I],
     "b2n_stem_pack_weight": [P, P, P, I],
-    "b2n_stem_unpack_wgrad": [P, P, I],
+    "b2n_stem_unpack_wgrad": [P, P, I, I],
     "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
     "b2n_bn_apply": [P] * 11 + [LL, I, I, I],
     "b2n_bn_bwd_reduce": [P] * 8 + [LL, I],
-    "b2n_bn_bwd_apply": [P] * 12 + [LL, I, I],
+    "b2n_bn_bwd_apply": [P] * 12 + [LL, I, I, I],
     "b2n_upsample_zero": [P, P] + [I] * 6,
     "b2n_bn_relu_maxpool": [P] * 7 + [I] * 4,
     "b2n_maxpool_relu_bwd": [P] * 6 + [I] * 4,
     "b2n_pool_bn_bwd_reduce": [P] * 8 + [I] * 4,
-    "b2n_pool_bn_bwd_apply": [P] * 12 + [I] * 5,
+    "b2n_pool_bn_bwd_apply": [P] * 12 + [I] * 6,
     "b2n_avgpool_fwd": [P, P, P, I, I, I],
-    "b2n_avgpool_bwd": [P, P, I, I, I],
+    "b2n_avgpool_bwd": [P, P, P, I, I, I],
     "b2n_linear_fwd": [P, LL, P, LL, P, P, LL, I, I, I, I, I],
     "b2n_linear_bwd_data": [P, LL, P, LL, P, LL, P, I, I, I, I],
     "b2n_linear_bwd_weight": [P, LL, P, LL, P, LL, P, I, I, I, I],
@@ -67,7 +67,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
             raise RuntimeError("libb2n.so is missing (%s); run __graft_entry__.build()" % LIB_PATH)
         from . import build as _build
 
-        _build.build_lib()
+        _build.build_lib()      # serialised across processes by a file lock (one rank compiles)
     lib = ctypes.CDLL(LIB_PATH)
     lib.b2n_version.restype = c_int
     lib.b2n_last_error.restype = c_char_p
@@ -96,8 +96,24 @@ def _conv(a):
 PROFILE = None
 
 
-def call(name: str, *args, work=0.0) -> None:
-    """Invoke an entry point on the current CUDA stream; raise on a non-zero return code."""
+def call(name: str, *args, work=0.0, device=None) -> None:
+    """Invoke an entry point on the current CUDA stream of the device that owns the tensor
+    arguments (``device``: for entry points that take pointer tables instead of tensors) --
+    switching device for the call if it is not the current one, since the library's launches and
+    per-device function attributes follow cudaGetDevice; raise on a non-zero return code."""
+    if device is None:
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                device = a.device
+                break
+    if device is not None and device.type == "cuda" and device.index is not None and \
+            device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            return _call(name, args, work)
+    return _call(name, args, work)
+
+
+def _call(name: str, args, work) -> None:
     lib = load()
     stream = torch.cuda.current_stream().cuda_stream
     prof = PROFILE.get(name) if PROFILE is not None else None

@@ -33,13 +33,27 @@ def _stale(target: str) -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """Compile libb2n.so in-tree.  Several ranks may import the package at once on a box where the
+    library is missing: an exclusive file lock lets one of them compile (into a temporary name,
+    renamed atomically) while the others wait and then find it fresh."""
+    import fcntl
+
     if not force and not _stale(LIB):
         return LIB
-    cmd = ["nvcc", *ARCH, *COMMON, "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
-           "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale(LIB):       # another process built it while we waited
+                return LIB
+            tmp = "%s.%d.tmp" % (LIB, os.getpid())
+            cmd = ["nvcc", *ARCH, *COMMON, "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+                   "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.run(cmd, check=True)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

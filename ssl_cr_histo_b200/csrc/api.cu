@@ -42,8 +42,12 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
                  const float* resid, const b2n_half* resid_h, const b2n_half* resid_l,
                  const float* mask, int relu, int round_tf32, double* stats,
                  const int* x_l_nonzero, int o_step, int o_h0, int o_w0, int o_H, int o_W,
+                 const float* gate, const float* bnb_y, const float* bnb_mean,
+                 const float* bnb_invstd, const float* bnb_scale, const float* bnb_shift,
                  void* stream) {
   ConvArgs a;
+  a.gate = gate; a.bnb_y = bnb_y; a.bnb_mean = bnb_mean; a.bnb_invstd = bnb_invstd;
+  a.bnb_scale = bnb_scale; a.bnb_shift = bnb_shift;
   a.a_lo_nonzero = x_l_nonzero;
   a.o_step = o_step; a.o_h0 = o_h0; a.o_w0 = o_w0; a.o_H = o_H; a.o_W = o_W;
   a.x = x; a.w = w_packed;
@@ -78,8 +82,9 @@ int b2n_pack_weight_dgrad(const float* w, float* wp, int K, int C, int R, int Sf
 int b2n_pack_weight_dgrad_s2(const float* w, float* wp, int K, int C, void* stream) {
   return counted(launch_pack_dgrad_s2(w, wp, K, C, S(stream)));
 }
-int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, void* stream) {
-  return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, S(stream)));
+int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, int accumulate,
+                     void* stream) {
+  return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, accumulate, S(stream)));
 }
 
 int b2n_stem_pack_input(const float* x, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
@@ -94,8 +99,8 @@ int b2n_stem_pack_input_u8(const unsigned char* x, b2n_half* xs_h, float* xs32, 
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream) {
   return counted(launch_stem_pack_weight(w, H16(ws_h), H16(ws_l), K, S(stream)));
 }
-int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, void* stream) {
-  return counted(launch_stem_unpack_wgrad(dws, dw, K, S(stream)));
+int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, void* stream) {
+  return counted(launch_stem_unpack_wgrad(dws, dw, K, accumulate, S(stream)));
 }
 
 int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
@@ -125,9 +130,10 @@ int b2n_bn_bwd_reduce(const float* g, const float* mask, const float* y, const f
 int b2n_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
                      const float* invstd, const float* gamma, const float* gate_scale,
                      const float* gate_shift, const double* sums, float* dy, float* dgamma,
-                     float* dbeta, long long rows, int C, int round_tf32, void* stream) {
+                     float* dbeta, long long rows, int C, int round_tf32, int accumulate,
+                     void* stream) {
   return counted(launch_bn_bwd_apply(g, mask, y, mean, invstd, gamma, gate_scale, gate_shift, sums, dy,
-                                     dgamma, dbeta, rows, C, round_tf32, S(stream)));
+                                     dgamma, dbeta, rows, C, round_tf32, accumulate, S(stream)));
 }
 int b2n_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                       void* stream) {
@@ -156,16 +162,18 @@ int b2n_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const float
                           const float* scale, const float* shift, const float* mean,
                           const float* invstd, const float* gamma, const double* sums, float* dy,
                           float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
-                          void* stream) {
+                          int accumulate, void* stream) {
   return counted(launch_pool_bn_bwd_apply(ga, idx, y, scale, shift, mean, invstd, gamma, sums, dy,
-                                          dgamma, dbeta, N, H, W, C, round_tf32, S(stream)));
+                                          dgamma, dbeta, N, H, W, C, round_tf32, accumulate,
+                                          S(stream)));
 }
 int b2n_avgpool_fwd(const b2n_half* a_h, const b2n_half* a_l, float* e, int N, int HW, int C,
                     void* stream) {
   return counted(launch_avgpool_fwd(H16(a_h), H16(a_l), e, N, HW, C, S(stream)));
 }
-int b2n_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, void* stream) {
-  return counted(launch_avgpool_bwd(ge, g, N, HW, C, S(stream)));
+int b2n_avgpool_bwd(const float* ge, const float* gate, float* g, int N, int HW, int C,
+                    void* stream) {
+  return counted(launch_avgpool_bwd(ge, gate, g, N, HW, C, S(stream)));
 }
 
 int b2n_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,

@@ -245,7 +245,7 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const float* __restrict__ gate_shift,
                                     const double* __restrict__ sums, float4* __restrict__ dy,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, size_t n4,
-                                    int C, double inv_count) {
+                                    int C, double inv_count, int accumulate) {
   extern __shared__ float chan[];  // [7][C]: gi, m1, m2, mean, invstd, gate scale, gate shift
   float* s_gi = chan;
   float* s_m1 = chan + C;
@@ -264,8 +264,9 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
     s_gs[c] = gate_scale != nullptr ? gate_scale[c] : 0.f;
     s_gh[c] = gate_shift != nullptr ? gate_shift[c] : 0.f;
     if (blockIdx.x == 0 && dgamma != nullptr) {
-      dbeta[c] = static_cast<float>(sums[c]);
-      dgamma[c] = static_cast<float>(sums[C + c]);
+      // accumulate: += into a gradient slot that other passes over the same weights also feed
+      dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(sums[c]);
+      dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(sums[C + c]);
     }
   }
   __syncthreads();
@@ -337,7 +338,8 @@ int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, cons
 int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
                         const float* invstd, const float* gamma, const float* gate_scale,
                         const float* gate_shift, const double* sums, float* dy, float* dgamma,
-                        float* dbeta, long long rows, int C, int round_tf32, cudaStream_t stream) {
+                        float* dbeta, long long rows, int C, int round_tf32, int accumulate,
+                        cudaStream_t stream) {
   if ((gate_scale != nullptr) != (gate_shift != nullptr))
     return set_error("bn_bwd_apply: gate_scale and gate_shift come as a pair");
   if (C % 4 != 0) return set_error("bn_bwd_apply: C %% 4 != 0");
@@ -357,11 +359,11 @@ int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const
   if (round_tf32)
     bn_bwd_apply_kernel<true><<<(unsigned)blocks, threads, smem, stream>>>(
         g4, m4, y4, mean, invstd, gamma, gate_scale, gate_shift, sums, d4, dgamma, dbeta, n4, C,
-        inv_count);
+        inv_count, accumulate);
   else
     bn_bwd_apply_kernel<false><<<(unsigned)blocks, threads, smem, stream>>>(
         g4, m4, y4, mean, invstd, gamma, gate_scale, gate_shift, sums, d4, dgamma, dbeta, n4, C,
-        inv_count);
+        inv_count, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_bwd_apply: %s", cudaGetErrorString(e));
   return 0;

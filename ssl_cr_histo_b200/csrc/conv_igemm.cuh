@@ -62,9 +62,19 @@ struct ConvParams {
   const __half* resid_h;  // (hi, lo) FP16 residual (identity shortcut) or null
   const __half* resid_l;
   const float* mask;      // when set, resid is only added where mask > 0 (ReLU gate)
+  const float* gate;      // when set, the whole result is zeroed where gate <= 0 (not with mask)
+  // BatchNorm-backward statistics of the result (data-gradient launches): the result g is the
+  // gradient w.r.t. relu(bn(y)); with bnb_scale/shift the ReLU gate fmaf(y, scale, shift) > 0 is
+  // applied to g first.  stats[0][k] += sum g, stats[1][k] += sum g * (y - mean[k]) * invstd[k].
+  const float* bnb_y;
+  const float* bnb_mean;
+  const float* bnb_invstd;
+  const float* bnb_scale;
+  const float* bnb_shift;
   int relu;
   int round_tf32;
-  double* stats;  // [2][Cout] per-channel sum / sum of squares of the raw accumulator, or null
+  double* stats;  // [2][Cout] per-channel sum / sum of squares of the raw accumulator (or the
+                  // BatchNorm-backward sums when bnb_y is set), or null
   // Strided output placement (parity classes of a stride-2 data gradient): output pixel (i, j)
   // of image n is stored at (o_h0 + i*o_step, o_w0 + j*o_step) of an [*, o_H, o_W, Cout]
   // tensor; pixels falling outside are dropped.  o_step == 0 selects the dense layout.
@@ -111,7 +121,8 @@ struct ConvSmem {
 // 128 x 64 tile is only ~1-3.5k tensor-pipe cycles), so their launches use specialised kernels.
 enum : int {
   kEpiStats = 1, kEpiAffine = 2, kEpiResid32 = 4, kEpiMask = 8, kEpiResid16 = 16, kEpiRelu = 32,
-  kEpiOut32 = 64, kEpiOut16 = 128, kEpiRound = 256
+  kEpiOut32 = 64, kEpiOut16 = 128, kEpiRound = 256, kEpiGate = 512, kEpiBnBwd = 1024,
+  kEpiBnGate = 2048
 };
 __host__ __device__ constexpr bool epi_on(int epi, int bit, bool runtime) {
   return epi >= 0 ? (epi & bit) != 0 : runtime;
@@ -383,7 +394,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ========================================================= epilogue
-    const bool f_stats = epi_on(EPI, kEpiStats, p.stats != nullptr);
+    const bool f_stats = epi_on(EPI, kEpiStats, p.stats != nullptr && p.bnb_y == nullptr);
     const bool f_affine = epi_on(EPI, kEpiAffine, p.scale != nullptr);
     const bool f_resid = epi_on(EPI, kEpiResid32, p.resid != nullptr);
     const bool f_mask = epi_on(EPI, kEpiMask, p.mask != nullptr);
@@ -392,6 +403,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     const bool f_out32 = epi_on(EPI, kEpiOut32, p.out != nullptr);
     const bool f_out16 = epi_on(EPI, kEpiOut16, p.out_h != nullptr);
     const bool f_round = epi_on(EPI, kEpiRound, p.round_tf32 != 0);
+    const bool f_gate = epi_on(EPI, kEpiGate, p.gate != nullptr);
+    const bool f_bnb = epi_on(EPI, kEpiBnBwd, p.bnb_y != nullptr);
+    const bool f_bngate = epi_on(EPI, kEpiBnGate, p.bnb_scale != nullptr);
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int ew = warp - 2;    // epilogue warp index (its private staging tile / statistics row)
     const int row_in_tile = quad * 32 + lane;
@@ -435,8 +449,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       // flight instead of one load -> use -> store round trip per row group (the stores may alias,
       // so the compiler cannot hoist).  64-wide tiles fetch the whole tile *before* waiting for the
       // accumulator, hiding the HBM latency behind the tile's MMAs.
-      auto prefetch = [&](int ch, float4(&pre_r)[8], float4(&pre_m)[8], uint2(&pre_h)[8],
-                          uint2(&pre_l)[8]) {
+      // pre_m holds the mask or the gate (mutually exclusive), pre_x the FP16 residual pair
+      // (hi in .x/.y, lo in .z/.w) or the bits of the BatchNorm-backward y (mutually exclusive).
+      auto prefetch = [&](int ch, float4(&pre_r)[8], float4(&pre_m)[8], uint4(&pre_x)[8]) {
         const int c4 = n_tile * BLOCK_N + ch * 32 + 4 * (lane & 7);
         if (f_resid) {
 #pragma unroll
@@ -444,31 +459,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             pre_r[sl] = row4[sl] != 0xFFFFFFFFu
                             ? *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(row4[sl]) << 2) + c4)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (f_mask) {
+        }
+        if ((f_resid && f_mask) || f_gate) {
+          const float* src = f_gate ? p.gate : p.mask;
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl)
-              pre_m[sl] = row4[sl] != 0xFFFFFFFFu
-                              ? *reinterpret_cast<const float4*>(p.mask + (static_cast<size_t>(row4[sl]) << 2) + c4)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int sl = 0; sl < 8; ++sl)
+            pre_m[sl] = row4[sl] != 0xFFFFFFFFu
+                            ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(row4[sl]) << 2) + c4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (f_resid16) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl) {
             const bool ok = row4[sl] != 0xFFFFFFFFu;
             const size_t o = (static_cast<size_t>(row4[sl]) << 2) + c4;
-            pre_h[sl] = ok ? *reinterpret_cast<const uint2*>(p.resid_h + o) : make_uint2(0u, 0u);
-            pre_l[sl] = ok ? *reinterpret_cast<const uint2*>(p.resid_l + o) : make_uint2(0u, 0u);
+            const uint2 h = ok ? *reinterpret_cast<const uint2*>(p.resid_h + o) : make_uint2(0u, 0u);
+            const uint2 l = ok ? *reinterpret_cast<const uint2*>(p.resid_l + o) : make_uint2(0u, 0u);
+            pre_x[sl] = make_uint4(h.x, h.y, l.x, l.y);
           }
+        } else if (f_bnb) {
+#pragma unroll
+          for (int sl = 0; sl < 8; ++sl)
+            pre_x[sl] = row4[sl] != 0xFFFFFFFFu
+                            ? *reinterpret_cast<const uint4*>(p.bnb_y + (static_cast<size_t>(row4[sl]) << 2) + c4)
+                            : make_uint4(0u, 0u, 0u, 0u);
         }
       };
       const uint32_t t_addr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
       auto process = [&](int ch, const float4(&pre_r)[8], const float4(&pre_m)[8],
-                         const uint2(&pre_h)[8], const uint2(&pre_l)[8]) {
+                         const uint4(&pre_x)[8]) {
         float v[32];
         tmem_ld_32x32(t_addr + ch * 32, v);
         const int n0 = n_tile * BLOCK_N + ch * 32;
         const int c4 = n0 + 4 * (lane & 7);
+        // per-channel constants of the BatchNorm-backward statistics (this lane's four channels)
+        float4 b_mu = make_float4(0.f, 0.f, 0.f, 0.f), b_is = b_mu, b_sc = b_mu, b_sh = b_mu;
+        if (f_bnb) {
+          b_mu = *reinterpret_cast<const float4*>(p.bnb_mean + c4);
+          b_is = *reinterpret_cast<const float4*>(p.bnb_invstd + c4);
+          if (f_bngate) {
+            b_sc = *reinterpret_cast<const float4*>(p.bnb_scale + c4);
+            b_sh = *reinterpret_cast<const float4*>(p.bnb_shift + c4);
+          }
+        }
         if (STACK) {  // second accumulator half: the hi * W_lo products
           float v2[32];
           tmem_ld_32x32(t_addr + BLOCK_N + ch * 32, v2);
@@ -521,7 +554,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               if (f_resid) {
                 const float4 r0 = pre_r[sl];
                 float rr[4] = {r0.x, r0.y, r0.z, r0.w};
-                if (f_mask) {
+                if (f_mask && !f_gate) {
                   const float4 m0 = pre_m[sl];
                   rr[0] = m0.x > 0.f ? rr[0] : 0.f; rr[1] = m0.y > 0.f ? rr[1] : 0.f;
                   rr[2] = m0.z > 0.f ? rr[2] : 0.f; rr[3] = m0.w > 0.f ? rr[3] : 0.f;
@@ -530,8 +563,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                 for (int k = 0; k < 4; ++k) o[k] += rr[k];
               }
               if (f_resid16) {
-                const uint2 rh = pre_h[sl];
-                const uint2 rl = pre_l[sl];
+                const uint2 rh = make_uint2(pre_x[sl].x, pre_x[sl].y);
+                const uint2 rl = make_uint2(pre_x[sl].z, pre_x[sl].w);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
                 const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
@@ -544,6 +577,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               if (f_relu) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
+              }
+              if (f_gate) {   // ReLU gate of the tensor this gradient belongs to
+                const float4 g0 = pre_m[sl];
+                o[0] = g0.x > 0.f ? o[0] : 0.f; o[1] = g0.y > 0.f ? o[1] : 0.f;
+                o[2] = g0.z > 0.f ? o[2] : 0.f; o[3] = g0.w > 0.f ? o[3] : 0.f;
+              }
+              if (f_bnb) {    // BatchNorm-backward sums of the (gated) gradient
+                const float yv[4] = {__uint_as_float(pre_x[sl].x), __uint_as_float(pre_x[sl].y),
+                                     __uint_as_float(pre_x[sl].z), __uint_as_float(pre_x[sl].w)};
+                const float mu[4] = {b_mu.x, b_mu.y, b_mu.z, b_mu.w};
+                const float is[4] = {b_is.x, b_is.y, b_is.z, b_is.w};
+                if (f_bngate) {
+                  const float sc[4] = {b_sc.x, b_sc.y, b_sc.z, b_sc.w};
+                  const float sh[4] = {b_sh.x, b_sh.y, b_sh.z, b_sh.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) o[k] = fmaf(yv[k], sc[k], sh[k]) > 0.f ? o[k] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  st_s[k] += o[k];
+                  st_q[k] += o[k] * (yv[k] - mu[k]) * is[k];
+                }
               }
               if (f_out16) {
                 uint2 ph, pl;
@@ -565,7 +620,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           }
           __syncwarp();
         }
-        if (f_stats) {
+        if (f_stats || f_bnb) {
           // lanes l, l+8, l+16, l+24 hold the same four channels (different rows); each epilogue
           // warp accumulates into its own smem row (no atomics, no cross-warp contention)
 #pragma unroll
@@ -586,29 +641,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         // one chunk per warp: warps 2..5 take columns 0..31, warps 6..9 columns 32..63
         const int ch = ew >> 2;
         float4 pr[8], pm[8];
-        uint2 ph[8], pl[8];
-        prefetch(ch, pr, pm, ph, pl);
+        uint4 px[8];
+        prefetch(ch, pr, pm, px);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        process(ch, pr, pm, ph, pl);
+        process(ch, pr, pm, px);
       } else if constexpr (BLOCK_N == 64 && EPI >= 0) {
         float4 pr0[8], pm0[8], pr1[8], pm1[8];
-        uint2 ph0[8], pl0[8], ph1[8], pl1[8];
-        prefetch(0, pr0, pm0, ph0, pl0);
-        prefetch(1, pr1, pm1, ph1, pl1);
+        uint4 px0[8], px1[8];
+        prefetch(0, pr0, pm0, px0);
+        prefetch(1, pr1, pm1, px1);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        process(0, pr0, pm0, ph0, pl0);
-        process(1, pr1, pm1, ph1, pl1);
+        process(0, pr0, pm0, px0);
+        process(1, pr1, pm1, px1);
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
           float4 pr[8], pm[8];
-          uint2 ph[8], pl[8];
-          prefetch(ch, pr, pm, ph, pl);
-          process(ch, pr, pm, ph, pl);
+          uint4 px[8];
+          prefetch(ch, pr, pm, px);
+          process(ch, pr, pm, px);
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back
@@ -617,7 +672,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (f_stats) {
+    if (f_stats || f_bnb) {
       // epilogue-only named barrier (warps 2..5 = 128 threads), then flush CTA partials
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * EPI_WARPS) {

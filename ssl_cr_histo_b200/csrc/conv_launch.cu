@@ -22,12 +22,15 @@ int elementwise_blocks_per_sm() {
 }
 
 int device_sm_count() {
-  static int sms = 0;
+  static int cache[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool cached = dev >= 0 && dev < kMaxDevices;
+  int sms = cached ? __atomic_load_n(&cache[dev], __ATOMIC_RELAXED) : 0;
   if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
+    if (cached) __atomic_store_n(&cache[dev], sms, __ATOMIC_RELAXED);
   }
   return sms;
 }
@@ -45,12 +48,13 @@ static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cuda
   auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS>;
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         RES_B ? kMaxDynSmem : L::total(0));
+  static PerDeviceMax configured;
+  const int want = RES_B ? kMaxDynSmem : L::total(0);
+  int dev;
+  if (configured.needs(want, &dev)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) return set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+    configured.set(dev, want);
   }
   kern<<<grid, conv_threads(EPI_WARPS), smem, stream>>>(m.a, m.b, m.a_lo, m.b_lo, p);
   cudaError_t e = cudaGetLastError();
@@ -119,6 +123,9 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.scale = a.scale; p.shift = a.shift; p.resid = a.resid; p.resid_h = a.resid_h;
   p.resid_l = a.resid_l; p.mask = a.mask; p.relu = a.relu; p.round_tf32 = a.round_tf32;
   p.stats = a.stats;
+  p.gate = a.gate;
+  p.bnb_y = a.bnb_y; p.bnb_mean = a.bnb_mean; p.bnb_invstd = a.bnb_invstd;
+  p.bnb_scale = a.bnb_scale; p.bnb_shift = a.bnb_shift;
   p.a_lo_nonzero = a.a_lo_nonzero;
   p.a_tiled2d = a.a_tiled2d;
   p.o_step = a.o_step; p.o_h0 = a.o_h0; p.o_w0 = a.o_w0; p.o_H = a.o_H; p.o_W = a.o_W;
@@ -126,8 +133,19 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if ((a.scale != nullptr) != (a.shift != nullptr))
     return set_error("conv: scale and shift come as a pair");
   if (a.mask != nullptr && a.resid == nullptr) return set_error("conv: mask without resid");
-  if (a.stats != nullptr && (a.scale != nullptr || a.shift != nullptr))
+  if (a.stats != nullptr && a.bnb_y == nullptr && (a.scale != nullptr || a.shift != nullptr))
     return set_error("conv: batch statistics are taken from the raw output (no scale/shift)");
+  if (a.gate != nullptr && a.mask != nullptr) return set_error("conv: gate and mask are exclusive");
+  if (a.bnb_y != nullptr) {
+    if (!a.stats || !a.bnb_mean || !a.bnb_invstd)
+      return set_error("conv: BatchNorm-backward sums need stats, mean and invstd");
+    if ((a.bnb_scale != nullptr) != (a.bnb_shift != nullptr))
+      return set_error("conv: bnb_scale and bnb_shift come as a pair");
+    if (a.resid_h != nullptr || a.o_step != 0 || !a.out || a.out_h)
+      return set_error("conv: BatchNorm-backward sums go with a dense fp32 result only");
+  } else if (a.bnb_mean || a.bnb_invstd || a.bnb_scale || a.bnb_shift) {
+    return set_error("conv: bnb_* given without bnb_y");
+  }
 
   ConvMaps m;
   const uint64_t ktot = (uint64_t)a.R * a.S * a.Cin;
@@ -167,15 +185,19 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
 
   // epilogue features of this launch; the combinations the network's 64-channel layers use have
   // specialised kernels (see the EPI comment in conv_igemm.cuh), everything else runs generic
-  const int epi = (a.stats ? kEpiStats : 0) | (a.scale ? kEpiAffine : 0) | (a.resid ? kEpiResid32 : 0) |
-                  (a.mask ? kEpiMask : 0) | (a.resid_h ? kEpiResid16 : 0) | (a.relu ? kEpiRelu : 0) |
-                  (a.out ? kEpiOut32 : 0) | (a.out_h ? kEpiOut16 : 0) | (a.round_tf32 ? kEpiRound : 0);
+  const int epi = (a.stats && !a.bnb_y ? kEpiStats : 0) | (a.scale ? kEpiAffine : 0) |
+                  (a.resid ? kEpiResid32 : 0) | (a.mask ? kEpiMask : 0) | (a.resid_h ? kEpiResid16 : 0) |
+                  (a.relu ? kEpiRelu : 0) | (a.out ? kEpiOut32 : 0) | (a.out_h ? kEpiOut16 : 0) |
+                  (a.round_tf32 ? kEpiRound : 0) | (a.gate ? kEpiGate : 0) | (a.bnb_y ? kEpiBnBwd : 0) |
+                  (a.bnb_scale ? kEpiBnGate : 0);
   constexpr int kTrainFwd = kEpiStats | kEpiOut32;                       // raw y + BN statistics
   constexpr int kEvalAct = kEpiAffine | kEpiRelu | kEpiOut16;            // folded BN + ReLU -> pair
   constexpr int kEvalActRes = kEvalAct | kEpiResid16;                    // ... + identity shortcut
   constexpr int kEvalStem = kEpiAffine | kEpiRelu | kEpiOut32;
   constexpr int kDgrad = kEpiOut32;
-  constexpr int kDgradRes = kEpiOut32 | kEpiResid32 | kEpiMask;          // + gated shortcut gradient
+  constexpr int kDgradRes = kEpiOut32 | kEpiResid32;                     // + (pre-gated) shortcut gradient
+  constexpr int kDgradResGate = kDgradRes | kEpiGate;                    // ... then the input's ReLU gate
+  constexpr int kDgradBn = kEpiOut32 | kEpiBnBwd | kEpiBnGate;           // bn1's gate + backward sums
   if (halo == 128 && split) {
     if (epi == kTrainFwd) return launch_variant<64, 128, 2, true, true, true, kTrainFwd>(m, p, grid, stream);
     if (epi == kEvalAct) return launch_variant<64, 128, 2, true, true, true, kEvalAct>(m, p, grid, stream);
@@ -185,6 +207,8 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (halo == 128) {
     if (epi == kDgrad) return launch_variant<64, 128, 4, false, true, true, kDgrad>(m, p, grid, stream);
     if (epi == kDgradRes) return launch_variant<64, 128, 4, false, true, true, kDgradRes>(m, p, grid, stream);
+    if (epi == kDgradResGate) return launch_variant<64, 128, 4, false, true, true, kDgradResGate>(m, p, grid, stream);
+    if (epi == kDgradBn) return launch_variant<64, 128, 4, false, true, true, kDgradBn>(m, p, grid, stream);
     return launch_variant<64, 128, 4, false, true, true>(m, p, grid, stream);
   }
   if (halo == 32 && split) {  // the stem: epilogue-paced, 8 epilogue warps
@@ -231,13 +255,14 @@ static int launch_wgrad_variant(const CUtensorMap& mx, const CUtensorMap& mdy,
                                 const WgradParams& p, int grid, cudaStream_t stream) {
   using L = WgradSmem<BLOCK_N, STAGES, PX>;
   auto kern = conv_wgrad_kernel<BLOCK_N, STAGES, PX>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceMax configured;
+  int dev;
+  if (configured.needs(L::TOTAL, &dev)) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return set_error("wgrad: cudaFuncSetAttribute(%d B): %s", L::TOTAL,
                                            cudaGetErrorString(e));
-    configured = true;
+    configured.set(dev, L::TOTAL);
   }
   kern<<<grid, kWgradThreads, L::TOTAL, stream>>>(mx, mdy, p);
   cudaError_t e = cudaGetLastError();
@@ -251,13 +276,14 @@ static int launch_wgrad_halo_variant(const CUtensorMap& mx, const CUtensorMap& m
   using L = WgradHaloSmem<NACC, STAGES>;
   static_assert(L::TOTAL <= kMaxDynSmem, "wgrad halo stage ring too large");
   auto kern = conv_wgrad_halo_kernel<NACC, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceMax configured;
+  int dev;
+  if (configured.needs(L::TOTAL, &dev)) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return set_error("wgrad halo: cudaFuncSetAttribute(%d B): %s", L::TOTAL,
                                            cudaGetErrorString(e));
-    configured = true;
+    configured.set(dev, L::TOTAL);
   }
   kern<<<grid, kWgradHaloThreads, L::TOTAL, stream>>>(mx, mdy, p);
   cudaError_t e = cudaGetLastError();

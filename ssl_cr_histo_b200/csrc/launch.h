@@ -10,8 +10,32 @@ namespace b2n {
 // printf-style error recorder; always returns a non-zero code so callers can `return set_error(..)`.
 int set_error(const char* fmt, ...);
 const char* last_error();
-int device_sm_count();
+int device_sm_count();   // of the current device (cached per device)
 int elementwise_blocks_per_sm();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device, and the entry points may be
+// called from several host threads (one per GPU under the reference's nn.DataParallel): every
+// launcher keeps one PerDeviceMax per kernel instantiation -- the largest value already set on each
+// device (lock-free; setting the attribute twice is harmless, so a lost race only repeats the call).
+constexpr int kMaxDevices = 64;
+struct PerDeviceMax {
+  int v[kMaxDevices] = {};
+  // true when `want` exceeds what has been configured on the current device (then call set())
+  bool needs(int want, int* dev_out) const {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    if (dev < 0 || dev >= kMaxDevices) return true;
+    return __atomic_load_n(&v[dev], __ATOMIC_ACQUIRE) < want;
+  }
+  void set(int dev, int want) {
+    if (dev < 0 || dev >= kMaxDevices) return;
+    int cur = __atomic_load_n(&v[dev], __ATOMIC_RELAXED);
+    while (cur < want && !__atomic_compare_exchange_n(&v[dev], &cur, want, false, __ATOMIC_RELEASE,
+                                                       __ATOMIC_RELAXED)) {
+    }
+  }
+};
 
 // Forward-style convolution: out[n,p,q,:] = sum_taps x[n, p*stride - pad_lo + r, ...] * w.
 // x is NHWC fp32 [N,H,W,Cin]; w is packed K-major [Cout][R*S*Cin]; out is NHWC [N,P,Q,Cout].
@@ -33,6 +57,12 @@ struct ConvArgs {
   const __half* resid_h = nullptr;
   const __half* resid_l = nullptr;
   const float* mask = nullptr;
+  const float* gate = nullptr;        // result zeroed where gate <= 0 (addressed like the output)
+  const float* bnb_y = nullptr;       // BatchNorm-backward sums of the result into `stats` ...
+  const float* bnb_mean = nullptr;
+  const float* bnb_invstd = nullptr;
+  const float* bnb_scale = nullptr;   // ... after the ReLU gate fmaf(y, scale, shift) > 0 (optional)
+  const float* bnb_shift = nullptr;
   int relu = 0;
   int round_tf32 = 0;
   double* stats = nullptr;
@@ -76,7 +106,8 @@ int launch_bn_bwd_reduce(const float* g, const float* mask, const float* y, cons
 int launch_bn_bwd_apply(const float* g, const float* mask, const float* y, const float* mean,
                         const float* invstd, const float* gamma, const float* gate_scale,
                         const float* gate_shift, const double* sums, float* dy, float* dgamma,
-                        float* dbeta, long long rows, int C, int round_tf32, cudaStream_t stream);
+                        float* dbeta, long long rows, int C, int round_tf32, int accumulate,
+                        cudaStream_t stream);
 int launch_upsample_zero(const float* dy, float* up, int N, int P, int Q, int H, int W, int C,
                          cudaStream_t stream);
 int launch_stem_pack_input(const float* x, __half* xs_h, __half* xs_l, float* xs32,
@@ -85,7 +116,8 @@ int launch_stem_pack_input_u8(const unsigned char* x, __half* xs_h, float* xs32,
                               cudaStream_t stream);
 int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
                             cudaStream_t stream);
-int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream);
+int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate,
+                             cudaStream_t stream);
 int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a32,
                            __half* a_h, __half* a_l, unsigned char* idx, int N, int H, int W,
                            int C, cudaStream_t stream);
@@ -100,16 +132,17 @@ int launch_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const fl
                              const float* scale, const float* shift, const float* mean,
                              const float* invstd, const float* gamma, const double* sums, float* dy,
                              float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
-                             cudaStream_t stream);
+                             int accumulate, cudaStream_t stream);
 int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, int HW, int C,
                        cudaStream_t stream);
-int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream);
+int launch_avgpool_bwd(const float* ge, const float* gate, float* g, int N, int HW, int C,
+                       cudaStream_t stream);
 int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C, int R, int S,
                     cudaStream_t stream);
 int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
                       cudaStream_t stream);
 int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream);
-int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S,
+int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S, int accumulate,
                         cudaStream_t stream);
 int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,
                       float* y, long long ldy, int rows, int in_f, int out_f, int relu,

@@ -7,7 +7,9 @@
 
 namespace b2n {
 
-// C[m][n] = sum_k A(m,k) * B(k,n)  (+ bias[n]) (relu) (* [mask[m][n] > 0]) (+= when accumulate)
+// C[m][n] = act(C_prev[m][n] (when accumulate) + sum_k A(m,k) * B(k,n) + bias[n]) * [mask[m][n] > 0]
+// -- the previous content is added BEFORE bias / ReLU / mask, so a product split over K
+// (cat(A,B) W^T = A Wa^T + B Wb^T) is two launches, the second carrying the bias and the ReLU.
 // A(m,k) = a[m*sam + k*sak], B(k,n) = b[k*sbk + n*sbn], C row-major with pitch ldc.
 struct GemmArgs {
   const float* a; long long sam, sak;
@@ -76,11 +78,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
       float v = acc[i][j];
+      const size_t o = static_cast<size_t>(m) * g.ldc + n;
+      if (g.accumulate) v += g.c[o];
       if (g.bias != nullptr) v += g.bias[n];
       if (g.relu) v = fmaxf(v, 0.f);
-      const size_t o = static_cast<size_t>(m) * g.ldc + n;
       if (g.mask != nullptr && !(g.mask[o] > 0.f)) v = 0.f;
-      if (g.accumulate) v += g.c[o];
       g.c[o] = v;
     }
   }

@@ -28,6 +28,9 @@ __device__ inline float block_sum(float v, float* scratch) {
 }
 
 // CE of one row; optionally writes grad = (softmax - onehot) * gscale and returns argmax.
+// A target outside [0, C) (F.cross_entropy's ignore_index = -100 included: the reference never
+// uses it) is not dereferenced; the row's loss and gradient become NaN so the step fails loudly
+// instead of training on garbage.
 __device__ inline float ce_row(const float* __restrict__ lg, int C, long long target,
                                float* __restrict__ grad, float gscale, int* amax) {
   float mx = lg[0];
@@ -37,11 +40,12 @@ __device__ inline float ce_row(const float* __restrict__ lg, int C, long long ta
   float se = 0.f;
   for (int c = 0; c < C; ++c) se += expf(lg[c] - mx);
   const float lse = logf(se) + mx;
+  const bool ok = target >= 0 && target < C;
   if (grad != nullptr)
     for (int c = 0; c < C; ++c)
-      grad[c] = (expf(lg[c] - lse) - (c == target ? 1.f : 0.f)) * gscale;
+      grad[c] = ok ? (expf(lg[c] - lse) - (c == target ? 1.f : 0.f)) * gscale : __int_as_float(0x7fc00000);
   if (amax != nullptr) *amax = am;
-  return lse - lg[target];
+  return ok ? lse - lg[target] : __int_as_float(0x7fc00000);
 }
 
 // mode 0: plain CE.  rows_x rows of logits_x vs targets (int64).

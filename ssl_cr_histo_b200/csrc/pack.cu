@@ -71,8 +71,9 @@ __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, float* __restr
   }
 }
 // weight-gradient result back to the parameter layout: dw[k][c][r][s] = dwf[k][(r*S+s)*C + c]
+// (accumulate: += into a gradient slot several passes over the same weights feed)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, float* __restrict__ dw, int K,
-                                    int C, int R, int S) {
+                                    int C, int R, int S, int accumulate) {
   const size_t total = static_cast<size_t>(K) * C * R * S;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -81,7 +82,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, float* __rest
     const int r = static_cast<int>(u % R); u /= R;
     const int c = static_cast<int>(u % C);
     const int k = static_cast<int>(u / C);
-    dw[t] = dwf[(static_cast<size_t>(k) * R * S + r * S + s) * C + c];
+    const float v = dwf[(static_cast<size_t>(k) * R * S + r * S + s) * C + c];
+    dw[t] = accumulate ? dw[t] + v : v;
   }
 }
 
@@ -108,8 +110,15 @@ int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C
   return 0;
 }
 B2N_PACK_LAUNCH(launch_pack_dgrad, pack_dgrad_kernel)
-B2N_PACK_LAUNCH(launch_unpack_wgrad, unpack_wgrad_kernel)
 #undef B2N_PACK_LAUNCH
+int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S, int accumulate,
+                        cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(K) * C * R * S;
+  unpack_wgrad_kernel<<<pack_grid(total), 256, 0, stream>>>(src, dst, K, C, R, S, accumulate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("launch_unpack_wgrad: %s", cudaGetErrorString(e));
+  return 0;
+}
 
 int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream) {
   pack_dgrad_s2_kernel<<<pack_grid(static_cast<size_t>(9) * C * K), 256, 0, stream>>>(src, dst, K, C);

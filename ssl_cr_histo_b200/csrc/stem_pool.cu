@@ -110,12 +110,13 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __half* __r
   }
 }
 __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw,
-                                         int K) {
+                                         int K, int accumulate) {
   const int total = K * 3 * 49;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int s = t % 7, r = (t / 7) % 7, c = (t / 49) % 3, k = t / 147;
     const int tr = (r + 1) >> 1, dy = (r + 1) & 1, ts = (s + 1) >> 1, dx = (s + 1) & 1;
-    dw[t] = dws[(k * 16 + tr * 4 + ts) * kStemC + (dy * 2 + dx) * 3 + c];
+    const float v = dws[(k * 16 + tr * 4 + ts) * kStemC + (dy * 2 + dx) * 3 + c];
+    dw[t] = accumulate ? dw[t] + v : v;
   }
 }
 
@@ -151,8 +152,9 @@ int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
   if (e != cudaSuccess) return set_error("stem_pack_weight: %s", cudaGetErrorString(e));
   return 0;
 }
-int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, cudaStream_t stream) {
-  stem_unpack_wgrad_kernel<<<37, 256, 0, stream>>>(dws, dw, K);
+int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate,
+                             cudaStream_t stream) {
+  stem_unpack_wgrad_kernel<<<37, 256, 0, stream>>>(dws, dw, K, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_unpack_wgrad: %s", cudaGetErrorString(e));
   return 0;
@@ -356,12 +358,13 @@ int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shif
   // pipelined variant when two slots of three y rows fit in shared memory
   const size_t smem = 2 * 3 * static_cast<size_t>(W) * C * 4 + 16 + 128;
   if ((static_cast<size_t>(W) * C * 4) % 16 == 0 && smem <= 227 * 1024 && getenv("B2N_NO_POOL_PIPE") == nullptr) {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDeviceMax configured;
+    int dev;
+    if (smem > 48 * 1024 && configured.needs((int)smem, &dev)) {
       cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_rows_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return set_error("bn_relu_maxpool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      configured = smem;
+      configured.set(dev, (int)smem);
     }
     int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
     if (per_sm > 2) per_sm = 2;
@@ -420,7 +423,7 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         double* __restrict__ sums, float4* __restrict__ dy, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int N, int H, int W, int P, int Q, int C,
-                        double inv_count) {
+                        double inv_count, int accumulate) {
   extern __shared__ uint8_t band_smem_raw[];
   uint8_t* smem = band_smem_raw + ((128u - (smem_u32(band_smem_raw) & 127u)) & 127u);
   const int tid = threadIdx.x;
@@ -448,8 +451,8 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
     gi = make_float4(ga4.x * is.x, ga4.y * is.y, ga4.z * is.z, ga4.w * is.w);
     if (blockIdx.x == 0 && dgamma != nullptr) {
       for (int k = tid; k < C; k += kBandThreads) {
-        dbeta[k] = static_cast<float>(sums[k]);
-        dgamma[k] = static_cast<float>(sums[C + k]);
+        dbeta[k] = (accumulate ? dbeta[k] : 0.f) + static_cast<float>(sums[k]);
+        dgamma[k] = (accumulate ? dgamma[k] : 0.f) + static_cast<float>(sums[C + k]);
       }
     }
   }
@@ -551,7 +554,7 @@ template <bool APPLY, bool ROUND>
 static int launch_band(const float* ga, const unsigned char* idx, const float* y, const float* scale,
                        const float* shift, const float* mean, const float* invstd, const float* gamma,
                        double* sums, float* dy, float* dgamma, float* dbeta, int N, int H, int W,
-                       int C, cudaStream_t stream) {
+                       int C, int accumulate, cudaStream_t stream) {
   const int C4 = C / 4;
   if (C % 16 != 0 || kBandThreads % C4 != 0)
     return set_error("pool_bn_bwd: unsupported C=%d", C);
@@ -564,11 +567,12 @@ static int launch_band(const float* ga, const unsigned char* idx, const float* y
   if (smem < kBandThreads * 8 * sizeof(float) + 128) smem = kBandThreads * 8 * sizeof(float) + 128;
   if (smem > 227 * 1024) return set_error("pool_bn_bwd: image row too wide (W=%d, C=%d)", W, C);
   auto kern = pool_bn_bwd_band_kernel<APPLY, ROUND>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDeviceMax configured;
+  int dev;
+  if (smem > 48 * 1024 && configured.needs((int)smem, &dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("pool_bn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = smem;
+    configured.set(dev, (int)smem);
   }
   const int nbands = N * ((H + 1) / 2);
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
@@ -580,7 +584,7 @@ static int launch_band(const float* ga, const unsigned char* idx, const float* y
   kern<<<grid, kBandThreads, smem, stream>>>(
       reinterpret_cast<const float4*>(ga), reinterpret_cast<const uchar4*>(idx),
       reinterpret_cast<const float4*>(y), scale, shift, mean, invstd, gamma, sums,
-      reinterpret_cast<float4*>(dy), dgamma, dbeta, N, H, W, P, Q, C, inv_count);
+      reinterpret_cast<float4*>(dy), dgamma, dbeta, N, H, W, P, Q, C, inv_count, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("pool_bn_bwd: %s", cudaGetErrorString(e));
   return 0;
@@ -591,20 +595,20 @@ int launch_pool_bn_bwd_reduce(const float* ga, const unsigned char* idx, const f
                               const float* invstd, double* sums, int N, int H, int W, int C,
                               cudaStream_t stream) {
   return launch_band<false, false>(ga, idx, y, scale, shift, mean, invstd, nullptr, sums, nullptr,
-                                   nullptr, nullptr, N, H, W, C, stream);
+                                   nullptr, nullptr, N, H, W, C, 0, stream);
 }
 
 int launch_pool_bn_bwd_apply(const float* ga, const unsigned char* idx, const float* y,
                              const float* scale, const float* shift, const float* mean,
                              const float* invstd, const float* gamma, const double* sums, float* dy,
                              float* dgamma, float* dbeta, int N, int H, int W, int C, int round_tf32,
-                             cudaStream_t stream) {
+                             int accumulate, cudaStream_t stream) {
   double* s = const_cast<double*>(sums);  // only read when APPLY
   if (round_tf32)
     return launch_band<true, true>(ga, idx, y, scale, shift, mean, invstd, gamma, s, dy, dgamma, dbeta,
-                                   N, H, W, C, stream);
+                                   N, H, W, C, accumulate, stream);
   return launch_band<true, false>(ga, idx, y, scale, shift, mean, invstd, gamma, s, dy, dgamma, dbeta,
-                                  N, H, W, C, stream);
+                                  N, H, W, C, accumulate, stream);
 }
 
 // ------------------------------------------------------------ global avg-pool
@@ -621,11 +625,17 @@ __global__ void avgpool_fwd_kernel(const __half* __restrict__ a_h, const __half*
     e[static_cast<size_t>(n) * C + c] = acc / static_cast<float>(HW);
   }
 }
-__global__ void avgpool_bwd_kernel(const float* __restrict__ ge, float* __restrict__ g, int HW, int C) {
+// gate (optional): the pooled activation itself -- its ReLU gate is applied here, at the
+// producer of the gradient, so no consumer has to read a mask tensor
+__global__ void avgpool_bwd_kernel(const float* __restrict__ ge, const float* __restrict__ gate,
+                                   float* __restrict__ g, int HW, int C) {
   const int n = blockIdx.x;
   const float inv = 1.f / static_cast<float>(HW);
-  for (int t = threadIdx.x; t < HW * C; t += blockDim.x)
-    g[static_cast<size_t>(n) * HW * C + t] = ge[static_cast<size_t>(n) * C + (t % C)] * inv;
+  for (int t = threadIdx.x; t < HW * C; t += blockDim.x) {
+    const size_t i = static_cast<size_t>(n) * HW * C + t;
+    const float v = ge[static_cast<size_t>(n) * C + (t % C)] * inv;
+    g[i] = gate == nullptr || gate[i] > 0.f ? v : 0.f;
+  }
 }
 int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, int HW, int C,
                        cudaStream_t stream) {
@@ -634,8 +644,9 @@ int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, in
   if (er != cudaSuccess) return set_error("avgpool_fwd: %s", cudaGetErrorString(er));
   return 0;
 }
-int launch_avgpool_bwd(const float* ge, float* g, int N, int HW, int C, cudaStream_t stream) {
-  avgpool_bwd_kernel<<<N, 256, 0, stream>>>(ge, g, HW, C);
+int launch_avgpool_bwd(const float* ge, const float* gate, float* g, int N, int HW, int C,
+                       cudaStream_t stream) {
+  avgpool_bwd_kernel<<<N, 256, 0, stream>>>(ge, gate, g, HW, C);
   cudaError_t er = cudaGetLastError();
   if (er != cudaSuccess) return set_error("avgpool_bwd: %s", cudaGetErrorString(er));
   return 0;

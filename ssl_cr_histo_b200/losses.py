@@ -1,5 +1,8 @@
 """Fused loss kernels (csrc/loss_lerp.cu) as autograd-aware functions.
 
+Class targets must lie in [0, C): an out-of-range label (``ignore_index`` is not supported -- the
+reference never uses it) is not dereferenced and turns the loss and its gradient into NaN.
+
 The reference's loops call torch losses themselves (pretrain_BreastPathQ.py:56,
 eval_BreastPathQ_SSL_CR.py:92-95, eval_Kather_SSL_CR.py:87-93); those keep working with the
 drop-in modules.  These functions are the opt-in single-launch versions: one pass over the
@@ -18,6 +21,8 @@ class _FusedLoss(torch.autograd.Function):
     def forward(ctx, mode, lambda_u, logits_x, targets, logits_u_w, logits_u_s):
         _lib.require_device(logits_x, "logits")
         dev = logits_x.device
+        if logits_x.dim() != 2:
+            raise RuntimeError("logits_x must be (rows, classes), got %s" % (tuple(logits_x.shape),))
         lx = logits_x.contiguous().float()
         rows_x, C = lx.shape
         losses = torch.empty(3, device=dev)
@@ -29,9 +34,15 @@ class _FusedLoss(torch.autograd.Function):
             if tf.numel() != lx.numel():
                 raise RuntimeError("MSE targets must have as many elements as logits_x")
         else:
-            ti = targets.contiguous().long()
+            ti = targets.contiguous().long().view(-1)
+            if ti.numel() != rows_x:
+                raise RuntimeError("expected %d class targets, got %d" % (rows_x, ti.numel()))
             amax = torch.empty(rows_x, device=dev, dtype=torch.long)
         if mode != 0:
+            if logits_u_w.shape != logits_u_s.shape or logits_u_s.dim() != 2 or \
+                    logits_u_s.shape[1] != C:
+                raise RuntimeError("logits_u_w %s and logits_u_s %s must both be (rows_u, %d)"
+                                   % (tuple(logits_u_w.shape), tuple(logits_u_s.shape), C))
             lw = logits_u_w.detach().contiguous().float()
             ls = logits_u_s.contiguous().float()
             rows_u = ls.shape[0]

@@ -10,7 +10,6 @@ all work unchanged) -- but every FLOP runs in the hand-written sm_100a kernels o
 """
 from __future__ import annotations
 
-import torch
 from torch import nn
 
 from . import heads
@@ -55,11 +54,8 @@ class TripletNet(nn.Module):
         E1 = self.model(i1)
         E2 = self.model(i2)
         E3 = self.model(i3)
-        n = E1.shape[0]
-        pairs = torch.cat((torch.cat((E1, E2), dim=1), torch.cat((E2, E3), dim=1),
-                           torch.cat((E1, E3), dim=1)), dim=0)          # (3N, 1024)
-        f = heads.mlp2(pairs, self.fc[0], self.fc[2])                    # (3N, 256)
-        return f.view(3, n, 256).permute(1, 0, 2).reshape(n, 768)        # cat(f12,f23,f13)
+        # pair concat + fc x3 + concat (:56-64) without materialising any concatenation
+        return heads.pair_mlp(E1, E2, E3, self.fc[0], self.fc[2])
 
 
 class TripletNet_Finetune(nn.Module):
@@ -78,8 +74,7 @@ class TripletNet_Finetune(nn.Module):
 
     def forward(self, i):
         E = self.model(i, n_updates=3)
-        f = heads.mlp2(torch.cat((E, E), dim=1), self.fc[0], self.fc[2])
-        return torch.cat((f, f, f), dim=1)
+        return heads.pair_mlp_same(E, self.fc[0], self.fc[2])
 
 
 class FinetuneResNet(nn.Module):

@@ -91,7 +91,7 @@ class Adam(torch.optim.Optimizer):
                 numel = (ctypes.c_longlong * n)(*[p.numel() for p in ps])
                 call("b2n_adam_multi", pt, gt, mt, vt, numel, n, float(group["lr"]), float(b1),
                      float(b2), float(group["eps"]), float(group["weight_decay"]), int(step),
-                     float(self.grad_scale))
+                     float(self.grad_scale), device=ps[0].device)
                 _touch(ps)
         return loss
 
@@ -140,6 +140,7 @@ class SGD(torch.optim.Optimizer):
                 numel = (ctypes.c_longlong * n)(*[p.numel() for p in ps])
                 call("b2n_sgd_multi", pt, gt, bt, numel, n, float(group["lr"]),
                      float(group["momentum"]), float(group["weight_decay"]),
-                     1 if group["nesterov"] else 0, first, float(self.grad_scale))
+                     1 if group["nesterov"] else 0, first, float(self.grad_scale),
+                     device=ps[0].device)
                 _touch(ps)
         return loss

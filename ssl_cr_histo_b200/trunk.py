@@ -42,25 +42,37 @@ class BasicBlock(nn.Module):
 
 
 class _PackCache:
-    """Packed (K-major, TF32-rounded) copies of conv weights, refreshed when a parameter's
-    version counter, storage or the global weight epoch changes.  Never copied or saved."""
+    """Packed (K-major) copies of conv weights.  Never copied or saved.
+
+    An entry is rebuilt when its tag -- the parameter's storage, autograd version counter,
+    ``_b2n_epoch`` (bumped by this package's optimizer kernels) or the global ``WEIGHT_EPOCH``
+    (bumped by ``weights.lerp_``) -- changes.  Writes made through ``p.data`` (the vendored
+    Lookahead, lookahead.py:96-97; RAdam; any EMA update) leave all of those untouched, so in
+    addition every pack is rebuilt on the first training-mode forward after a backward pass (the
+    point where an optimizer of any kind has had its turn) and after ``invalidate()``.  An
+    eval-mode module whose weights are written through ``.data`` outside this package must call
+    ``trunk.invalidate_packs()``."""
 
     def __init__(self):
         self.entries = {}
+        self.floor = 0          # entries built before this generation are stale
+        self.generation = 1
 
     def __deepcopy__(self, memo):
         return _PackCache()
 
+    def invalidate(self):
+        self.generation += 1
+        self.floor = self.generation
+
     def get(self, key: str, param: torch.Tensor, maker):
-        # _b2n_epoch: bumped by kernels that write this parameter behind autograd's version counter
-        # (optim.Adam / optim.SGD); WEIGHT_EPOCH: bumped by whole-model writes (weights.lerp_)
         tag = (param.data_ptr(), param._version, getattr(param, "_b2n_epoch", 0), _lib.WEIGHT_EPOCH,
                param.device)
         hit = self.entries.get(key)
-        if hit is not None and hit[0] == tag:
+        if hit is not None and hit[0] == tag and hit[2] >= self.floor:
             return hit[1]
         packed = maker(param.detach())
-        self.entries[key] = (tag, packed)
+        self.entries[key] = (tag, packed, self.generation)
         return packed
 
 
@@ -141,6 +153,12 @@ class ResNet18Trunk(nn.Module):
                 out.append(b.downsample[1])
         return out
 
+    def invalidate_packs(self) -> None:
+        """Drop the cached weight packs.  Only needed after writing parameters of an *eval-mode*
+        module through ``p.data`` (which no version counter sees); training-mode forwards refresh
+        the packs after every backward pass on their own."""
+        self._packs.invalidate()
+
     def forward(self, x: torch.Tensor, n_updates: int = 1) -> torch.Tensor:
         """``n_updates`` > 1 applies that many identical BN running-stat updates in closed form
         (TripletNet_Finetune runs the same input through the trunk three times)."""
@@ -207,7 +225,7 @@ class _Act:
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
           resid=None, resid_pair=None, mask=None, relu=0, rnd=0, stats=None, out=None,
           out_pair=None, want_out=True, alg=1.0, lo_flag=None, pad_hi_w=None, R_w=None,
-          placement=(0, 0, 0, 0, 0)):
+          placement=(0, 0, 0, 0, 0), gate=None, bnb=None):
     """One conv launch.  ``x`` / ``wp`` are either an ``_Act`` and an FP16 (hi, lo) weight pair
     (error-compensated forward) or plain fp32 tensors (single TF32 pass: data gradients).
     ``alg``: algorithmic / executed FLOP ratio of this launch (the stem runs 147 real taps in a
@@ -229,16 +247,20 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
     # algorithmic DRAM bytes of the launch: every operand / result tensor touched once
     n_out = float(N) * P * Q * Cout if placement[0] == 0 else float(N) * P * Q * Cout
     byt = n_out * (4.0 * (out is not None) + 4.0 * (out_pair is not None) + 4.0 * (resid is not None)
-                   + 4.0 * (mask is not None) + 4.0 * (resid_pair is not None))
+                   + 4.0 * (mask is not None) + 4.0 * (resid_pair is not None)
+                   + 4.0 * (gate is not None) + 4.0 * (bnb is not None))
     if isinstance(x, _Act):   # hi*hi + hi*lo + lo*hi (the lo plane of integer images is skipped)
         byt += float(N) * H * W * Cin * (2.0 if lo_flag is not None else 4.0)
         work = (nominal * alg, nominal * (2.0 if lo_flag is not None else 3.0), 0.0, "fwd", byt)
     else:
         byt += float(N) * H * W * Cin * 4.0
         work = (nominal * alg, 0.0, nominal, "dgrad", byt)
+    # bnb = (y, BN state, gate_from_y): BatchNorm-backward sums of the result, see b2n.h
+    by, bst, bgate = bnb if bnb is not None else (None, None, False)
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, S, stride,
          pad_lo, pad_hi, pad_lo, phw, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
-         lo_flag, *placement, work=work)
+         lo_flag, *placement, gate, by, bst.mean if bst else None, bst.invstd if bst else None,
+         bst.scale if bgate else None, bst.shift if bgate else None, work=work)
     return out
 
 
@@ -263,6 +285,9 @@ class _TrunkFn(torch.autograd.Function):
         if (H | W) & 1:
             raise RuntimeError("H and W must be even (got %dx%d)" % (H, W))
         packs = trunk._packs
+        if training and getattr(trunk, "_packs_dirty", True):
+            packs.invalidate()          # see _PackCache: p.data writes are invisible to the tags
+            trunk._packs_dirty = False
         bns = trunk.bn_layers()
         total_c = sum(b.num_features for b in bns)
         stats_all = torch.zeros(2 * total_c, device=dev, dtype=torch.float64) if training else None
@@ -377,6 +402,7 @@ class _TrunkFn(torch.autograd.Function):
         if sv is None:
             raise RuntimeError("trunk backward called without saved activations")
         ctx.saved = None  # free activations as early as possible
+        trunk._packs_dirty = True   # an optimizer follows: the next training forward repacks
         params = list(trunk.parameters())
         needs = ctx.needs_input_grad[4:]
         grads = {id(p): None for p in params}
@@ -394,21 +420,78 @@ class _TrunkFn(torch.autograd.Function):
             return (None, None, None, None) + tuple(None for _ in params)
         min_unit = min(i for i, n in enumerate(unit_need) if n)
 
-        def bn_backward(g, mask, y, st, bn, rows, C, gate_from_y=False):
-            """``mask``: post-ReLU tensor gating g, or None; ``gate_from_y``: the ReLU input is this
-            BN's own output, so the gate is recomputed from y (no mask tensor is read)."""
+        # One zero-fill per backward pass for every BatchNorm-backward sum pair and every packed
+        # weight-gradient accumulator (instead of one torch.zeros launch each).
+        bn_list = trunk.bn_layers()
+        sums_all = torch.zeros(2 * sum(b.num_features for b in bn_list), device=dev, dtype=torch.float64)
+        sums_off = {}
+        off = 0
+        for b in bn_list:
+            sums_off[id(b)] = off
+            off += 2 * b.num_features
+
+        def sums_of(bn):
+            o = sums_off[id(bn)]
+            return sums_all[o:o + 2 * bn.num_features]
+
+        convs = [trunk.conv1] + [c for b in blocks for c in
+                                 ([b.conv1, b.conv2] + ([b.downsample[0]] if b.downsample is not None else []))]
+        dwp_off, total = {}, 0
+        for c in convs:
+            if need[id(c.weight)]:
+                dwp_off[id(c)] = total
+                # the stem's packed gradient is [64][16 taps * STEM_C] (space-to-depth view)
+                total += 64 * 16 * STEM_C if c is trunk.conv1 else c.weight.numel()
+        dwp_all = torch.zeros(total, device=dev, dtype=torch.float32) if total else None
+
+        def dwp_of(conv, rows, cols):
+            o = dwp_off[id(conv)]
+            return dwp_all[o:o + rows * cols].view(rows, cols)
+
+        def emit(p, make):
+            """Deliver a parameter gradient: into the parameter's arena slot (ddp.GradAllReducer,
+            accumulating -- autograd then sees None and launches nothing), else as a fresh tensor."""
+            slot = getattr(p, "_b2n_grad_slot", None)
+            if slot is not None:
+                make(slot, 1)
+                sink = getattr(p, "_b2n_grad_sink", None)
+                if sink is not None:
+                    sink.ready(p)
+            else:
+                t = torch.empty_like(p)
+                make(t, 0)
+                grads[id(p)] = t
+
+        def bn_backward(g, y, st, bn, rows, C, reduced=False, gate_from_y=False):
+            """g: gradient w.r.t. the BN output, already ReLU-gated by its producer (the gate of
+            every activation gradient is applied by the kernel that writes it).  ``reduced``: the
+            producer also accumulated the two BatchNorm-backward sums (conv epilogue).
+            ``gate_from_y``: g is not gated yet and the ReLU input is this BN's own output (the
+            stem's unfused chain)."""
             gsc, gsh = (st.scale, st.shift) if gate_from_y else (None, None)
-            sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
-            call("b2n_bn_bwd_reduce", g, mask, y, st.mean, st.invstd, gsc, gsh, sums, rows, C)
+            sums = sums_of(bn)
+            if not reduced:
+                call("b2n_bn_bwd_reduce", g, None, y, st.mean, st.invstd, gsc, gsh, sums, rows, C)
             dy = torch.empty_like(y)
-            dgamma = torch.empty(C, device=dev)
-            dbeta = torch.empty(C, device=dev)
-            call("b2n_bn_bwd_apply", g, mask, y, st.mean, st.invstd, bn.weight, gsc, gsh, sums, dy,
-                 dgamma, dbeta, rows, C, 1)
-            if need[id(bn.weight)]:
-                grads[id(bn.weight)] = dgamma
-            if need[id(bn.bias)]:
-                grads[id(bn.bias)] = dbeta
+            wg, bg = need[id(bn.weight)], need[id(bn.bias)]
+            sw = getattr(bn.weight, "_b2n_grad_slot", None) if wg else None
+            sb = getattr(bn.bias, "_b2n_grad_slot", None) if bg else None
+            if wg and bg and sw is not None and sb is not None:
+                dgamma, dbeta, acc = sw, sb, 1
+            else:
+                dgamma, dbeta, acc = torch.empty(C, device=dev), torch.empty(C, device=dev), 0
+            call("b2n_bn_bwd_apply", g, None, y, st.mean, st.invstd, bn.weight, gsc, gsh, sums, dy,
+                 dgamma, dbeta, rows, C, 1, acc)
+            if acc:
+                for p in (bn.weight, bn.bias):
+                    sink = getattr(p, "_b2n_grad_sink", None)
+                    if sink is not None:
+                        sink.ready(p)
+            else:
+                if wg:
+                    grads[id(bn.weight)] = dgamma
+                if bg:
+                    grads[id(bn.bias)] = dbeta
             return dy
 
         main = torch.cuda.current_stream(dev)
@@ -444,19 +527,19 @@ class _TrunkFn(torch.autograd.Function):
             P, Q = dy.shape[1], dy.shape[2]
             wflops = 2.0 * N * P * Q * K * R * S * C
             with _on_side(x_in, dy):
-                dwp = torch.zeros(K, R * S * C, device=dev, dtype=torch.float32)
+                dwp = dwp_of(conv, K, R * S * C)
                 call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
                      work=(wflops, 0.0, wflops, "wgrad", 4.0 * N * (H * W * C + P * Q * K)))
-                dw = torch.empty_like(conv.weight)
-                call("b2n_unpack_wgrad", dwp, dw, K, C, R, S)
-            if side is not None:
+                emit(conv.weight, lambda t, acc: call("b2n_unpack_wgrad", dwp, t, K, C, R, S, acc))
+            dw = grads[id(conv.weight)]
+            if side is not None and dw is not None:
                 dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
-            grads[id(conv.weight)] = dw
 
         last = sv["blocks"][-1]
         hw = last["ph"] * last["pw"]
         g = torch.empty(N, last["ph"], last["pw"], 512, device=dev, dtype=torch.float32)
-        call("b2n_avgpool_bwd", ge.contiguous().float(), g, N, hw, 512)
+        # g is the gradient w.r.t. the block's post-ReLU output: gated here, at its producer
+        call("b2n_avgpool_bwd", ge.contiguous().float(), last["a_out"], g, N, hw, 512)
 
         for bi in range(len(blocks) - 1, -1, -1):
             unit = bi + 1
@@ -467,22 +550,28 @@ class _TrunkFn(torch.autograd.Function):
             h, w, ph, pw = rec["h"], rec["w"], rec["ph"], rec["pw"]
             rows = N * ph * pw
             need_in = unit > min_unit
+            # the block input is a post-ReLU block output (gate its gradient) except for the first
+            # block, whose input is the max-pooled stem activation (the pool backward gates)
+            in_gate = rec["a_in"] if bi > 0 else None
             # main branch: bn2 <- conv2 <- relu/bn1 <- conv1
-            dy2 = bn_backward(g, rec["a_out"], rec["y2"], rec["b2"], blk.bn2, rows, cout)
+            dy2 = bn_backward(g, rec["y2"], rec["b2"], blk.bn2, rows, cout)
             wgrad(blk.conv2, rec["a1"], dy2, ph, pw, 1, 1)
             wd2 = packs.get("b%d.w2d" % bi, blk.conv2.weight, _pack_dgrad)
-            da1 = _conv(dy2, wd2, N, ph, pw, cout, cout, 3, 1, 1, 1)
-            dy1 = bn_backward(da1, None, rec["y1"], rec["b1"], blk.bn1, rows, cout, gate_from_y=True)
+            # conv2's data gradient: bn1's ReLU gate (recomputed from y1) and both BatchNorm-backward
+            # sums are taken in the conv epilogue -- no separate reduction pass over da1 / y1
+            da1 = _conv(dy2, wd2, N, ph, pw, cout, cout, 3, 1, 1, 1, stats=sums_of(blk.bn1),
+                        bnb=(rec["y1"], rec["b1"], True))
+            dy1 = bn_backward(da1, rec["y1"], rec["b1"], blk.bn1, rows, cout, reduced=True)
             wgrad(blk.conv1, rec["a_in"], dy1, h, w, s, 1)
             g_in = None
             if blk.downsample is not None:
                 dconv, dbn = blk.downsample[0], blk.downsample[1]
-                dyd = bn_backward(g, rec["a_out"], rec["yd"], rec["bd"], dbn, rows, cout)
+                dyd = bn_backward(g, rec["yd"], rec["bd"], dbn, rows, cout)
                 wgrad(dconv, rec["a_in"], dyd, h, w, s, 0)
                 if need_in:
                     # stride-2 data gradients by output parity (no zero-stuffing): the 1x1
                     # shortcut conv only reaches even pixels; the 3x3 conv is four small stride-1
-                    # tap subsets over dY, each writing its own quarter of g_in.
+                    # tap subsets over dY, each writing (and ReLU-gating) its own quarter of g_in.
                     g_in = torch.empty(N, h, w, cin, device=dev, dtype=torch.float32)
                     wdd = packs.get("b%d.wdd" % bi, dconv.weight, _pack_dgrad)
                     _conv(dyd, wdd, N, ph, pw, cout, cin, 1, 1, 0, 0, out=g_in,
@@ -491,11 +580,11 @@ class _TrunkFn(torch.autograd.Function):
                     for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
                         _conv(dy1, wcls[cls], N, ph, pw, cout, cin, 1 + a0, 1, 0, a0, R_w=1 + b0,
                               pad_hi_w=b0, out=g_in, resid=g_in if cls == 0 else None,
-                              placement=(2, a0, b0, h, w))
+                              placement=(2, a0, b0, h, w), gate=in_gate)
             elif need_in:
                 wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
-                # identity shortcut: add the ReLU-gated upstream gradient in the epilogue
-                g_in = _conv(dy1, wd1, N, ph, pw, cout, cin, 3, 1, 1, 1, resid=g, mask=rec["a_out"])
+                # identity shortcut: add the (already gated) upstream gradient in the epilogue
+                g_in = _conv(dy1, wd1, N, ph, pw, cout, cin, 3, 1, 1, 1, resid=g, gate=in_gate)
             g = g_in
 
         if min_unit == 0:
@@ -506,33 +595,44 @@ class _TrunkFn(torch.autograd.Function):
             q2 = (W2 - 1) // 2 + 1
             if 2 * (2 * W2 * 64 * 4 + 2 * q2 * 64 * 5) + 1024 <= 227 * 1024:
                 # maxpool + ReLU + BN backward fused: two sweeps over the stem output instead of five
-                sums = torch.zeros(2 * 64, device=dev, dtype=torch.float64)
+                sums = sums_of(trunk.bn1)
                 call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
                      bn0.invstd, sums, N, H2, W2, 64)
                 dy0 = torch.empty_like(sv["y0"])
-                dgamma, dbeta = torch.empty(64, device=dev), torch.empty(64, device=dev)
+                bw, bb = trunk.bn1.weight, trunk.bn1.bias
+                sw = getattr(bw, "_b2n_grad_slot", None) if need[id(bw)] else None
+                sb = getattr(bb, "_b2n_grad_slot", None) if need[id(bb)] else None
+                if sw is not None and sb is not None:
+                    dgamma, dbeta, acc = sw, sb, 1
+                else:
+                    dgamma, dbeta, acc = torch.empty(64, device=dev), torch.empty(64, device=dev), 0
                 call("b2n_pool_bn_bwd_apply", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
-                     bn0.invstd, trunk.bn1.weight, sums, dy0, dgamma, dbeta, N, H2, W2, 64, 1)
-                if need[id(trunk.bn1.weight)]:
-                    grads[id(trunk.bn1.weight)] = dgamma
-                if need[id(trunk.bn1.bias)]:
-                    grads[id(trunk.bn1.bias)] = dbeta
+                     bn0.invstd, bw, sums, dy0, dgamma, dbeta, N, H2, W2, 64, 1, acc)
+                if acc:
+                    for p in (bw, bb):
+                        sink = getattr(p, "_b2n_grad_sink", None)
+                        if sink is not None:
+                            sink.ready(p)
+                else:
+                    if need[id(bw)]:
+                        grads[id(bw)] = dgamma
+                    if need[id(bb)]:
+                        grads[id(bb)] = dbeta
             else:
                 gz = torch.empty_like(sv["y0"])
                 call("b2n_maxpool_relu_bwd", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, gz, N, H2,
                      W2, 64)
-                dy0 = bn_backward(gz, None, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
+                dy0 = bn_backward(gz, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
             if need[id(trunk.conv1.weight)]:
                 with _on_side(sv["xs"], dy0):
-                    dws = torch.zeros(64, 16 * STEM_C, device=dev, dtype=torch.float32)
+                    dws = dwp_of(trunk.conv1, 64, 16 * STEM_C)
                     call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
                          work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
                                "wgrad", 4.0 * N * H2 * W2 * (STEM_C + 64)))
-                    dw = torch.empty_like(trunk.conv1.weight)
-                    call("b2n_stem_unpack_wgrad", dws, dw, 64)
-                if side is not None:
+                    emit(trunk.conv1.weight, lambda t, acc: call("b2n_stem_unpack_wgrad", dws, t, 64, acc))
+                dw = grads[id(trunk.conv1.weight)]
+                if side is not None and dw is not None:
                     dw.record_stream(main)
-                grads[id(trunk.conv1.weight)] = dw
 
         if side is not None:
             main.wait_stream(side)   # all weight gradients are complete before anyone reads them

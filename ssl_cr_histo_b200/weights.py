@@ -37,7 +37,8 @@ def lerp_(dst: Sequence[torch.Tensor], src: Sequence[torch.Tensor], alpha: float
     dptr = PtrArr(*[d.data_ptr() for d in dst])
     sptr = PtrArr(*[s.data_ptr() for s in src])
     numel = LLArr(*[d.numel() for d in dst])
-    call("b2n_lerp_multi", dptr, sptr, numel, n, float(alpha), 1 if write_back else 0)
+    call("b2n_lerp_multi", dptr, sptr, numel, n, float(alpha), 1 if write_back else 0,
+         device=dst[0].device)
     _lib.WEIGHT_EPOCH += 1  # parameters changed behind autograd's version counters
 
 

@@ -65,7 +65,7 @@ def conv(x_nhwc, wp, N, H, W, Cin, Cout, R, stride, plo, phi, **kw):
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, y, yp[0], yp[1], N, H, W, Cin, Cout, R, R, stride,
          plo, phi, plo, phi, kw.get("scale"), kw.get("shift"), kw.get("resid"), rp[0], rp[1],
          kw.get("mask"), kw.get("relu", 0), kw.get("rnd", 0), kw.get("stats"), kw.get("lo_flag"),
-         0, 0, 0, 0, 0)
+         0, 0, 0, 0, 0, kw.get("gate"), *kw.get("bnb", (None,) * 5))
     return y
 
 
@@ -154,6 +154,55 @@ def test_conv_epilogue_scale_shift_resid_mask_relu_round():
     assert torch.equal(from_nhwc(y.cpu()), O.tf32_round(ref))
 
 
+@pytest.mark.parametrize("shape", [(3, 56, 56, 64, 64), (2, 28, 28, 128, 128), (5, 7, 7, 512, 512),
+                                   (1, 5, 9, 64, 64)])
+def test_conv_dgrad_epilogue_gate_and_batchnorm_backward_sums(shape):
+    """What the trunk's backward launches: (a) conv1's data gradient + the (pre-gated) shortcut
+    gradient, zeroed by the ReLU gate of the block input; (b) conv2's data gradient with bn1's
+    ReLU gate recomputed from y and the two BatchNorm-backward sums taken in the epilogue --
+    against b2n_bn_bwd_reduce over the materialised tensors (integer-valued data: exact)."""
+    N, H, W, Cin, Cout = shape
+    w = ints((Cout, Cin, 3, 3), -2, 2, 51, 0.25)
+    dy = ints((N, Cout, H, W), -4, 4, 52)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=1, padding=1)
+    resid, act = ints((N, Cin, H, W), -16, 16, 53), ints((N, Cin, H, W), -1, 1, 54)
+    g = to_nhwc(dy).to(DEV)
+    out = conv(g, pack_dgrad(w), N, H, W, Cout, Cin, 3, 1, 1, 1, resid=to_nhwc(resid).to(DEV),
+               gate=to_nhwc(act).to(DEV))
+    assert torch.equal(from_nhwc(out.cpu()), torch.where(act > 0, ref + resid, torch.zeros(())))
+    out = conv(g, pack_dgrad(w), N, H, W, Cout, Cin, 3, 1, 1, 1, gate=to_nhwc(act).to(DEV))
+    assert torch.equal(from_nhwc(out.cpu()), torch.where(act > 0, ref, torch.zeros(())))
+    # (b) y: raw output of the BN in front of the ReLU; small integers keep every product exact
+    y = ints((N, Cin, H, W), -3, 3, 55)
+    mean, invstd = ints((Cin,), -1, 1, 56, 0.5), ints((Cin,), 1, 2, 57, 0.5)
+    scale, shift = ints((Cin,), 1, 2, 58), ints((Cin,), -2, 2, 59, 0.5)
+    yd = to_nhwc(y).to(DEV)
+    stats = torch.zeros(2 * Cin, device=DEV, dtype=torch.float64)
+    out = conv(g, pack_dgrad(w), N, H, W, Cout, Cin, 3, 1, 1, 1, stats=stats,
+               bnb=(yd, mean.to(DEV), invstd.to(DEV), scale.to(DEV), shift.to(DEV)))
+    gate = (y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)) > 0
+    want = torch.where(gate, ref, torch.zeros(()))
+    assert torch.equal(from_nhwc(out.cpu()), want)
+    xhat = (y - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+    # (per-CTA partial sums are fp32: exact up to the rounding of long sums)
+    tol = dict(rtol=1e-6, atol=1e-5 * float((want.abs() * xhat.abs()).sum((0, 2, 3)).max()))
+    assert torch.allclose(stats[:Cin].cpu(), want.double().sum((0, 2, 3)), **tol)
+    assert torch.allclose(stats[Cin:].cpu(), (want.double() * xhat.double()).sum((0, 2, 3)), **tol)
+    s_ref = torch.zeros(2 * Cin, device=DEV, dtype=torch.float64)
+    call("b2n_bn_bwd_reduce", to_nhwc(ref).to(DEV), None, yd, mean.to(DEV), invstd.to(DEV),
+         scale.to(DEV), shift.to(DEV), s_ref, N * H * W, Cin)
+    assert torch.allclose(stats, s_ref, **tol)
+    # without the y-derived gate: plain sums of the result
+    stats.zero_()
+    out = conv(g, pack_dgrad(w), N, H, W, Cout, Cin, 3, 1, 1, 1, stats=stats,
+               bnb=(yd, mean.to(DEV), invstd.to(DEV), None, None))
+    assert torch.equal(from_nhwc(out.cpu()), ref)
+    assert torch.allclose(stats[:Cin].cpu(), ref.double().sum((0, 2, 3)), **tol)
+    with pytest.raises(RuntimeError, match="exclusive"):
+        conv(g, pack_dgrad(w), N, H, W, Cout, Cin, 3, 1, 1, 1, resid=to_nhwc(resid).to(DEV),
+             mask=to_nhwc(act).to(DEV), gate=to_nhwc(act).to(DEV))
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_wgrad_bit_exact(case):
     N, H, W, Cin, Cout, R, s, p = case
@@ -165,8 +214,10 @@ def test_conv_wgrad_bit_exact(case):
     call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
          p, p, p, p)
     dw = torch.empty(Cout, Cin, R, R, device=DEV)
-    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R)
+    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 0)
     assert torch.equal(dw.cpu(), ref)
+    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 1)      # accumulate: a second writer of the slot
+    assert torch.equal(dw.cpu(), 2 * ref)
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -203,10 +254,13 @@ def test_conv_dgrad_stride2_parity_classes_bit_exact(shape):
     g_in = torch.full((N, H, W, Cin), float("nan"), device=DEV)
     buf = torch.empty(9 * Cin * Cout, device=DEV)
     call("b2n_pack_weight_dgrad_s2", w3.to(DEV), buf, Cout, Cin)
+    act = ints((N, Cin, H, W), -1, 1, 45)            # the block input whose ReLU gate the classes apply
+    gate_t = to_nhwc(act).to(DEV)
 
-    def launch(x, wp, R, S, phi_h, phi_w, resid, place):
+    def launch(x, wp, R, S, phi_h, phi_w, resid, place, gate=None):
         call("b2n_conv_fwd", x, None, None, wp, None, None, g_in, None, None, N, P, Q, Cout, Cin, R, S,
-             1, 0, phi_h, 0, phi_w, None, None, resid, None, None, None, 0, 0, None, None, *place)
+             1, 0, phi_h, 0, phi_w, None, None, resid, None, None, None, 0, 0, None, None, *place,
+             gate, None, None, None, None, None)
 
     launch(to_nhwc(dy1).to(DEV), pack_dgrad(w1), 1, 1, 0, 0, None, (2, 0, 0, H, W))
     d3, off = to_nhwc(dy3).to(DEV), 0
@@ -216,6 +270,16 @@ def test_conv_dgrad_stride2_parity_classes_bit_exact(shape):
                (2, a0, b0, H, W))
         off += n
     assert torch.equal(from_nhwc(g_in.cpu()), ref)
+    # the same with every class launch gating its quarter (gradient w.r.t. a post-ReLU input)
+    g_in.fill_(float("nan"))
+    launch(to_nhwc(dy1).to(DEV), pack_dgrad(w1), 1, 1, 0, 0, None, (2, 0, 0, H, W))
+    off = 0
+    for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        n = Cin * (1 + a0) * (1 + b0) * Cout
+        launch(d3, buf[off:off + n], 1 + a0, 1 + b0, a0, b0, g_in if cls == 0 else None,
+               (2, a0, b0, H, W), gate=gate_t)
+        off += n
+    assert torch.equal(from_nhwc(g_in.cpu()), torch.where(act > 0, ref, torch.zeros(())))
 
 
 @pytest.mark.parametrize("size", [(2, 64, 64), (1, 224, 224), (3, 34, 46)])
@@ -248,8 +312,10 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     dws = torch.zeros(64, 16 * 32, device=DEV)
     call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1)
     dw = torch.empty(64, 3, 7, 7, device=DEV)
-    call("b2n_stem_unpack_wgrad", dws, dw, 64)
+    call("b2n_stem_unpack_wgrad", dws, dw, 64, 0)
     assert torch.equal(dw.cpu(), ref_dw)
+    call("b2n_stem_unpack_wgrad", dws, dw, 64, 1)
+    assert torch.equal(dw.cpu(), 2 * ref_dw)
 
 
 def test_conv_rejects_bad_shapes_loudly():
@@ -299,7 +365,11 @@ def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
     call("b2n_bn_bwd_reduce", gout.to(DEV), out, yd, mean, invstd, None, None, sums, rows, C)
     dy, dgamma, dbeta = torch.empty(rows, C, device=DEV), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
     call("b2n_bn_bwd_apply", gout.to(DEV), out, yd, mean, invstd, gamma.to(DEV), None, None, sums, dy,
-         dgamma, dbeta, rows, C, 0)
+         dgamma, dbeta, rows, C, 0, 0)
+    dg2, db2 = dgamma.clone(), dbeta.clone()
+    call("b2n_bn_bwd_apply", gout.to(DEV), out, yd, mean, invstd, gamma.to(DEV), None, None, sums, dy,
+         dg2, db2, rows, C, 0, 1)                               # accumulate into a gradient slot
+    assert torch.equal(dg2, 2 * dgamma) and torch.equal(db2, 2 * dbeta)
     scale_t = float(yr.grad.abs().max())
     assert float((dy.cpu() - yr.grad).abs().max()) < 2e-4 * scale_t
     assert torch.allclose(dgamma.cpu(), bn.weight.grad, rtol=1e-3, atol=1e-3)
@@ -313,9 +383,9 @@ def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
     assert torch.equal(s_m, s_y)
     dy_m, dy_y = torch.empty(rows, C, device=DEV), torch.empty(rows, C, device=DEV)
     call("b2n_bn_bwd_apply", gout.to(DEV), act, yd, mean, invstd, gamma.to(DEV), None, None, s_m, dy_m,
-         dgamma, dbeta, rows, C, 1)
+         dgamma, dbeta, rows, C, 1, 0)
     call("b2n_bn_bwd_apply", gout.to(DEV), None, yd, mean, invstd, gamma.to(DEV), scale, shift, s_m, dy_y,
-         dgamma, dbeta, rows, C, 1)
+         dgamma, dbeta, rows, C, 1, 0)
     assert torch.equal(dy_m, dy_y)
     # eval-mode fold
     call("b2n_bn_fold_eval", gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, C, 1e-5)
@@ -360,14 +430,14 @@ def test_bn_relu_maxpool_forward_backward(shape):
     call("b2n_bn_bwd_reduce", gz, None, yd, mean, invstd, None, None, s_ref, rows, C)
     dy_ref, dg_ref, db_ref = torch.empty_like(yd), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
     call("b2n_bn_bwd_apply", gz, None, yd, mean, invstd, gamma, None, None, s_ref, dy_ref, dg_ref, db_ref,
-         rows, C, 1)
+         rows, C, 1, 0)
     s_f = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
     call("b2n_pool_bn_bwd_reduce", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), mean,
          invstd, s_f, N, H, W, C)
     assert torch.allclose(s_f, s_ref, rtol=1e-5, atol=1e-5)
     dy_f, dg_f, db_f = torch.empty_like(yd), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
     call("b2n_pool_bn_bwd_apply", to_nhwc(ga).to(DEV), idx, yd, scale.to(DEV), shift.to(DEV), mean,
-         invstd, gamma, s_ref, dy_f, dg_f, db_f, N, H, W, C, 1)
+         invstd, gamma, s_ref, dy_f, dg_f, db_f, N, H, W, C, 1, 0)
     # (a position picked by 3-4 windows sums their gradients in scatter order: a last-bit
     # difference there can move the TF32 rounding of dy by one TF32 ulp = 2^-11 relative)
     assert torch.allclose(dy_f, dy_ref, rtol=1e-3, atol=1e-6 * float(dy_ref.abs().max()))
@@ -383,8 +453,11 @@ def test_avgpool():
     assert torch.allclose(e.cpu(), a.mean(1), rtol=1e-5, atol=1e-6)
     ge = torch.randn(5, 512)
     g = torch.empty(5, 49, 512, device=DEV)
-    call("b2n_avgpool_bwd", ge.to(DEV), g, 5, 49, 512)
-    assert torch.allclose(g.cpu(), (ge / 49).unsqueeze(1).expand(5, 49, 512), rtol=1e-6)
+    call("b2n_avgpool_bwd", ge.to(DEV), None, g, 5, 49, 512)
+    want = (ge / 49).unsqueeze(1).expand(5, 49, 512)
+    assert torch.allclose(g.cpu(), want, rtol=1e-6)
+    call("b2n_avgpool_bwd", ge.to(DEV), a.to(DEV), g, 5, 49, 512)      # gated by the pooled activation
+    assert torch.allclose(g.cpu(), torch.where(a > 0, want, torch.zeros(())), rtol=1e-6)
 
 
 @pytest.mark.parametrize("n", [1, 2, 77, 768])
@@ -412,6 +485,48 @@ def test_heads_forward_backward_fp32(n):
     lin_m.load_state_dict(lin.state_dict())
     f = torch.randn(n, 768)
     assert torch.allclose(heads.linear(f.to(DEV), lin_m).cpu(), lin(f).detach(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 5, 256])
+def test_pair_mlp_matches_the_concatenating_reference(n):
+    """models/net.py:56-64 (three concatenated pairs through the shared MLP, concatenated again) and
+    its E1 == E2 == E3 special case (:88-103), forward and every gradient -- also when the parameter
+    gradients are delivered into arena slots that already hold a value (accumulate)."""
+    from ssl_cr_histo_b200 import heads
+
+    torch.manual_seed(100 + n)
+    fc = torch.nn.Sequential(torch.nn.Linear(1024, 512), torch.nn.ReLU(True), torch.nn.Linear(512, 256))
+    E = [torch.randn(n, 512, requires_grad=True) for _ in range(3)]
+    dy = torch.randn(n, 768)
+    ref = O._pairwise_features(fc, *E)
+    ref.backward(dy)
+    m = torch.nn.Sequential(torch.nn.Linear(1024, 512), torch.nn.ReLU(True), torch.nn.Linear(512, 256)).to(DEV)
+    m.load_state_dict(fc.state_dict())
+    Em = [e.detach().to(DEV).requires_grad_(True) for e in E]
+    out = heads.pair_mlp(*Em, m[0], m[2])
+    out.backward(dy.to(DEV))
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    for a, b in zip(Em, E):
+        assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-4, atol=1e-5)
+    for a, b in zip(m.parameters(), fc.parameters()):
+        assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-4, atol=1e-4)
+    # the same input three times, evaluated once; gradients into pre-filled slots
+    for p in fc.parameters():
+        p.grad = None
+    e = torch.randn(n, 512, requires_grad=True)
+    ref = O._pairwise_features(fc, e, e, e)
+    ref.backward(dy)
+    for p in m.parameters():
+        p.grad = None
+        p._b2n_grad_slot = torch.ones_like(p)
+    em = e.detach().to(DEV).requires_grad_(True)
+    out = heads.pair_mlp_same(em, m[0], m[2])
+    out.backward(dy.to(DEV))
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(em.grad.cpu(), e.grad, rtol=1e-4, atol=1e-5)
+    for a, b in zip(m.parameters(), fc.parameters()):
+        assert a.grad is None                                   # autograd saw nothing: it went to the slot
+        assert torch.allclose(a._b2n_grad_slot.cpu() - 1, b.grad, rtol=1e-4, atol=1e-4)
 
 
 def test_fused_losses_match_torch():
@@ -454,6 +569,14 @@ def test_fused_losses_match_torch():
     assert torch.equal(pseudo.cpu(), tu) and torch.equal(pred.cpu(), torch.argmax(lx, 1))
     assert torch.allclose(am.grad.cpu(), a.grad, rtol=1e-5, atol=1e-7)
     assert torch.allclose(bm.grad.cpu(), b.grad, rtol=1e-5, atol=1e-7)
+    # a label outside [0, C) is never dereferenced: the loss turns NaN instead of reading garbage
+    bad = tgt.clone(); bad[5] = -100
+    loss, _ = losses.cross_entropy(lg.to(DEV), bad.to(DEV))
+    assert torch.isnan(loss)
+    with pytest.raises(RuntimeError, match="must both be"):
+        losses.consistency_ce(lx.to(DEV), tx.to(DEV), lw[:20].to(DEV), ls.to(DEV), 1.0)
+    with pytest.raises(RuntimeError, match="class targets"):
+        losses.cross_entropy(lg.to(DEV), tgt[:30].to(DEV))
 
 
 def test_lerp_handoff_bitwise_and_lookahead_golden():

@@ -7,10 +7,14 @@ Tolerances (BASELINE.json north_star / SURVEY.md section 8d):
     error-compensated 3xTF32);
   * RSP argmax: bit-exact, with an asserted top-2 margin floor;
   * BN running statistics: <= 1e-3 relative (measured ~3e-5), counters exact;
-  * gradients: <= 3e-2 relative L2 per tensor (measured ~1e-2).  The backward convs multiply
-    plain TF32 operands, and -- the larger part -- a forward difference of only ~5e-5 (the
-    tensor core's FP32 accumulation order) already flips ~1e-5 of the ReLU gates, which a
-    gradient with random-sign terms sees as sqrt(flipped fraction).  DESIGN.md, "Numerics".
+  * gradients: <= 2e-2 relative L2 per tensor = 2x the measured ~1e-2.  SURVEY 8(d) asked for 1e-3;
+    tools/grad_gate.py (profiles/r2_grad_gate.md) shows that no implementation can meet that
+    against an fp32 oracle: the oracle in float64 -- the exact answer -- is itself 4.3e-3 (worst
+    tensor) / 2.5e-3 (median) away from the fp32 oracle at N=8, 224x224, because a forward
+    difference of ~1e-6 already flips ReLU gates and a gradient of random-sign terms sees that as
+    sqrt(flipped fraction).  The TF32 operand rounding of the backward convs alone contributes
+    1.3e-3 (oracle with TF32_BACKWARD); torch's own GPU default (TF32 everywhere) is at 1.5e-1.
+    DESIGN.md, "Numerics".
 """
 import copy
 
@@ -27,7 +31,7 @@ from util import golden, max_rel, rel_l2, top2_margin
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL = 1e-3
-GRAD_TOL = 3e-2
+GRAD_TOL = 2e-2
 
 
 def pair(kind, head, seed=42):
@@ -60,6 +64,15 @@ def assert_grads_close(mine, ref, tol=GRAD_TOL):
         r = rel_l2(g1, g2)
         if r > worst[1]:
             worst = (n1, r)
+    try:        # measured floors of every gradient comparison, for DESIGN.md / the tolerance
+        import inspect, json, os
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "grad_worst.jsonl"), "a") as f:
+            f.write(json.dumps({"test": inspect.stack()[1].function, "tensor": worst[0],
+                                "rel_l2": worst[1]}) + "\n")
+    except OSError:
+        pass
     assert worst[1] <= tol, "gradient %s differs by %.3e relative L2" % worst
     return worst[1]
 
@@ -380,3 +393,170 @@ def test_single_patch_and_non_square_train_step(N, H, W):
     if N > 1:       # (with one sample and a 2x2 final map the BN statistics are too thin for a grad gate)
         assert_grads_close([gm, gh], [om, oh])
     assert_buffers_close(gm, om)
+
+
+# ------------------------------------------------------------------ BASELINE batch sizes vs the oracle
+def _need_host_memory(gb):
+    import psutil
+    avail = psutil.virtual_memory().available / 2 ** 30
+    if avail < gb:
+        pytest.skip("full-size CPU oracle needs ~%d GB of host memory, %.0f GB available" % (gb, avail))
+
+
+def _report(name, rows):
+    """Per-tensor gradient / buffer differences of a full-size run, kept next to the bench artefacts."""
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_%s.json" % name), "w") as f:
+        json.dump(rows, f, indent=1)
+    print("\n[%s] " % name + ", ".join("%s=%.3g" % (k, v) for k, v in rows["summary"].items()))
+
+
+def _grad_table(mine, ref):
+    return {n1: rel_l2(g1, g2) for (n1, g1), (_, g2) in zip(grads_of(mine), grads_of(ref)) if g1 is not None}
+
+
+def test_cfg3_full_size_consistency_step_vs_oracle():
+    """BASELINE.json configs[2] at its real size -- eval_BreastPathQ_SSL_CR.py:62-105 with
+    --batch_size 64 --mu 8 --modules_student 0: 192 labeled + 512 weak + 512 strong 224x224
+    patches, teacher eval / student train, MSE/MSE, Adam -- once against the CPU oracle (which runs
+    the trunk three times per model call, models/net.py:88-90).  704-row tiles wrap the 148 SMs
+    hundreds of times and the HALO rasters reach 2.4 M rows here; nothing smaller exercises that."""
+    _need_host_memory(150)
+    b, mu, size = 64, 8, 224
+    ix = O.synthetic_patches(3 * b, size, seed=10)
+    iw, is_ = O.synthetic_patches(b * mu, size, seed=11), O.synthetic_patches(b * mu, size, seed=12)
+    tx = torch.rand(3 * b, generator=torch.Generator().manual_seed(6))
+
+    def run(models, dev):
+        student, cls_s = models
+        teacher, cls_t = copy.deepcopy(student), copy.deepcopy(cls_s)
+        O.freeze_by_index(teacher, 64)
+        for p in cls_t.parameters():
+            p.requires_grad = False
+        teacher.eval(); cls_t.eval(); student.train(); cls_s.train()
+        opt = O.make_cr_optimizer(list(student.parameters()) + list(cls_s.parameters()))
+        before = [p.detach().clone() for p in list(student.parameters()) + list(cls_s.parameters())]
+        out = O.consistency_step(teacher, student, cls_t, cls_s, opt, ix.to(dev), tx.to(dev),
+                                 iw.to(dev), is_.to(dev), 1.0, "mse")
+        return out, before
+
+    om, oh, gm, gh = pair("finetune", ("finetune", 1))
+    out_g, before_g = run((gm, gh), DEV)
+    torch.cuda.synchronize()
+    out_o, _ = run((om, oh), "cpu")
+    summary = {}
+    for k in ("logits_u_w", "logits_x", "logits_u_s"):
+        summary[k] = max_rel(out_g[k], out_o[k])
+        assert summary[k] <= TOL, (k, summary[k])
+    for k in ("sup", "cons", "loss"):
+        summary[k] = abs(float(out_g[k]) - float(out_o[k])) / max(abs(float(out_o[k])), 1e-3)
+        assert summary[k] <= TOL, (k, summary[k])
+    assert_buffers_close(gm, om)
+    table = _grad_table([gm, gh], [om, oh])
+    summary["grad_rel_l2_worst"] = max(table.values())
+    summary["grad_rel_l2_median"] = sorted(table.values())[len(table) // 2]
+    # Adam's first step moves every weight by ~lr * sign(g): the updated weights agree to a small
+    # fraction of lr except where a near-zero gradient element has the other sign (bounded by 2 lr)
+    lr, flips, total = 1e-4, 0, 0
+    for (n, p), (_, q), p0 in zip(list(gm.named_parameters()) + list(gh.named_parameters()),
+                                  list(om.named_parameters()) + list(oh.named_parameters()), before_g):
+        d = (p.detach().cpu() - q.detach()).abs()
+        assert float(d.max()) <= 2.1 * lr + 1e-6 * float(q.abs().max()), n
+        flips += int((d > 0.25 * lr).sum()); total += d.numel()
+        assert not torch.equal(p.detach(), p0), n           # the optimizer really stepped
+    summary["adam_step_fraction_off_by_quarter_lr"] = flips / total
+    assert flips / total < 0.02
+    _report("cfg3_full", {"summary": summary, "grad_rel_l2": table})
+    assert summary["grad_rel_l2_worst"] <= GRAD_TOL, max(table, key=table.get)
+
+
+def test_cfg2_full_size_rsp_step_vs_oracle():
+    """BASELINE.json configs[1] at its real size -- pretrain_BreastPathQ.py:42-68 with 256 triples
+    (768 patches, three trunk passes with per-pass BN statistics), CE over the 6 orders,
+    SGD-Nesterov: logits, loss, bit-exact argmax (margin-checked), BN buffers, gradients, updated
+    weights against the CPU oracle."""
+    _need_host_memory(64)
+    N, size = 256, 224
+    i1, i2, i3 = (O.synthetic_patches(N, size, seed=s) for s in (0, 1, 2))
+    target = torch.randint(0, 6, (N,), generator=torch.Generator().manual_seed(5))
+    om, oh, gm, gh = pair("triplet", ("classifier", 6))
+    for m in (om, oh, gm, gh):
+        m.train()
+    opt_g = O.make_rsp_optimizer(list(gm.parameters()) + list(gh.parameters()))
+    out_g = O.rsp_pretrain_step(gm, gh, opt_g, i1.to(DEV), i2.to(DEV), i3.to(DEV), target.to(DEV))
+    torch.cuda.synchronize()
+    opt_o = O.make_rsp_optimizer(list(om.parameters()) + list(oh.parameters()))
+    out_o = O.rsp_pretrain_step(om, oh, opt_o, i1, i2, i3, target)
+    summary = {"logits": max_rel(out_g["output"], out_o["output"]),
+               "feats": max_rel(out_g["feats"], out_o["feats"]),
+               "loss": abs(float(out_g["loss"]) - float(out_o["loss"])) / float(out_o["loss"])}
+    assert summary["logits"] <= TOL and summary["feats"] <= TOL and summary["loss"] <= TOL, summary
+    # bit-exact permutation id wherever the oracle's own top-2 margin exceeds 10x the logit error;
+    # rows below that margin are ties at fp32 resolution and are counted, not compared
+    err = float((out_g["output"].cpu() - out_o["output"]).abs().max())
+    top = out_o["output"].double().topk(2, dim=1).values
+    decided = (top[:, 0] - top[:, 1]) > 10 * err
+    summary["argmax_rows_decided"] = float(decided.float().mean())
+    assert summary["argmax_rows_decided"] >= 0.97
+    assert torch.equal(out_g["pred"].cpu()[decided], out_o["pred"][decided])
+    assert_buffers_close(gm, om)
+    table = _grad_table([gm, gh], [om, oh])
+    summary["grad_rel_l2_worst"] = max(table.values())
+    summary["grad_rel_l2_median"] = sorted(table.values())[len(table) // 2]
+    for (n, p), (_, q) in zip(gm.named_parameters(), om.named_parameters()):
+        assert float((p.cpu() - q).abs().max()) <= TOL * float(q.abs().max()) + 1e-5, n
+    _report("cfg2_full", {"summary": summary, "grad_rel_l2": table})
+    assert summary["grad_rel_l2_worst"] <= GRAD_TOL, max(table, key=table.get)
+
+
+def test_parameter_writes_through_data_are_seen_by_the_packed_weights():
+    """The vendored Lookahead (lookahead.py:96-97) and RAdam write ``p.data``, which bumps no version
+    counter.  A training-mode trunk repacks after every backward pass; an eval-mode one is told with
+    ``invalidate_packs()``."""
+    _, _, gm, gh = pair("finetune", ("finetune", 9))
+    x = O.synthetic_patches(4, 64, seed=95).to(DEV)
+    target = torch.tensor([0, 3, 8, 1], device=DEV)
+    gm.train()
+    F.cross_entropy(gh(gm(x)), target).backward()
+    for p in gm.parameters():
+        p.data.mul_(0.5)                                   # lookahead-style write, _version unchanged
+    fresh = copy.deepcopy(gm)                              # packs are never copied: built from p.data
+    with torch.no_grad():
+        assert torch.equal(gm(x), fresh(x))
+    gm.eval(); fresh.eval()
+    with torch.no_grad():
+        before = gm(x)
+        for p in gm.parameters():
+            p.data.mul_(1.5)
+        gm.model.invalidate_packs()
+        after = gm(x)
+        expect = copy.deepcopy(gm).eval()(x)
+    assert not torch.equal(before, after) and torch.equal(after, expect)
+
+
+@pytest.mark.parametrize("kind", ["finetune", "triplet"])
+def test_gradient_arena_slots_equal_autograd_accumulation(kind):
+    """ddp.GradAllReducer on one rank is just the flat arena: the backward kernels accumulate every
+    parameter gradient straight into its slot (three writers per slot for TripletNet's three trunk
+    passes) and autograd sees None -- same values as the per-parameter tensors autograd would have
+    summed."""
+    from ssl_cr_histo_b200 import ddp
+    head = ("finetune", 9) if kind == "finetune" else ("classifier", 6)
+    _, _, gm, gh = pair(kind, head)
+    gm2, gh2 = copy.deepcopy(gm), copy.deepcopy(gh)
+    xs = [O.synthetic_patches(4, 64, seed=96 + i).to(DEV) for i in range(3 if kind == "triplet" else 1)]
+    target = torch.tensor([0, 3, 5, 1], device=DEV)
+    gm.train(); gm2.train()
+    F.cross_entropy(gh(gm(*xs)), target).backward()
+    params2 = list(gm2.parameters()) + list(gh2.parameters())
+    red = ddp.GradAllReducer(params2)
+    for _ in range(2):                                     # slots are re-zeroed, not re-allocated
+        red.zero_grad()
+        F.cross_entropy(gh2(gm2(*xs)), target).backward()
+        red.all_reduce()
+    for (n, p), q in zip(list(gm.named_parameters()) + list(gh.named_parameters()), params2):
+        assert q.grad.data_ptr() == q._b2n_grad_slot.data_ptr(), n
+        assert rel_l2(q.grad, p.grad) < 1e-5, n            # (split-K atomics: order varies)

@@ -32,7 +32,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), "libb2n.so does not export %s" % name
     assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
     lib.b2n_version.restype = ctypes.c_int
-    assert lib.b2n_version() == 1
+    assert lib.b2n_version() == 2
 
 
 def test_library_has_blackwell_tensor_core_and_tma_sass():
@@ -147,18 +147,35 @@ def _ddp_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(0)
-    lin = torch.nn.Linear(5, 3)                                  # same weights on every rank
+    torch.manual_seed(rank)                                      # replicas start DIFFERENT ...
+    lin, lin2 = torch.nn.Linear(5, 3), torch.nn.Linear(3, 2)
     frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
-    red = ddp.GradAllReducer(list(lin.parameters()) + [frozen])
-    assert red.nbytes == (15 + 3) * 4
+    params = list(lin.parameters()) + list(lin2.parameters())
+    # two buckets (32-byte limit), started as their gradients are reported ready
+    red = ddp.GradAllReducer(params + [frozen], overlap=True, bucket_mb=32 / 2 ** 20)
+    out["w%d" % rank] = lin.weight.detach().clone()              # ... and are synchronised to rank 0
+    assert red.nbytes == (15 + 3 + 6 + 2) * 4 and len(red.buckets) == 2
+    assert lin2.bias.grad.data_ptr() == red.flat.data_ptr()      # arena in backward order
+    assert lin.weight._b2n_grad_slot.data_ptr() == lin.weight.grad.data_ptr()
     data = torch.arange(40, dtype=torch.float32).view(8, 5) / 10.0
     shard = ddp.shard(data, rank, world)
-    red.zero_grad()
-    lin(shard).pow(2).mean().backward()
-    red.all_reduce()
-    out[rank] = torch.cat([p.grad.flatten() for p in lin.parameters()]).clone()
-    assert lin.weight.grad.data_ptr() == red.flat.data_ptr()     # still aliased into the arena
+    for step in range(2):                                        # re-armed by zero_grad
+        red.zero_grad()
+        lin2(lin(shard)).pow(2).mean().backward()                # autograd accumulates into the slots
+        for p in reversed(params):                               # what the package's backward reports
+            red.ready(p)
+        assert all(n == -1 for n in red._pending)                # both buckets already in flight
+        red.all_reduce()
+    out[rank] = torch.cat([p.grad.flatten() for p in params]).clone()
+    assert lin.weight.grad.data_ptr() == red._slots[id(lin.weight)].data_ptr()   # still in the arena
+    # a plain (non-overlapped) reducer and set_to_none
+    red2 = ddp.GradAllReducer(params, sync_initial=False)
+    for p in params:
+        p.grad = None
+    red2.zero_grad()
+    lin2(lin(shard)).pow(2).mean().backward()
+    red2.all_reduce(average=False)
+    out["sum%d" % rank] = torch.cat([p.grad.flatten() for p in params]).clone()
     dist.destroy_process_group()
 
 
@@ -168,12 +185,14 @@ def test_grad_arena_allreduce_world2_matches_full_batch():
     out = mgr.dict()
     mp.spawn(_ddp_worker, args=(world, port, out), nprocs=world, join=True)
     torch.manual_seed(0)
-    lin = torch.nn.Linear(5, 3)
+    lin, lin2 = torch.nn.Linear(5, 3), torch.nn.Linear(3, 2)
+    assert torch.equal(out["w0"], lin.weight.detach()) and torch.equal(out["w1"], out["w0"])
     data = torch.arange(40, dtype=torch.float32).view(8, 5) / 10.0
-    lin(data).pow(2).mean().backward()
-    full = torch.cat([p.grad.flatten() for p in lin.parameters()])
+    lin2(lin(data)).pow(2).mean().backward()
+    full = torch.cat([p.grad.flatten() for p in list(lin.parameters()) + list(lin2.parameters())])
     assert torch.allclose(out[0], out[1])
     assert torch.allclose(out[0], full, rtol=1e-5, atol=1e-6)    # mean of shard means == full mean
+    assert torch.allclose(out["sum0"], 2 * full, rtol=1e-5, atol=1e-6)   # average=False leaves the sum
 
 
 def test_shard_rejects_ragged_batches():
