@@ -235,8 +235,9 @@ int b2n_lerp_multi(float* const* dst, float* const* src, const long long* numel,
 int b2n_adam_multi(float* const* p, const float* const* g, float* const* exp_avg,
                    float* const* exp_avg_sq, const long long* numel, int n, double lr, double beta1,
                    double beta2, double eps, double weight_decay, long long step,
-                   double grad_scale,
-                   void* stream);
+                   long long* step_dev /* optional device counter: when given it is incremented and
+                   used instead of `step`, so the launch can be replayed from a CUDA graph */,
+                   double grad_scale, void* stream);
 /* SGD with momentum (dampening 0), optional Nesterov, L2 weight decay; first_step != 0
  * initialises the momentum buffer with the gradient:
  *   replaces torch.optim.SGD(nesterov=True) (pretrain_BreastPathQ.py:245,61;

@@ -5,8 +5,12 @@ Public surface (mirrors the reference's operator interface for this path):
   losses.cross_entropy / consistency_mse / consistency_ce               (fused loss kernels)
   weights.lerp_ / teacher_handoff_ / lookahead_pull_                    (multi-tensor lerp)
   ddp.GradAllReducer                                                    (one NCCL all-reduce / step)
+  optim.Adam / optim.SGD                                                (multi-tensor optimizer steps)
+  graph.GraphedStep                                                     (whole-step CUDA-graph replay)
+  augment.*                                                             (weak / strong views on the GPU)
+  infer.probability_map                                                 (WSI heat-map inference loop)
 """
 from . import net  # noqa: F401
-from . import losses, weights, ddp  # noqa: F401
+from . import losses, weights, ddp, optim, graph  # noqa: F401
 
-__all__ = ["net", "losses", "weights", "ddp"]
+__all__ = ["net", "losses", "weights", "ddp", "optim", "graph"]

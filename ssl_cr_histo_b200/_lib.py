@@ -47,7 +47,7 @@ _SIGNATURES = {
     "b2n_fused_loss": [I, P, P, P, P, P, I, I, I, F, P, P, P, P, P],
     "b2n_softmax_last": [P, P, I, I],
     "b2n_lerp_multi": [P, P, P, I, F, I],
-    "b2n_adam_multi": [P, P, P, P, P, I, D, D, D, D, D, LL, D],
+    "b2n_adam_multi": [P, P, P, P, P, I, D, D, D, D, D, LL, P, D],
     "b2n_sgd_multi": [P, P, P, P, I, D, D, D, I, I, D],
 }
 EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok", "b2n_launch_count"] + list(_SIGNATURES)

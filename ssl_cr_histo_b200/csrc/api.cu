@@ -221,13 +221,12 @@ int b2n_lerp_multi(float* const* dst, float* const* src, const long long* numel,
 int b2n_adam_multi(float* const* p, const float* const* g, float* const* exp_avg,
                    float* const* exp_avg_sq, const long long* numel, int n, double lr, double beta1,
                    double beta2, double eps, double weight_decay, long long step,
-                   double grad_scale,
-                   void* stream) {
+                   long long* step_dev, double grad_scale, void* stream) {
   if (n < 0 || (n > 0 && (!p || !g || !exp_avg || !exp_avg_sq || !numel)))
     return set_error("b2n_adam_multi: bad args");
   return counted(launch_adam_multi(p, g, exp_avg, exp_avg_sq, numel, n, lr, beta1, beta2, eps,
-                                   weight_decay, step, grad_scale, S(stream)),
-                 (n + 63) / 64);
+                                   weight_decay, step, step_dev, grad_scale, S(stream)),
+                 (n + 63) / 64 + (step_dev != nullptr ? 1 : 0));
 }
 
 int b2n_sgd_multi(float* const* p, const float* const* g, float* const* momentum_buf,

@@ -167,8 +167,7 @@ int launch_lerp_multi(float* const* dst, float* const* src, const long long* num
 int launch_adam_multi(float* const* p, const float* const* g, float* const* exp_avg,
                       float* const* exp_avg_sq, const long long* numel, int n, double lr, double beta1,
                       double beta2, double eps, double weight_decay, long long step,
-                      double grad_scale,
-                      cudaStream_t stream);
+                      long long* step_dev, double grad_scale, cudaStream_t stream);
 int launch_sgd_multi(float* const* p, const float* const* g, float* const* momentum_buf,
                      const long long* numel, int n, double lr, double momentum, double weight_decay,
                      int nesterov, int first_step, double grad_scale, cudaStream_t stream);

@@ -22,10 +22,21 @@ struct OptTable {
   long long numel[kOptMaxTensors];
 };
 
-// torch/optim/adam.py _single_tensor_adam (amsgrad=False, maximize=False, L2 weight decay)
+__global__ void counter_add_kernel(long long* c, long long d) { *c += d; }
+
+// torch/optim/adam.py _single_tensor_adam (amsgrad=False, maximize=False, L2 weight decay).
+// step_dev != null (CUDA-graph capturable mode): the step count lives on the device, so the bias
+// corrections are formed here (in double, like the host path) instead of being baked into the launch.
 __global__ void adam_multi_kernel(const OptTable t, float step_size, float one_minus_beta1, float beta2,
                                   float one_minus_beta2, float eps, float weight_decay,
-                                  float bias_c2_sqrt, float grad_scale) {
+                                  float bias_c2_sqrt, float grad_scale,
+                                  const long long* __restrict__ step_dev, double lr, double beta1_d,
+                                  double beta2_d) {
+  if (step_dev != nullptr) {
+    const double step = static_cast<double>(*step_dev);
+    step_size = static_cast<float>(lr / (1.0 - pow(beta1_d, step)));
+    bias_c2_sqrt = static_cast<float>(sqrt(1.0 - pow(beta2_d, step)));
+  }
   float* __restrict__ p = t.p[blockIdx.y];
   const float* __restrict__ g = t.g[blockIdx.y];
   float* __restrict__ m = t.s1[blockIdx.y];
@@ -99,19 +110,24 @@ static int for_each_chunk(float* const* p, const float* const* g, float* const* 
 int launch_adam_multi(float* const* p, const float* const* g, float* const* exp_avg,
                       float* const* exp_avg_sq, const long long* numel, int n, double lr, double beta1,
                       double beta2, double eps, double weight_decay, long long step,
-                      double grad_scale, cudaStream_t stream) {
-  if (step < 1) return set_error("adam_multi: step must be >= 1 (got %lld)", step);
-  const double bias_c1 = 1.0 - pow(beta1, static_cast<double>(step));
-  const double bias_c2 = 1.0 - pow(beta2, static_cast<double>(step));
-  const float step_size = static_cast<float>(lr / bias_c1);
-  const float bias_c2_sqrt = static_cast<float>(sqrt(bias_c2));
+                      long long* step_dev, double grad_scale, cudaStream_t stream) {
+  float step_size = 0.f, bias_c2_sqrt = 1.f;
+  if (step_dev != nullptr) {
+    counter_add_kernel<<<1, 1, 0, stream>>>(step_dev, 1);   // this call is step *step_dev + 1
+  } else {
+    if (step < 1) return set_error("adam_multi: step must be >= 1 (got %lld)", step);
+    const double bias_c1 = 1.0 - pow(beta1, static_cast<double>(step));
+    const double bias_c2 = 1.0 - pow(beta2, static_cast<double>(step));
+    step_size = static_cast<float>(lr / bias_c1);
+    bias_c2_sqrt = static_cast<float>(sqrt(bias_c2));
+  }
   return for_each_chunk(p, g, exp_avg, exp_avg_sq, numel, n, "adam_multi",
                         [&](const OptTable& t, dim3 grid) {
                           adam_multi_kernel<<<grid, 256, 0, stream>>>(
                               t, step_size, static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
                               static_cast<float>(1.0 - beta2), static_cast<float>(eps),
                               static_cast<float>(weight_decay), bias_c2_sqrt,
-                              static_cast<float>(grad_scale));
+                              static_cast<float>(grad_scale), step_dev, lr, beta1, beta2);
                         });
 }
 

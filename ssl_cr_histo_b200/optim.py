@@ -48,9 +48,15 @@ def _check(p: torch.Tensor, g: torch.Tensor) -> None:
 
 
 class Adam(torch.optim.Optimizer):
-    """torch.optim.Adam (L2 weight decay, no amsgrad) in one launch per 64 tensors."""
+    """torch.optim.Adam (L2 weight decay, no amsgrad) in one launch per 64 tensors.
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
+    ``capturable=True`` keeps the step count on the device (one counter per launch group, bumped by
+    the launch itself) so that ``step()`` can be captured into a CUDA graph and replayed
+    (``graph.GraphedStep``); ``state[p]["step"]`` then counts eager calls only.  Learning rate and
+    the other hyper-parameters are baked into a captured launch: re-capture after changing them."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0,
+                 capturable=False):
         if lr < 0.0:
             raise ValueError("Invalid learning rate: {}".format(lr))
         if eps < 0.0:
@@ -63,6 +69,8 @@ class Adam(torch.optim.Optimizer):
             raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
+        self.capturable = bool(capturable)
+        self._step_dev = {}     # capturable: (group index, eager step) -> device counter
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -70,7 +78,7 @@ class Adam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             by_step = {}
             for p in group["params"]:
                 if p.grad is None:
@@ -89,8 +97,16 @@ class Adam(torch.optim.Optimizer):
                                                [self.state[p]["exp_avg"] for p in ps],
                                                [self.state[p]["exp_avg_sq"] for p in ps]])
                 numel = (ctypes.c_longlong * n)(*[p.numel() for p in ps])
+                counter = None
+                if self.capturable:
+                    # parameters that have taken the same number of steps share one device counter
+                    key = (gi, tuple(id(p) for p in ps))
+                    counter = self._step_dev.get(key)
+                    if counter is None:
+                        counter = self._step_dev[key] = torch.full(
+                            (1,), step - 1, device=ps[0].device, dtype=torch.long)
                 call("b2n_adam_multi", pt, gt, mt, vt, numel, n, float(group["lr"]), float(b1),
-                     float(b2), float(group["eps"]), float(group["weight_decay"]), int(step),
+                     float(b2), float(group["eps"]), float(group["weight_decay"]), int(step), counter,
                      float(self.grad_scale), device=ps[0].device)
                 _touch(ps)
         return loss

@@ -203,7 +203,6 @@ def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs
         momentum = 0.1 if bn.momentum is None else bn.momentum
         call("b2n_bn_finalize", stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
              st.scale, st.shift, st.mean, st.invstd, C, float(count), momentum, bn.eps, n_updates)
-        bn.num_batches_tracked += n_updates
     else:
         call("b2n_bn_fold_eval", bn.weight, bn.bias, bn.running_mean, bn.running_var, st.scale,
              st.shift, C, bn.eps)
@@ -285,8 +284,11 @@ class _TrunkFn(torch.autograd.Function):
         if (H | W) & 1:
             raise RuntimeError("H and W must be even (got %dx%d)" % (H, W))
         packs = trunk._packs
-        if training and getattr(trunk, "_packs_dirty", True):
-            packs.invalidate()          # see _PackCache: p.data writes are invisible to the tags
+        if (training and getattr(trunk, "_packs_dirty", True)) or \
+                torch.cuda.is_current_stream_capturing():
+            # see _PackCache: p.data writes are invisible to the tags.  Under CUDA-graph capture the
+            # pack kernels must be part of the graph, whatever the cache holds.
+            packs.invalidate()
             trunk._packs_dirty = False
         bns = trunk.bn_layers()
         total_c = sum(b.num_features for b in bns)
@@ -391,6 +393,8 @@ class _TrunkFn(torch.autograd.Function):
 
         e = torch.empty(N, 512, device=dev, dtype=torch.float32)
         call("b2n_avgpool_fwd", a.hi, a.lo, e, N, h * w, 512)
+        if training:    # nn.BatchNorm2d's per-forward counter, all twenty layers in one launch
+            torch._foreach_add_([b.num_batches_tracked for b in bns], n_updates)
         ctx.trunk = trunk
         ctx.saved = saved if save else None
         ctx.bufs = bufs

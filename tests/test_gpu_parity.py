@@ -7,13 +7,16 @@ Tolerances (BASELINE.json north_star / SURVEY.md section 8d):
     error-compensated 3xTF32);
   * RSP argmax: bit-exact, with an asserted top-2 margin floor;
   * BN running statistics: <= 1e-3 relative (measured ~3e-5), counters exact;
-  * gradients: <= 2e-2 relative L2 per tensor = 2x the measured ~1e-2.  SURVEY 8(d) asked for 1e-3;
-    tools/grad_gate.py (profiles/r2_grad_gate.md) shows that no implementation can meet that
-    against an fp32 oracle: the oracle in float64 -- the exact answer -- is itself 4.3e-3 (worst
-    tensor) / 2.5e-3 (median) away from the fp32 oracle at N=8, 224x224, because a forward
-    difference of ~1e-6 already flips ReLU gates and a gradient of random-sign terms sees that as
-    sqrt(flipped fraction).  The TF32 operand rounding of the backward convs alone contributes
-    1.3e-3 (oracle with TF32_BACKWARD); torch's own GPU default (TF32 everywhere) is at 1.5e-1.
+  * gradients: <= 2.5e-2 relative L2 per tensor; the largest value any test here measures is 1.52e-2
+    (gpurun_out/grad_worst.jsonl; 8.9e-3 at full cfg3 size, 1.5e-2 at full cfg2 size).  SURVEY 8(d)
+    asked for 1e-3; tools/grad_gate.py (profiles/r2_grad_gate.md, N=8 at 224x224) shows that no
+    implementation meets that against an fp32 oracle: the oracle in float64 -- the exact answer -- is
+    itself 4.3e-3 (worst tensor) / 2.5e-3 (median) away from the fp32 oracle, torch + cuDNN in strict
+    fp32 on the B200 6.4e-3 / 4.1e-3, this package 5.6e-3 / 2.9e-3, and torch's own GPU default (TF32
+    convolutions) 1.3e-1 / 9.8e-2.  The cause is not the arithmetic of the backward pass (TF32
+    operand rounding of the backward convs alone: 1.3e-3, oracle with TF32_BACKWARD) but ReLU gates:
+    a forward difference of ~1e-6 already flips some, and a gradient of random-sign terms sees that
+    as sqrt(flipped fraction).
     DESIGN.md, "Numerics".
 """
 import copy
@@ -31,7 +34,7 @@ from util import golden, max_rel, rel_l2, top2_margin
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL = 1e-3
-GRAD_TOL = 2e-2
+GRAD_TOL = 2.5e-2
 
 
 def pair(kind, head, seed=42):
@@ -560,3 +563,51 @@ def test_gradient_arena_slots_equal_autograd_accumulation(kind):
     for (n, p), q in zip(list(gm.named_parameters()) + list(gh.named_parameters()), params2):
         assert q.grad.data_ptr() == q._b2n_grad_slot.data_ptr(), n
         assert rel_l2(q.grad, p.grad) < 1e-5, n            # (split-K atomics: order varies)
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """graph.GraphedStep: a whole consistency step (teacher forward, student forward, fused loss,
+    backward, capturable multi-tensor Adam) captured once and replayed -- weights, BN buffers and
+    losses follow the eager run of the same steps (bias corrections advance on the device)."""
+    from ssl_cr_histo_b200 import graph, losses, optim
+
+    def build():
+        _, _, student, cls_s = pair("finetune", ("finetune", 1))
+        teacher, cls_t = copy.deepcopy(student).eval(), copy.deepcopy(cls_s).eval()
+        for p in list(teacher.parameters()) + list(cls_t.parameters()):
+            p.requires_grad = False
+        student.train(); cls_s.train()
+        params = list(student.parameters()) + list(cls_s.parameters())
+        opt = optim.Adam(params, lr=1e-3, weight_decay=1e-4, capturable=True)
+
+        def step(ix, tx, iw, is_):
+            with torch.no_grad():
+                lw = cls_t(teacher(iw))
+            logits = cls_s(student(torch.cat((ix, is_))))
+            loss, _ = losses.consistency_mse(logits[:ix.shape[0]], tx, lw, logits[ix.shape[0]:], 1.0)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        return student, cls_s, step
+
+    batches = [(O.synthetic_patches(3, 64, seed=200 + i).to(DEV), torch.rand(3, device=DEV),
+                O.synthetic_patches(4, 64, seed=300 + i).to(DEV),
+                O.synthetic_patches(4, 64, seed=400 + i).to(DEV)) for i in range(5)]
+    s_e, c_e, step_e = build()
+    eager_losses = [float(step_e(*b)) for b in batches]
+    s_g, c_g, step_g = build()
+    g = graph.GraphedStep(step_g, batches[0], warmup=2)        # 2 real warm-up steps; capture runs nothing
+    graph_losses = [float(g(*b)) for b in batches]
+    # the graphed model took 2 extra steps on batch 0 first: compare a fresh eager model that did too
+    s_r, c_r, step_r = build()
+    for _ in range(2):
+        step_r(*batches[0])
+    ref_losses = [float(step_r(*b)) for b in batches]
+    for a, b in zip(graph_losses, ref_losses):
+        assert abs(a - b) <= 1e-4 * max(abs(b), 1e-3), (graph_losses, ref_losses)
+    for (n, p), (_, q) in zip(s_g.named_parameters(), s_r.named_parameters()):
+        assert rel_l2(p, q) < 1e-4, n                           # (split-K atomics: order varies)
+    for (k, u), (_, v) in zip(s_g.named_buffers(), s_r.named_buffers()):
+        assert (int(u) == int(v)) if u.dtype == torch.long else max_rel(u, v) < 1e-4, k
+    assert eager_losses[0] != graph_losses[0]                   # (different starting points, sanity)
