@@ -246,6 +246,40 @@ int b2n_sgd_multi(float* const* p, const float* const* g, float* const* momentum
                   const long long* numel, int n, double lr, double momentum, double weight_decay,
                   int nesterov, int first_step, double grad_scale, void* stream);
 
+/* ---- weak / strong augmentation on the GPU --------------------------------
+ * Batches are uint8 (N,3,H,W), planes contiguous -- the layout the trunk's uint8 input path takes.
+ * Per-image parameters are device arrays of N entries; `apply` (may be NULL = all) selects the
+ * images an operation touches, the others are copied through.  src == dst is allowed for the
+ * point-wise operations (not for blur / warp).  Replaces, one launch per batch instead of Python
+ * per image: TransformFix (dataset.py:663-677) and the RandAugment pool
+ * (models/randaugment.py:51-126), whose arithmetic lives in albumentations 0.1.8 / imgaug 0.4 /
+ * scikit-image 0.15 / OpenCV (requirements.txt:10,128,369,241). */
+/* RandomHorizontalFlip + RandomCrop: dst[n,c,y,x] = flipped(src[n])[c, top+y, left+x]. */
+int b2n_aug_flip_crop(const unsigned char* src, unsigned char* dst, const int* top, const int* left,
+                      const int* flip, int N, int Hs, int Ws, int H, int W, void* stream);
+/* albumentations brightness_contrast_adjust: uint8(clip(float32(x) * alpha[n] + offset[n], 0, 255)). */
+int b2n_aug_brightness_contrast(const unsigned char* src, unsigned char* dst, const float* alpha,
+                                const float* offset, const int* apply, int N, int H, int W,
+                                void* stream);
+/* mean[n] = mean over the image's 3*H*W bytes (the `beta * np.mean(img)` brightness reference). */
+int b2n_aug_image_mean(const unsigned char* src, float* mean, int N, int H, int W, void* stream);
+/* albumentations shift_hsv (HueSaturationValue): OpenCV 8-bit RGB->HSV, integer shifts, HSV->RGB. */
+int b2n_aug_hsv_shift(const unsigned char* src, unsigned char* dst, const int* dh, const int* ds,
+                      const int* dv, const int* apply, int N, int H, int W, void* stream);
+/* imgaug AdditiveGaussianNoise(per_channel=False): uint8(clip(round(x + noise[n,0,y,x]))). */
+int b2n_aug_add_noise(const unsigned char* src, unsigned char* dst, const float* noise, const int* apply,
+                      int N, int H, int W, void* stream);
+/* albumentations Blur = cv2.blur: ksize[n] x ksize[n] box filter (odd, <= 7), BORDER_REFLECT_101. */
+int b2n_aug_box_blur(const unsigned char* src, unsigned char* dst, const int* ksize, const int* apply,
+                     int N, int H, int W, void* stream);
+/* colour_augmentation (models/randaugment.py:17-48): rgb2hed, stain offsets delta[n][3], hed2rgb. */
+int b2n_aug_hed_jitter(const unsigned char* src, unsigned char* dst, const float* delta, const int* apply,
+                       int N, int H, int W, void* stream);
+/* cv2.warpAffine / cv2.resize with INTER_CUBIC: minv[n][6] maps output (x, y) to source (sx, sy);
+ * BORDER_REFLECT_101, or edge replication when clamp_border (resize).  (N,3,Hs,Ws) -> (N,3,H,W). */
+int b2n_aug_warp_affine(const unsigned char* src, unsigned char* dst, const float* minv, const int* apply,
+                        int N, int Hs, int Ws, int H, int W, int clamp_border, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

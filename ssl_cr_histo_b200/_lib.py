@@ -49,6 +49,14 @@ _SIGNATURES = {
     "b2n_lerp_multi": [P, P, P, I, F, I],
     "b2n_adam_multi": [P, P, P, P, P, I, D, D, D, D, D, LL, P, D],
     "b2n_sgd_multi": [P, P, P, P, I, D, D, D, I, I, D],
+    "b2n_aug_flip_crop": [P, P, P, P, P, I, I, I, I, I],
+    "b2n_aug_brightness_contrast": [P, P, P, P, P, I, I, I],
+    "b2n_aug_image_mean": [P, P, I, I, I],
+    "b2n_aug_hsv_shift": [P, P, P, P, P, P, I, I, I],
+    "b2n_aug_add_noise": [P, P, P, P, I, I, I],
+    "b2n_aug_box_blur": [P, P, P, P, I, I, I],
+    "b2n_aug_hed_jitter": [P, P, P, P, I, I, I],
+    "b2n_aug_warp_affine": [P, P, P, P, I, I, I, I, I, I],
 }
 EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok", "b2n_launch_count"] + list(_SIGNATURES)
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2n.so")
 SOURCES = ["api.cu", "errors.cu", "tmap.cu", "conv_launch.cu", "bn.cu", "stem_pool.cu", "pack.cu",
-           "linear.cu", "loss_lerp.cu", "optim.cu"]
+           "linear.cu", "loss_lerp.cu", "optim.cu", "augment.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo"]
 

@@ -238,4 +238,48 @@ int b2n_sgd_multi(float* const* p, const float* const* g, float* const* momentum
                  (n + 63) / 64);
 }
 
+// ---- GPU augmentation ----
+int b2n_aug_flip_crop(const unsigned char* src, unsigned char* dst, const int* top, const int* left,
+                      const int* flip, int N, int Hs, int Ws, int H, int W, void* stream) {
+  if (!src || !dst || !top || !left || !flip) return set_error("b2n_aug_flip_crop: null argument");
+  return counted(launch_aug_flip_crop(src, dst, top, left, flip, N, Hs, Ws, H, W, S(stream)));
+}
+int b2n_aug_brightness_contrast(const unsigned char* src, unsigned char* dst, const float* alpha,
+                                const float* offset, const int* apply, int N, int H, int W,
+                                void* stream) {
+  if (!src || !dst || !alpha || !offset) return set_error("b2n_aug_brightness_contrast: null argument");
+  return counted(launch_aug_brightness_contrast(src, dst, alpha, offset, apply, N, H, W, S(stream)));
+}
+int b2n_aug_image_mean(const unsigned char* src, float* mean, int N, int H, int W, void* stream) {
+  if (!src || !mean) return set_error("b2n_aug_image_mean: null argument");
+  return counted(launch_aug_image_mean(src, mean, N, H, W, S(stream)));
+}
+int b2n_aug_hsv_shift(const unsigned char* src, unsigned char* dst, const int* dh, const int* ds,
+                      const int* dv, const int* apply, int N, int H, int W, void* stream) {
+  if (!src || !dst || !dh || !ds || !dv) return set_error("b2n_aug_hsv_shift: null argument");
+  return counted(launch_aug_hsv_shift(src, dst, dh, ds, dv, apply, N, H, W, S(stream)));
+}
+int b2n_aug_add_noise(const unsigned char* src, unsigned char* dst, const float* noise, const int* apply,
+                      int N, int H, int W, void* stream) {
+  if (!src || !dst || !noise) return set_error("b2n_aug_add_noise: null argument");
+  return counted(launch_aug_add_noise(src, dst, noise, apply, N, H, W, S(stream)));
+}
+int b2n_aug_box_blur(const unsigned char* src, unsigned char* dst, const int* ksize, const int* apply,
+                     int N, int H, int W, void* stream) {
+  if (!src || !dst || !ksize) return set_error("b2n_aug_box_blur: null argument");
+  if (src == dst) return set_error("b2n_aug_box_blur: in-place operation is not supported");
+  return counted(launch_aug_box_blur(src, dst, ksize, apply, N, H, W, S(stream)));
+}
+int b2n_aug_hed_jitter(const unsigned char* src, unsigned char* dst, const float* delta, const int* apply,
+                       int N, int H, int W, void* stream) {
+  if (!src || !dst || !delta) return set_error("b2n_aug_hed_jitter: null argument");
+  return counted(launch_aug_hed_jitter(src, dst, delta, apply, N, H, W, S(stream)));
+}
+int b2n_aug_warp_affine(const unsigned char* src, unsigned char* dst, const float* minv, const int* apply,
+                        int N, int Hs, int Ws, int H, int W, int clamp_border, void* stream) {
+  if (!src || !dst || !minv) return set_error("b2n_aug_warp_affine: null argument");
+  if (src == dst) return set_error("b2n_aug_warp_affine: in-place operation is not supported");
+  return counted(launch_aug_warp_affine(src, dst, minv, apply, N, Hs, Ws, H, W, clamp_border, S(stream)));
+}
+
 }  // extern "C"

@@ -164,6 +164,24 @@ int launch_softmax_last(const float* logits, float* out, int rows, int C, cudaSt
 int launch_lerp_multi(float* const* dst, float* const* src, const long long* numel, int n,
                       float alpha, int write_back, cudaStream_t stream);
 
+// ---- GPU augmentation of uint8 (N,3,H,W) batches (augment.cu) ----
+int launch_aug_flip_crop(const unsigned char* src, unsigned char* dst, const int* top, const int* left,
+                         const int* flip, int N, int Hs, int Ws, int H, int W, cudaStream_t stream);
+int launch_aug_brightness_contrast(const unsigned char* src, unsigned char* dst, const float* alpha,
+                                   const float* offset, const int* apply, int N, int H, int W,
+                                   cudaStream_t stream);
+int launch_aug_image_mean(const unsigned char* src, float* mean, int N, int H, int W, cudaStream_t stream);
+int launch_aug_hsv_shift(const unsigned char* src, unsigned char* dst, const int* dh, const int* ds,
+                         const int* dv, const int* apply, int N, int H, int W, cudaStream_t stream);
+int launch_aug_add_noise(const unsigned char* src, unsigned char* dst, const float* noise, const int* apply,
+                         int N, int H, int W, cudaStream_t stream);
+int launch_aug_box_blur(const unsigned char* src, unsigned char* dst, const int* ksize, const int* apply,
+                        int N, int H, int W, cudaStream_t stream);
+int launch_aug_hed_jitter(const unsigned char* src, unsigned char* dst, const float* delta, const int* apply,
+                          int N, int H, int W, cudaStream_t stream);
+int launch_aug_warp_affine(const unsigned char* src, unsigned char* dst, const float* minv, const int* apply,
+                           int N, int Hs, int Ws, int H, int W, int clamp_border, cudaStream_t stream);
+
 int launch_adam_multi(float* const* p, const float* const* g, float* const* exp_avg,
                       float* const* exp_avg_sq, const long long* numel, int n, double lr, double beta1,
                       double beta2, double eps, double weight_decay, long long step,

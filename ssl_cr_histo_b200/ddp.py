@@ -153,6 +153,8 @@ class GradAllReducer:
                 for w in self._works:
                     w.wait()            # the current stream waits; the host does not block
                 self._works = []
+                if self._stream is not None:    # rejoin the side stream (required under graph capture)
+                    torch.cuda.current_stream(self.flat.device).wait_stream(self._stream)
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             if average:

@@ -650,6 +650,38 @@ def test_fused_optimizers_match_torch_optim(kind):
         assert torch.allclose(om.state[mine[0]]["exp_avg_sq"], orf.state[ref[0]]["exp_avg_sq"], rtol=2e-6)
 
 
+def test_capturable_adam_counts_steps_on_the_device_and_replays_from_a_graph():
+    """optim.Adam(capturable=True): the bias corrections come from a device-side step counter that
+    the launch itself advances -- three eager steps and three CUDA-graph replays of one captured
+    step() equal six torch.optim.Adam steps."""
+    from ssl_cr_histo_b200 import optim as fused
+    g = torch.Generator().manual_seed(13)
+    shapes = [(64, 3, 7, 7), (64,), (33, 5)] + [(7 + i,) for i in range(70)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    mine = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    ref = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    om = fused.Adam(mine, lr=1e-2, weight_decay=1e-4, capturable=True)
+    orf = torch.optim.Adam(ref, lr=1e-2, weight_decay=1e-4)
+    grads = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    for a, b, gr in zip(mine, ref, grads):
+        a.grad, b.grad = gr.clone(), gr.clone()                # static gradient buffers
+    for _ in range(3):
+        om.step(); orf.step()
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), i
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        om.step()
+    for k in range(3):
+        for a, b in zip(mine, ref):                            # new gradient values, same buffers
+            a.grad.mul_(0.5 + k); b.grad.mul_(0.5 + k)
+        graph.replay(); orf.step()
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        assert torch.allclose(a, b, rtol=4e-6, atol=2e-7), (i, float((a - b).abs().max()))
+
+
 def test_fused_optimizer_invalidates_packed_weights():
     """A step writes parameters behind autograd's version counters: the trunk must re-pack."""
     import ssl_cr_histo_b200.net as net
