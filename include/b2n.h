@@ -130,7 +130,8 @@ int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, vo
  * (momentum, unbiased variance).  running_* may be null (no update). */
 int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float* scale, float* shift, float* mean, float* invstd,
-                    int C, double count, float momentum, float eps, int n_updates, void* stream);
+                    float* inv_gamma /* optional: 1/gamma (0 where gamma == 0) */, int C, double count,
+                    float momentum, float eps, int n_updates, void* stream);
 /* eval mode: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean*scale */
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                      const float* running_var, float* scale, float* shift, int C, float eps,
@@ -201,6 +202,13 @@ int b2n_linear_bwd_data(const float* dy, long long lddy, const float* w, long lo
 int b2n_linear_bwd_weight(const float* dy, long long lddy, const float* x, long long ldx, float* dw,
                           long long lddw, float* db /* may be null */, int rows, int in_f,
                           int out_f, int accumulate, void* stream);
+
+/* y[r][k*width + c] = y[r][c] for k = 1..copies-1, and out[r][c] = sum_k dy[r][k*width + c]: the
+ * pair features cat(f, f, f) of TripletNet_Finetune.forward (models/net.py:92-103) and their
+ * gradient, when the three trunk passes saw the same input (one evaluation of the pair MLP). */
+int b2n_cols_replicate(float* y, long long ld, int rows, int width, int copies, void* stream);
+int b2n_cols_sum(const float* dy, long long ld, float* out, int rows, int width, int copies,
+                 void* stream);
 
 /* ---- fused losses ------------------------------------------------------------------------
  * mode 0: mean softmax-CE of logits_x vs targets_i + argmax (pretrain_BreastPathQ.py:56,66)

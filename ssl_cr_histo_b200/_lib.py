@@ -29,7 +29,7 @@ _SIGNATURES = {
     "b2n_stem_pack_input_u8": [P, P, P, I, I, I],
     "b2n_stem_pack_weight": [P, P, P, I],
     "b2n_stem_unpack_wgrad": [P, P, I, I],
-    "b2n_bn_finalize": [P] * 9 + [I, D, F, F, I],
+    "b2n_bn_finalize": [P] * 10 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
     "b2n_bn_apply": [P] * 11 + [LL, I, I, I],
     "b2n_bn_bwd_reduce": [P] * 8 + [LL, I],
@@ -44,6 +44,8 @@ _SIGNATURES = {
     "b2n_linear_fwd": [P, LL, P, LL, P, P, LL, I, I, I, I, I],
     "b2n_linear_bwd_data": [P, LL, P, LL, P, LL, P, I, I, I, I],
     "b2n_linear_bwd_weight": [P, LL, P, LL, P, LL, P, I, I, I, I],
+    "b2n_cols_replicate": [P, LL, I, I, I],
+    "b2n_cols_sum": [P, LL, P, I, I, I],
     "b2n_fused_loss": [I, P, P, P, P, P, I, I, I, F, P, P, P, P, P],
     "b2n_softmax_last": [P, P, I, I],
     "b2n_lerp_multi": [P, P, P, I, F, I],

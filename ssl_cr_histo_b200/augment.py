@@ -11,7 +11,7 @@ Rotate_Crop) at magnitude ``val = v/30 * (max - min) + min``, ``v = randint(1, m
 only *draws the parameters* (same distributions, per image) and every operation runs as one kernel
 launch over the whole uint8 (N,3,H,W) batch; the result feeds the trunk's uint8 input path
 directly.  The low-level functions take explicit per-image parameters, which is what the parity
-tests drive against oracle/ref_augment.py.
+tests drive against the CPU restatement of the same operations.
 
 There is no CPU fallback: tensors must live on a CUDA (sm_100a) device.
 """

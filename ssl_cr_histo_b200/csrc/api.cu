@@ -105,9 +105,10 @@ int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, vo
 
 int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float* scale, float* shift, float* mean, float* invstd,
-                    int C, double count, float momentum, float eps, int n_updates, void* stream) {
+                    float* inv_gamma, int C, double count, float momentum, float eps, int n_updates,
+                    void* stream) {
   return counted(launch_bn_finalize(stats, gamma, beta, running_mean, running_var, scale, shift, mean,
-                            invstd, C, count, momentum, eps, n_updates, S(stream)));
+                            invstd, inv_gamma, C, count, momentum, eps, n_updates, S(stream)));
 }
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                      float* scale, float* shift, int C, float eps, void* stream) {
@@ -196,6 +197,14 @@ int b2n_linear_bwd_weight(const float* dy, long long lddy, const float* x, long 
   if (rc == 0 && db != nullptr)
     rc = counted(launch_colsum(dy, lddy, db, rows, out_f, accumulate, S(stream)));
   return rc;
+}
+
+int b2n_cols_replicate(float* y, long long ld, int rows, int width, int copies, void* stream) {
+  return counted(launch_cols_replicate(y, ld, rows, width, copies, S(stream)));
+}
+int b2n_cols_sum(const float* dy, long long ld, float* out, int rows, int width, int copies,
+                 void* stream) {
+  return counted(launch_cols_sum(dy, ld, out, rows, width, copies, S(stream)));
 }
 
 int b2n_fused_loss(int mode, const float* logits_x, const long long* targets_i,

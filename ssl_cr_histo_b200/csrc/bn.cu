@@ -17,8 +17,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out, int C, double count,
-                                   float momentum, float eps, int n_updates) {
+                                   float* __restrict__ invstd_out, float* __restrict__ inv_gamma,
+                                   int C, double count, float momentum, float eps, int n_updates) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = stats[c] / count;
@@ -30,6 +30,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
   shift[c] = beta[c] - static_cast<float>(mean) * sc;
   mean_out[c] = static_cast<float>(mean);
   invstd_out[c] = invstd;
+  // 1 / gamma: lets a consumer that only sees the activation a = gamma * xhat + beta recover xhat
+  // (the stem's BatchNorm-backward sums are taken over the max-pooled activation)
+  if (inv_gamma != nullptr) inv_gamma[c] = gamma[c] != 0.f ? 1.f / gamma[c] : 0.f;
   if (running_mean != nullptr && n_updates > 0) {
     // n_updates identical updates r <- (1-m) r + m b collapse to one closed-form update;
     // n_updates = 3 reproduces TripletNet_Finetune.forward's three passes (models/net.py:88-90).
@@ -154,11 +157,11 @@ int launch_bn_apply(const float* y, const float* scale, const float* shift, cons
 
 int launch_bn_finalize(const double* stats, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float* scale, float* shift,
-                       float* mean, float* invstd, int C, double count, float momentum, float eps,
-                       int n_updates, cudaStream_t stream) {
+                       float* mean, float* invstd, float* inv_gamma, int C, double count,
+                       float momentum, float eps, int n_updates, cudaStream_t stream) {
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, gamma, beta, running_mean,
-                                                         running_var, scale, shift, mean, invstd, C,
-                                                         count, momentum, eps, n_updates);
+                                                         running_var, scale, shift, mean, invstd,
+                                                         inv_gamma, C, count, momentum, eps, n_updates);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_finalize: %s", cudaGetErrorString(e));
   return 0;

@@ -655,6 +655,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         tc_fence_after();
         process(0, pr0, pm0, px0);
         process(1, pr1, pm1, px1);
+      } else if constexpr (EPI >= 0) {
+        // wide tiles with a compiled-in epilogue: the operands of chunk 0 are fetched before the
+        // accumulator wait and those of chunk ch + 1 while chunk ch is processed
+        float4 pr[2][8], pm[2][8];
+        uint4 px[2][8];
+        prefetch(0, pr[0], pm[0], px[0]);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          if (ch + 1 < BLOCK_N / 32) prefetch(ch + 1, pr[(ch + 1) & 1], pm[(ch + 1) & 1], px[(ch + 1) & 1]);
+          process(ch, pr[ch & 1], pm[ch & 1], px[ch & 1]);
+        }
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();

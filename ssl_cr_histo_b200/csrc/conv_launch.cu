@@ -198,6 +198,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr int kDgradRes = kEpiOut32 | kEpiResid32;                     // + (pre-gated) shortcut gradient
   constexpr int kDgradResGate = kDgradRes | kEpiGate;                    // ... then the input's ReLU gate
   constexpr int kDgradBn = kEpiOut32 | kEpiBnBwd | kEpiBnGate;           // bn1's gate + backward sums
+  constexpr int kDgradResGateBn = kDgradResGate | kEpiBnBwd;             // first block: + the stem BN's sums
   if (halo == 128 && split) {
     if (epi == kTrainFwd) return launch_variant<64, 128, 2, true, true, true, kTrainFwd>(m, p, grid, stream);
     if (epi == kEvalAct) return launch_variant<64, 128, 2, true, true, true, kEvalAct>(m, p, grid, stream);
@@ -209,6 +210,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     if (epi == kDgradRes) return launch_variant<64, 128, 4, false, true, true, kDgradRes>(m, p, grid, stream);
     if (epi == kDgradResGate) return launch_variant<64, 128, 4, false, true, true, kDgradResGate>(m, p, grid, stream);
     if (epi == kDgradBn) return launch_variant<64, 128, 4, false, true, true, kDgradBn>(m, p, grid, stream);
+    if (epi == kDgradResGateBn) return launch_variant<64, 128, 4, false, true, true, kDgradResGateBn>(m, p, grid, stream);
     return launch_variant<64, 128, 4, false, true, true>(m, p, grid, stream);
   }
   if (halo == 32 && split) {  // the stem: epilogue-paced, 8 epilogue warps
@@ -235,6 +237,11 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     if (block_n == 64) return launch_variant<64, 64, 8, true, false>(m, p, grid, stream);
   } else {
     if (block_n == 64) return launch_variant<64, 128, 6, false, false>(m, p, grid, stream);
+    // layers 2-4: conv2's data gradient with bn1's gate + BatchNorm-backward sums compiled in
+    if (block_n == 128 && epi == kDgradBn)
+      return launch_variant<128, 128, 5, false, false, false, kDgradBn>(m, p, grid, stream);
+    if (block_n == 256 && epi == kDgradBn)
+      return launch_variant<256, 128, 4, false, false, false, kDgradBn>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 5, false, false>(m, p, grid, stream);
     if (block_n == 256) return launch_variant<256, 128, 4, false, false>(m, p, grid, stream);
   }

@@ -92,8 +92,8 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream);
 // ---- element-wise / small kernels (bn.cu, stem_pool.cu, pack.cu, linear.cu, loss_lerp.cu) ----
 int launch_bn_finalize(const double* stats, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float* scale, float* shift,
-                       float* mean, float* invstd, int C, double count, float momentum, float eps,
-                       int n_updates, cudaStream_t stream);
+                       float* mean, float* invstd, float* inv_gamma, int C, double count,
+                       float momentum, float eps, int n_updates, cudaStream_t stream);
 int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                         float* scale, float* shift, int C, float eps, cudaStream_t stream);
 int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
@@ -153,6 +153,9 @@ int launch_linear_bwd_data(const float* dy, long long lddy, const float* w, long
 int launch_linear_bwd_weight(const float* dy, long long lddy, const float* x, long long ldx,
                              float* dw, long long lddw, int rows, int in_f, int out_f,
                              int accumulate, cudaStream_t stream);
+int launch_cols_replicate(float* y, long long ld, int rows, int width, int copies, cudaStream_t stream);
+int launch_cols_sum(const float* dy, long long ld, float* out, int rows, int width, int copies,
+                    cudaStream_t stream);
 int launch_colsum(const float* dy, long long lddy, float* db, int rows, int out_f, int accumulate,
                   cudaStream_t stream);
 int launch_fused_loss(int mode, const float* logits_x, const long long* targets_i,

@@ -125,6 +125,53 @@ int launch_linear_bwd_weight(const float* dy, long long lddy, const float* x, lo
   return run_gemm(g, stream, "linear_bwd_weight");
 }
 
+// Column-block helpers of the pair head when its three pair rows are identical
+// (TripletNet_Finetune, models/net.py:92-103): the (rows, copies*width) feature matrix holds `copies`
+// equal blocks side by side -- filled from block 0 -- and its gradient is the sum of the blocks.
+__global__ void cols_replicate_kernel(float* __restrict__ y, long long ld, int rows, int width,
+                                      int copies) {
+  const long long total = static_cast<long long>(rows) * width;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = t / width;
+    const int c = static_cast<int>(t - r * width);
+    const float v = y[r * ld + c];
+    for (int k = 1; k < copies; ++k) y[r * ld + k * width + c] = v;
+  }
+}
+__global__ void cols_sum_kernel(const float* __restrict__ dy, long long ld, float* __restrict__ out,
+                                int rows, int width, int copies) {
+  const long long total = static_cast<long long>(rows) * width;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = t / width;
+    const int c = static_cast<int>(t - r * width);
+    float v = dy[r * ld + c];
+    for (int k = 1; k < copies; ++k) v += dy[r * ld + k * width + c];   // left to right, like autograd
+    out[t] = v;
+  }
+}
+static unsigned cols_grid(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > 1184) b = 1184;
+  return static_cast<unsigned>(b < 1 ? 1 : b);
+}
+int launch_cols_replicate(float* y, long long ld, int rows, int width, int copies, cudaStream_t stream) {
+  if (rows <= 0 || width <= 0 || copies < 1) return rows == 0 ? 0 : set_error("cols_replicate: bad shape");
+  cols_replicate_kernel<<<cols_grid(1ll * rows * width), 256, 0, stream>>>(y, ld, rows, width, copies);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("cols_replicate: %s", cudaGetErrorString(e));
+  return 0;
+}
+int launch_cols_sum(const float* dy, long long ld, float* out, int rows, int width, int copies,
+                    cudaStream_t stream) {
+  if (rows <= 0 || width <= 0 || copies < 1) return rows == 0 ? 0 : set_error("cols_sum: bad shape");
+  cols_sum_kernel<<<cols_grid(1ll * rows * width), 256, 0, stream>>>(dy, ld, out, rows, width, copies);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("cols_sum: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // db[o] (+)= sum_n dy[n][o]
 __global__ void colsum_kernel(const float* __restrict__ dy, long long lddy, float* __restrict__ db,
                               int rows, int out_f, int accumulate) {

@@ -158,8 +158,8 @@ class _PairMLPSameFn(torch.autograd.Function):
         y = torch.empty(n, 3 * odim, device=dev, dtype=torch.float32)
         _fwd(e, d, w1, 2 * d, None, h, hdim, n, d, hdim, 0, 0)
         _fwd(e, d, w1[:, d:], 2 * d, b1, h, hdim, n, d, hdim, 1, 1)
-        for k in range(3):
-            _fwd(h, hdim, w2, hdim, b2, y[:, k * odim:], 3 * odim, n, hdim, odim, 0, 0)
+        _fwd(h, hdim, w2, hdim, b2, y, 3 * odim, n, hdim, odim, 0, 0)          # block 0 ...
+        call("b2n_cols_replicate", y, 3 * odim, n, odim, 3)                     # ... = blocks 1, 2
         ctx.save_for_backward(e, w1, w2, h)
         ctx.params = (w1p, b1p, w2p, b2p)
         return y
@@ -177,12 +177,11 @@ class _PairMLPSameFn(torch.autograd.Function):
         dw2, db2, a2 = pg.pair(w2p, b2p, nw2 or nb2)
         dw1, db1, a1 = pg.pair(w1p, b1p, nw1 or nb1)
         dh = torch.empty(n, hdim, device=dev, dtype=torch.float32)
-        for k in range(3):
-            dyk = dy[:, k * odim:]
-            if dw2 is not None:
-                _bwd_weight(dyk, 3 * odim, h, hdim, dw2, hdim, db2, n, hdim, odim, int(a2 or k > 0))
-            # dh = [h > 0] * sum_k dy_k W2  (accumulate adds the previous content before the mask)
-            _bwd_data(dyk, 3 * odim, w2, hdim, dh, hdim, h, n, hdim, odim, 1 if k > 0 else 0)
+        df = torch.empty(n, odim, device=dev, dtype=torch.float32)
+        call("b2n_cols_sum", dy, 3 * odim, df, n, odim, 3)     # the three pair rows share f
+        if dw2 is not None:
+            _bwd_weight(df, odim, h, hdim, dw2, hdim, db2, n, hdim, odim, a2)
+        _bwd_data(df, odim, w2, hdim, dh, hdim, h, n, hdim, odim, 0)
         if dw1 is not None:
             # each of the three pair rows contributes dh_k^T E to both column halves and
             # colsum(dh_k) to the bias; the rows are identical, so dh already holds the sum

