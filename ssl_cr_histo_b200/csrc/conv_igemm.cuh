@@ -663,10 +663,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         prefetch(0, pr[0], pm[0], px[0]);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-          if (ch + 1 < BLOCK_N / 32) prefetch(ch + 1, pr[(ch + 1) & 1], pm[(ch + 1) & 1], px[(ch + 1) & 1]);
-          process(ch, pr[ch & 1], pm[ch & 1], px[ch & 1]);
+        // (two chunks per iteration so that the buffer index stays a compile-time constant
+        // without unrolling all eight chunks of a 256-wide tile)
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ch += 2) {
+          prefetch(ch + 1, pr[1], pm[1], px[1]);
+          process(ch, pr[0], pm[0], px[0]);
+          if (ch + 2 < BLOCK_N / 32) prefetch(ch + 2, pr[0], pm[0], px[0]);
+          process(ch + 1, pr[1], pm[1], px[1]);
         }
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);

@@ -231,6 +231,12 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   }
   if (split && kbytes == 128) {
     if (block_n == 64) return launch_variant<64, 128, 4, true, false>(m, p, grid, stream);
+    // layers 2-4, eval mode: folded BN + ReLU (+ identity shortcut) -> FP16 pair with the epilogue
+    // compiled in (the shortcut operands of chunk ch + 1 are fetched while chunk ch is processed)
+    if (block_n == 128 && epi == kEvalAct) return launch_variant<128, 128, 3, true, false, false, kEvalAct>(m, p, grid, stream);
+    if (block_n == 128 && epi == kEvalActRes) return launch_variant<128, 128, 3, true, false, false, kEvalActRes>(m, p, grid, stream);
+    if (block_n == 256 && epi == kEvalAct) return launch_variant<256, 128, 2, true, false, false, kEvalAct>(m, p, grid, stream);
+    if (block_n == 256 && epi == kEvalActRes) return launch_variant<256, 128, 2, true, false, false, kEvalActRes>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 3, true, false>(m, p, grid, stream);
     if (block_n == 256) return launch_variant<256, 128, 2, true, false>(m, p, grid, stream);
   } else if (split) {
