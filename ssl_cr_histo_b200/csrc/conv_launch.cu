@@ -193,6 +193,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr int kTrainFwd = kEpiStats | kEpiOut32;                       // raw y + BN statistics
   constexpr int kEvalAct = kEpiAffine | kEpiRelu | kEpiOut16;            // folded BN + ReLU -> pair
   constexpr int kEvalActRes = kEvalAct | kEpiResid16;                    // ... + identity shortcut
+  constexpr int kEvalActRes32 = kEvalAct | kEpiResid32;                  // ... + fp32 shortcut (downsample branch)
   constexpr int kEvalStem = kEpiAffine | kEpiRelu | kEpiOut32;
   constexpr int kDgrad = kEpiOut32;
   constexpr int kDgradRes = kEpiOut32 | kEpiResid32;                     // + (pre-gated) shortcut gradient
@@ -237,6 +238,10 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     if (block_n == 128 && epi == kEvalActRes) return launch_variant<128, 128, 3, true, false, false, kEvalActRes>(m, p, grid, stream);
     if (block_n == 256 && epi == kEvalAct) return launch_variant<256, 128, 2, true, false, false, kEvalAct>(m, p, grid, stream);
     if (block_n == 256 && epi == kEvalActRes) return launch_variant<256, 128, 2, true, false, false, kEvalActRes>(m, p, grid, stream);
+    if (block_n == 128 && epi == kTrainFwd) return launch_variant<128, 128, 3, true, false, false, kTrainFwd>(m, p, grid, stream);
+    if (block_n == 256 && epi == kTrainFwd) return launch_variant<256, 128, 2, true, false, false, kTrainFwd>(m, p, grid, stream);
+    if (block_n == 128 && epi == kEvalActRes32) return launch_variant<128, 128, 3, true, false, false, kEvalActRes32>(m, p, grid, stream);
+    if (block_n == 256 && epi == kEvalActRes32) return launch_variant<256, 128, 2, true, false, false, kEvalActRes32>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 3, true, false>(m, p, grid, stream);
     if (block_n == 256) return launch_variant<256, 128, 2, true, false>(m, p, grid, stream);
   } else if (split) {
