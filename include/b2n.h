@@ -88,10 +88,17 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
  * dw_packed must be zeroed by the caller.  Cin a multiple of 32, Cout a multiple of 64.  Stride-1
  * same-width convs with Cout = 64 and R*Cin/32 <= 6 (layer1, the stem) run the tap-sharing kernel
  * in which one CTA owns all of dW for a slab of pixels.  Replaces cudnnConvolutionBackwardFilter reached from
- * loss.backward() (pretrain_BreastPathQ.py:60). */
+ * loss.backward() (pretrain_BreastPathQ.py:60).
+ * deterministic != 0: no atomics -- every split-K CTA group stores its own partial plane, so
+ * dw_packed must hold b2n_conv_wgrad_planes(...) planes of [Cout][R*S*Cin] floats (no zero-fill
+ * needed) and b2n_unpack_wgrad sums them in a fixed order: bit-repeatable gradients. */
 int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
                    int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                   int pad_w_hi, void* stream);
+                   int pad_w_hi, int deterministic, void* stream);
+/* Planes a deterministic b2n_conv_wgrad of this shape writes on the current device (>= 1; < 0 on
+ * error).  Host-side only, no launch. */
+int b2n_conv_wgrad_planes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                          int pad_h_lo, int pad_h_hi, int pad_w_lo, int pad_w_hi);
 
 /* (K,C,R,S) parameter -> forward pack [K][(r*S+s)*C + c] as a (hi, lo) FP16 pair, data-gradient
  * pack [C][((R-1-r)*S+(S-1-s))*K + k] (TF32-rounded fp32); packed weight gradient -> (K,C,R,S). */
@@ -105,7 +112,7 @@ int b2n_pack_weight_dgrad_s2(const float* w, float* w_packed, int K, int C, void
 /* accumulate != 0: dw += (several passes over shared weights feed one gradient slot, e.g. the
  * three trunk passes of TripletNet.forward or a flat all-reduce arena). */
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, int accumulate,
-                     void* stream);
+                     int planes /* partial planes to sum, 1 = plain */, void* stream);
 
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
 /* x NCHW fp32 (N,3,H,W), H and W even -> NHWC space-to-depth views (12 real channels): the
@@ -122,7 +129,8 @@ int b2n_stem_pack_input_u8(const unsigned char* x_nchw, b2n_half* xs_h, float* x
 /* w (K,3,7,7) -> (hi, lo) FP16 pair [K][16 taps * 16];  packed gradient [K][16 taps * 32] ->
  * (K,3,7,7). */
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream);
-int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, void* stream);
+int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, int planes,
+                          void* stream);
 
 /* ---- BatchNorm / ReLU / residual (tv:93-103,269-270; nn.BatchNorm2d train + eval) -------- */
 /* Batch statistics -> per-channel affine (scale = gamma*invstd, shift = beta - mean*scale),

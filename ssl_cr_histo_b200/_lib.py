@@ -20,15 +20,15 @@ P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 # name -> argument ctypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
     "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P, P] + [I] * 5 + [P] * 6,
-    "b2n_conv_wgrad": [P, P, P] + [I] * 12,
+    "b2n_conv_wgrad": [P, P, P] + [I] * 13,
     "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
     "b2n_pack_weight_dgrad_s2": [P, P, I, I],
-    "b2n_unpack_wgrad": [P, P, I, I, I, I, I],
+    "b2n_unpack_wgrad": [P, P, I, I, I, I, I, I],
     "b2n_stem_pack_input": [P, P, P, P, P, I, I, I],
     "b2n_stem_pack_input_u8": [P, P, P, I, I, I],
     "b2n_stem_pack_weight": [P, P, P, I],
-    "b2n_stem_unpack_wgrad": [P, P, I, I],
+    "b2n_stem_unpack_wgrad": [P, P, I, I, I],
     "b2n_bn_finalize": [P] * 10 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
     "b2n_bn_apply": [P] * 11 + [LL, I, I, I],
@@ -60,7 +60,8 @@ _SIGNATURES = {
     "b2n_aug_hed_jitter": [P, P, P, P, I, I, I],
     "b2n_aug_warp_affine": [P, P, P, P, I, I, I, I, I, I],
 }
-EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok", "b2n_launch_count"] + list(_SIGNATURES)
+EXPORTS = ["b2n_version", "b2n_last_error", "b2n_device_ok", "b2n_launch_count",
+           "b2n_conv_wgrad_planes"] + list(_SIGNATURES)
 
 _lib = None
 # bumped whenever a kernel writes parameters behind autograd's back (lerp), so that cached
@@ -83,6 +84,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.b2n_last_error.restype = c_char_p
     lib.b2n_device_ok.restype = c_int
     lib.b2n_launch_count.restype = ctypes.c_ulonglong
+    lib.b2n_conv_wgrad_planes.restype = c_int
+    lib.b2n_conv_wgrad_planes.argtypes = [c_int] * 12
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = list(sig) + [c_void_p]
@@ -137,6 +140,15 @@ def _call(name: str, args, work) -> None:
     if prof is not None:
         e1.record()
         prof.append((e0, e1, work))
+
+
+def wgrad_planes(*shape) -> int:
+    """Partial planes a deterministic b2n_conv_wgrad of this shape writes (host-side query)."""
+    lib = load()
+    n = lib.b2n_conv_wgrad_planes(*[int(v) for v in shape])
+    if n < 1:
+        raise RuntimeError("b2n_conv_wgrad_planes failed: %s" % lib.b2n_last_error().decode())
+    return n
 
 
 def launch_count() -> int:

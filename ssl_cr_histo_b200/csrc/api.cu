@@ -63,13 +63,22 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
 
 int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
                    int Cout, int R, int Sf, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                   int pad_w_hi, void* stream) {
+                   int pad_w_hi, int deterministic, void* stream) {
   if (!x || !dy || !dw_packed) return set_error("b2n_conv_wgrad: null tensor");
   WgradArgs a;
+  a.deterministic = deterministic;
   a.x = x; a.dy = dy; a.dw = dw_packed;
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.R = R; a.S = Sf; a.stride = stride;
   a.pad_h_lo = pad_h_lo; a.pad_h_hi = pad_h_hi; a.pad_w_lo = pad_w_lo; a.pad_w_hi = pad_w_hi;
   return counted(launch_wgrad(a, S(stream)));
+}
+
+int b2n_conv_wgrad_planes(int N, int H, int W, int Cin, int Cout, int R, int Sf, int stride,
+                          int pad_h_lo, int pad_h_hi, int pad_w_lo, int pad_w_hi) {
+  WgradArgs a;
+  a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.R = R; a.S = Sf; a.stride = stride;
+  a.pad_h_lo = pad_h_lo; a.pad_h_hi = pad_h_hi; a.pad_w_lo = pad_w_lo; a.pad_w_hi = pad_w_hi;
+  return wgrad_planes(a);
 }
 
 int b2n_pack_weight_fwd(const float* w, b2n_half* wp_h, b2n_half* wp_l, int K, int C, int R, int Sf,
@@ -83,8 +92,8 @@ int b2n_pack_weight_dgrad_s2(const float* w, float* wp, int K, int C, void* stre
   return counted(launch_pack_dgrad_s2(w, wp, K, C, S(stream)));
 }
 int b2n_unpack_wgrad(const float* dwp, float* dw, int K, int C, int R, int Sf, int accumulate,
-                     void* stream) {
-  return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, accumulate, S(stream)));
+                     int planes, void* stream) {
+  return counted(launch_unpack_wgrad(dwp, dw, K, C, R, Sf, accumulate, planes, S(stream)));
 }
 
 int b2n_stem_pack_input(const float* x, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
@@ -99,8 +108,9 @@ int b2n_stem_pack_input_u8(const unsigned char* x, b2n_half* xs_h, float* xs32, 
 int b2n_stem_pack_weight(const float* w, b2n_half* ws_h, b2n_half* ws_l, int K, void* stream) {
   return counted(launch_stem_pack_weight(w, H16(ws_h), H16(ws_l), K, S(stream)));
 }
-int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, void* stream) {
-  return counted(launch_stem_unpack_wgrad(dws, dw, K, accumulate, S(stream)));
+int b2n_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, int planes,
+                          void* stream) {
+  return counted(launch_stem_unpack_wgrad(dws, dw, K, accumulate, planes, S(stream)));
 }
 
 int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean,

@@ -311,8 +311,37 @@ static int launch_wgrad_halo_variant(const CUtensorMap& mx, const CUtensorMap& m
 
 // Tap-sharing variant (conv_wgrad_halo.cuh): stride-1 same-width convs with 64 output channels
 // whose R * Cin/32 accumulators fit TMEM -- layer1's 3x3 convs (6) and the 4x4 s2d stem (4).
+static bool wgrad_is_halo(const WgradArgs& a) {
+  return a.stride == 1 && a.Cout == 64 && a.S >= 2 && a.S <= 4 && a.pad_w_lo + a.pad_w_hi == a.S - 1 &&
+         a.R * (a.Cin / 32) <= 6 && !a.no_halo && getenv("B2N_NO_HALO") == nullptr;
+}
+static int wgrad_halo_grid(const WgradArgs& a, int P, int Q) {
+  const long long positions = 1ll * a.N * P * (Q + a.S - 1);
+  const long long slabs = (positions + kWhPX - 1) / kWhPX;
+  long long grid = a.force_splits > 0 ? a.force_splits : device_sm_count();
+  return (int)(grid > slabs ? slabs : grid);
+}
+static int wgrad_generic_splits(const WgradArgs& a, long long M) {
+  const int block_n = a.Cout % 256 == 0 ? 256 : (a.Cout % 128 == 0 ? 128 : 64);
+  const int px = block_n == 256 ? 32 : 64;
+  const long long slabs = (M + px - 1) / px;
+  const int out_tiles = ((a.R * a.S * a.Cin + 127) / 128) * (a.Cout / block_n);
+  long long splits = a.force_splits > 0 ? a.force_splits : device_sm_count() / out_tiles;
+  if (splits < 1) splits = 1;
+  return (int)(splits > slabs ? slabs : splits);
+}
+
+int wgrad_planes(const WgradArgs& a) {
+  if (a.Cin % 32 != 0 || a.Cout % 64 != 0) { set_error("wgrad: unsupported channel counts"); return -1; }
+  const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
+  const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
+  if (P <= 0 || Q <= 0 || a.N <= 0) { set_error("wgrad: empty problem"); return -1; }
+  return wgrad_is_halo(a) ? wgrad_halo_grid(a, P, Q) : wgrad_generic_splits(a, 1ll * a.N * P * Q);
+}
+
 static int launch_wgrad_halo(const WgradArgs& a, int P, int Q, cudaStream_t stream) {
   WgradHaloParams p;
+  p.deterministic = a.deterministic;
   p.P = P; p.Q = Q; p.Cin = a.Cin; p.R = a.R; p.S = a.S;
   p.pad_h = a.pad_h_lo; p.pad_w = a.pad_w_lo;
   p.Ktot = a.R * a.S * a.Cin;
@@ -330,8 +359,7 @@ static int launch_wgrad_halo(const WgradArgs& a, int P, int Q, cudaStream_t stre
   if (make_im2col_map(&mdy, a.dy, kF32, a.N, P, Q, a.Cout, 1, 1, 0, 0, 0, a.S - 1, 1, 32, kWhPX,
                       kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
-  int grid = a.force_splits > 0 ? a.force_splits : device_sm_count();
-  if (grid > p.slabs_total) grid = p.slabs_total;
+  const int grid = wgrad_halo_grid(a, P, Q);
   if (p.nacc <= 4) return launch_wgrad_halo_variant<4, 4>(mx, mdy, p, grid, stream);
   return launch_wgrad_halo_variant<6, 3>(mx, mdy, p, grid, stream);
 }
@@ -344,9 +372,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   if (P <= 0 || Q <= 0 || a.N <= 0) return set_error("wgrad: empty problem");
   const long long M = 1ll * a.N * P * Q;
   if (M > 2000000000ll) return set_error("wgrad: too many pixels");
-  if (a.stride == 1 && a.Cout == 64 && a.S >= 2 && a.S <= 4 && a.pad_w_lo + a.pad_w_hi == a.S - 1 &&
-      a.R * (a.Cin / 32) <= 6 && !a.no_halo && getenv("B2N_NO_HALO") == nullptr)
-    return launch_wgrad_halo(a, P, Q, stream);
+  if (wgrad_is_halo(a)) return launch_wgrad_halo(a, P, Q, stream);
   const int block_n = a.Cout % 256 == 0 ? 256 : (a.Cout % 128 == 0 ? 128 : 64);
 
   WgradParams p;
@@ -359,11 +385,10 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   const int px = block_n == 256 ? 32 : 64;  // pixels per stage (bigger boxes amortise TMA issue)
   p.slabs_total = (int)((M + px - 1) / px);
   const int out_tiles = p.num_m_tiles * p.num_n_tiles;
-  int splits = a.force_splits > 0 ? a.force_splits : device_sm_count() / out_tiles;
-  if (splits < 1) splits = 1;
-  if (splits > p.slabs_total) splits = p.slabs_total;
+  const int splits = wgrad_generic_splits(a, M);
   p.splits = splits;
   p.dw = a.dw;
+  p.deterministic = a.deterministic;
 
   CUtensorMap mx, mdy;
   if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,

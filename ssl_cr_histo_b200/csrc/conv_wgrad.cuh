@@ -10,7 +10,8 @@
 //   * A rows: im2col-mode TMA boxes of (32 channels x PX pixels), one per 32-channel group;
 //   * B cols: tiled-mode TMA boxes of (32 dY channels x PX pixels).
 // Split-K over pixel slabs across CTAs; partial tiles are accumulated into dW with coalesced
-// fp32 reductions (dW must be zeroed by the caller).  Replaces cudnnConvolutionBackwardFilter
+// fp32 reductions (dW must be zeroed by the caller) -- or, in deterministic mode, stored as one
+// plane per split and summed in a fixed order by the unpack kernel (bit-repeatable gradients).  Replaces cudnnConvolutionBackwardFilter
 // reached from loss.backward() (pretrain_BreastPathQ.py:60).
 #pragma once
 #include "ptx.cuh"
@@ -26,7 +27,9 @@ struct WgradParams {
   int num_n_tiles;  // Cout / BLOCK_N
   int splits;
   int slabs_total;  // ceil(M_total / PX)
-  float* dw;        // [Cout][Ktot]
+  float* dw;        // [Cout][Ktot]; deterministic mode: [splits][Cout][Ktot] partial planes
+  int deterministic;  // 0: fp32 reductions into one zeroed plane; 1: every split stores its own
+                      // plane (no atomics; b2n_unpack_wgrad sums the planes in a fixed order)
 };
 
 constexpr int kWgradThreads = 192;
@@ -182,10 +185,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x,
         tmem_ld_wait();
         if (row_ok) {
           float* dst = p.dw + static_cast<size_t>(n_tile * BLOCK_N + ch * 32) * p.Ktot + grow;
+          if (p.deterministic) {
+            dst += static_cast<size_t>(split) * p.Cout * p.Ktot;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, v[i]);
+            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(i) * p.Ktot] = v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, v[i]);
+          }
         }
       }
+    }
+  } else if (p.deterministic && warp >= 2) {
+    // a trailing split without slabs still owns a plane: it is all zero
+    const int grow = m_tile * 128 + (warp & 3) * 32 + lane;
+    if (grow < p.Ktot) {
+      float* dst = p.dw + static_cast<size_t>(split) * p.Cout * p.Ktot +
+                   static_cast<size_t>(n_tile * BLOCK_N) * p.Ktot + grow;
+      for (int i = 0; i < BLOCK_N; ++i) dst[static_cast<size_t>(i) * p.Ktot] = 0.f;
     }
   }
 

@@ -31,7 +31,8 @@ struct WgradHaloParams {
   int Ktot;            // R*S*Cin
   int nacc;            // R * Cin/32 accumulators
   int slabs_total;     // ceil(N*P*(Q+S-1) / PX)
-  float* dw;           // [64][Ktot]
+  float* dw;           // [64][Ktot]; deterministic mode: [gridDim.x][64][Ktot] partial planes
+  int deterministic;   // see WgradParams
 };
 
 constexpr int kWgradHaloThreads = 192;
@@ -169,10 +170,27 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x,
             tmem_ld_32x32(t_addr + ch * 32, v);
             tmem_ld_wait();
             float* dst = p.dw + static_cast<size_t>(ch * 32) * p.Ktot + grow;
+            if (p.deterministic) {
+              dst += static_cast<size_t>(blockIdx.x) * 64 * p.Ktot;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, v[i]);
+              for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(i) * p.Ktot] = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, v[i]);
+            }
           }
         }
+      }
+    }
+  } else if (p.deterministic && warp >= 2) {
+    // a trailing CTA without slabs still owns a plane: it is all zero
+    const int slot = warp & 3;
+    if (slot < p.S) {
+      for (int a = 0; a < p.nacc; ++a) {
+        const int r = a / groups, g = a - r * groups;
+        float* dst = p.dw + static_cast<size_t>(blockIdx.x) * 64 * p.Ktot +
+                     (r * p.S + slot) * p.Cin + g * 32 + lane;
+        for (int i = 0; i < 64; ++i) dst[static_cast<size_t>(i) * p.Ktot] = 0.f;
       }
     }
   }

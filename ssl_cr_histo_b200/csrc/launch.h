@@ -85,8 +85,12 @@ struct WgradArgs {
   int pad_h_lo = 0, pad_h_hi = 0, pad_w_lo = 0, pad_w_hi = 0;
   int force_splits = 0;  // 0 = heuristic
   int no_halo = 0;       // force the one-box-per-tap kernel (tests)
+  int deterministic = 0; // dw holds wgrad_planes() partial planes, stored without atomics
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t stream);
+// number of [Cout][R*S*Cin] planes a deterministic launch of this shape writes on the current
+// device (>= 1), or -1 with the error set
+int wgrad_planes(const WgradArgs& a);
 
 
 // ---- element-wise / small kernels (bn.cu, stem_pool.cu, pack.cu, linear.cu, loss_lerp.cu) ----
@@ -116,7 +120,7 @@ int launch_stem_pack_input_u8(const unsigned char* x, __half* xs_h, float* xs32,
                               cudaStream_t stream);
 int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
                             cudaStream_t stream);
-int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate,
+int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, int planes,
                              cudaStream_t stream);
 int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shift, float* a32,
                            __half* a_h, __half* a_l, unsigned char* idx, int N, int H, int W,
@@ -143,7 +147,7 @@ int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
                       cudaStream_t stream);
 int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream);
 int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S, int accumulate,
-                        cudaStream_t stream);
+                        int planes, cudaStream_t stream);
 int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,
                       float* y, long long ldy, int rows, int in_f, int out_f, int relu,
                       int accumulate, cudaStream_t stream);

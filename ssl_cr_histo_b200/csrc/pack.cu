@@ -72,8 +72,10 @@ __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, float* __restr
 }
 // weight-gradient result back to the parameter layout: dw[k][c][r][s] = dwf[k][(r*S+s)*C + c]
 // (accumulate: += into a gradient slot several passes over the same weights feed)
+// planes > 1: dwf holds that many [K][R*S*C] partial planes (deterministic split-K), summed here
+// in plane order
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, float* __restrict__ dw, int K,
-                                    int C, int R, int S, int accumulate) {
+                                    int C, int R, int S, int accumulate, int planes) {
   const size_t total = static_cast<size_t>(K) * C * R * S;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -82,7 +84,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, float* __rest
     const int r = static_cast<int>(u % R); u /= R;
     const int c = static_cast<int>(u % C);
     const int k = static_cast<int>(u / C);
-    const float v = dwf[(static_cast<size_t>(k) * R * S + r * S + s) * C + c];
+    const size_t src = (static_cast<size_t>(k) * R * S + r * S + s) * C + c;
+    float v = dwf[src];
+    for (int pl = 1; pl < planes; ++pl) v += dwf[static_cast<size_t>(pl) * total + src];
     dw[t] = accumulate ? dw[t] + v : v;
   }
 }
@@ -112,9 +116,10 @@ int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C
 B2N_PACK_LAUNCH(launch_pack_dgrad, pack_dgrad_kernel)
 #undef B2N_PACK_LAUNCH
 int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S, int accumulate,
-                        cudaStream_t stream) {
+                        int planes, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(K) * C * R * S;
-  unpack_wgrad_kernel<<<pack_grid(total), 256, 0, stream>>>(src, dst, K, C, R, S, accumulate);
+  if (planes < 1) return set_error("unpack_wgrad: planes must be >= 1");
+  unpack_wgrad_kernel<<<pack_grid(total), 256, 0, stream>>>(src, dst, K, C, R, S, accumulate, planes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("launch_unpack_wgrad: %s", cudaGetErrorString(e));
   return 0;

@@ -110,12 +110,14 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __half* __r
   }
 }
 __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw,
-                                         int K, int accumulate) {
+                                         int K, int accumulate, int planes) {
   const int total = K * 3 * 49;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int s = t % 7, r = (t / 7) % 7, c = (t / 49) % 3, k = t / 147;
     const int tr = (r + 1) >> 1, dy = (r + 1) & 1, ts = (s + 1) >> 1, dx = (s + 1) & 1;
-    const float v = dws[(k * 16 + tr * 4 + ts) * kStemC + (dy * 2 + dx) * 3 + c];
+    const int src = (k * 16 + tr * 4 + ts) * kStemC + (dy * 2 + dx) * 3 + c;
+    float v = dws[src];
+    for (int pl = 1; pl < planes; ++pl) v += dws[static_cast<size_t>(pl) * K * 16 * kStemC + src];
     dw[t] = accumulate ? dw[t] + v : v;
   }
 }
@@ -152,9 +154,10 @@ int launch_stem_pack_weight(const float* w, __half* ws_h, __half* ws_l, int K,
   if (e != cudaSuccess) return set_error("stem_pack_weight: %s", cudaGetErrorString(e));
   return 0;
 }
-int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate,
+int launch_stem_unpack_wgrad(const float* dws, float* dw, int K, int accumulate, int planes,
                              cudaStream_t stream) {
-  stem_unpack_wgrad_kernel<<<37, 256, 0, stream>>>(dws, dw, K, accumulate);
+  if (planes < 1) return set_error("stem_unpack_wgrad: planes must be >= 1");
+  stem_unpack_wgrad_kernel<<<37, 256, 0, stream>>>(dws, dw, K, accumulate, planes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("stem_unpack_wgrad: %s", cudaGetErrorString(e));
   return 0;

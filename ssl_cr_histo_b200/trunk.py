@@ -181,6 +181,18 @@ class ResNet18Trunk(nn.Module):
 _SIDE_STREAMS = {}
 OVERLAP_WGRAD = os.environ.get("B2N_OVERLAP_WGRAD", "0") not in ("", "0")
 
+# Weight gradients are split-K sums over pixel slabs.  By default the partial tiles are reduced
+# with fp32 atomics (summation order, hence the last bits, vary from run to run); in deterministic
+# mode every split stores its own plane and the unpack kernel adds the planes in a fixed order:
+# bit-repeatable gradients for ~20 MB of scratch per conv and no measurable time.
+DETERMINISTIC_WGRAD = os.environ.get("B2N_DETERMINISTIC", "0") not in ("", "0")
+
+
+def set_deterministic(flag: bool) -> None:
+    """Bit-repeatable weight gradients (two-stage split-K reduction instead of atomics)."""
+    global DETERMINISTIC_WGRAD
+    DETERMINISTIC_WGRAD = bool(flag)
+
 
 def _side_stream(dev: torch.device) -> torch.cuda.Stream:
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
@@ -444,9 +456,10 @@ class _TrunkFn(torch.autograd.Function):
 
         convs = [trunk.conv1] + [c for b in blocks for c in
                                  ([b.conv1, b.conv2] + ([b.downsample[0]] if b.downsample is not None else []))]
+        det = DETERMINISTIC_WGRAD
         dwp_off, total = {}, 0
         for c in convs:
-            if need[id(c.weight)]:
+            if need[id(c.weight)] and not det:
                 dwp_off[id(c)] = total
                 # the stem's packed gradient is [64][16 taps * STEM_C] (space-to-depth view)
                 total += 64 * 16 * STEM_C if c is trunk.conv1 else c.weight.numel()
@@ -535,10 +548,12 @@ class _TrunkFn(torch.autograd.Function):
             P, Q = dy.shape[1], dy.shape[2]
             wflops = 2.0 * N * P * Q * K * R * S * C
             with _on_side(x_in, dy):
-                dwp = dwp_of(conv, K, R * S * C)
+                planes = _lib.wgrad_planes(N, H, W, C, K, R, S, stride, pad, pad, pad, pad) if det else 1
+                dwp = torch.empty(planes, K, R * S * C, device=dev) if det else dwp_of(conv, K, R * S * C)
                 call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
+                     1 if det else 0,
                      work=(wflops, 0.0, wflops, "wgrad", 4.0 * N * (H * W * C + P * Q * K)))
-                emit(conv.weight, lambda t, acc: call("b2n_unpack_wgrad", dwp, t, K, C, R, S, acc))
+                emit(conv.weight, lambda t, acc: call("b2n_unpack_wgrad", dwp, t, K, C, R, S, acc, planes))
             dw = grads[id(conv.weight)]
             if side is not None and dw is not None:
                 dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
@@ -649,11 +664,15 @@ class _TrunkFn(torch.autograd.Function):
                 dy0 = bn_backward(gz, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
             if need[id(trunk.conv1.weight)]:
                 with _on_side(sv["xs"], dy0):
-                    dws = dwp_of(trunk.conv1, 64, 16 * STEM_C)
+                    planes = _lib.wgrad_planes(N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1) if det else 1
+                    dws = (torch.empty(planes, 64, 16 * STEM_C, device=dev) if det
+                           else dwp_of(trunk.conv1, 64, 16 * STEM_C))
                     call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
+                         1 if det else 0,
                          work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
                                "wgrad", 4.0 * N * H2 * W2 * (STEM_C + 64)))
-                    emit(trunk.conv1.weight, lambda t, acc: call("b2n_stem_unpack_wgrad", dws, t, 64, acc))
+                    emit(trunk.conv1.weight,
+                         lambda t, acc: call("b2n_stem_unpack_wgrad", dws, t, 64, acc, planes))
                 dw = grads[id(trunk.conv1.weight)]
                 if side is not None and dw is not None:
                     dw.record_stream(main)

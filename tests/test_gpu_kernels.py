@@ -212,12 +212,19 @@ def test_conv_wgrad_bit_exact(case):
     ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, R, R), dy, stride=s, padding=p)
     dwp = torch.zeros(Cout, R * R * Cin, device=DEV)
     call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
-         p, p, p, p)
+         p, p, p, p, 0)
     dw = torch.empty(Cout, Cin, R, R, device=DEV)
-    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 0)
+    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 0, 1)
     assert torch.equal(dw.cpu(), ref)
-    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 1)      # accumulate: a second writer of the slot
+    call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 1, 1)   # accumulate: a second writer of the slot
     assert torch.equal(dw.cpu(), 2 * ref)
+    # deterministic mode: one plane per split-K group, no atomics, no zero-fill, summed by the unpack
+    planes = _lib.wgrad_planes(N, H, W, Cin, Cout, R, R, s, p, p, p, p)
+    part = torch.full((planes, Cout, R * R * Cin), float("nan"), device=DEV)
+    call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), part, N, H, W, Cin, Cout, R, R, s,
+         p, p, p, p, 1)
+    call("b2n_unpack_wgrad", part, dw, Cout, Cin, R, R, 0, planes)
+    assert torch.equal(dw.cpu(), ref)
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -310,12 +317,17 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     dy = ints(tuple(ref.shape), -1, 1, 33)
     ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=3)
     dws = torch.zeros(64, 16 * 32, device=DEV)
-    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1)
+    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 0)
     dw = torch.empty(64, 3, 7, 7, device=DEV)
-    call("b2n_stem_unpack_wgrad", dws, dw, 64, 0)
+    call("b2n_stem_unpack_wgrad", dws, dw, 64, 0, 1)
     assert torch.equal(dw.cpu(), ref_dw)
-    call("b2n_stem_unpack_wgrad", dws, dw, 64, 1)
+    call("b2n_stem_unpack_wgrad", dws, dw, 64, 1, 1)
     assert torch.equal(dw.cpu(), 2 * ref_dw)
+    planes = _lib.wgrad_planes(N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1)
+    part = torch.full((planes, 64, 16 * 32), float("nan"), device=DEV)
+    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), part, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 1)
+    call("b2n_stem_unpack_wgrad", part, dw, 64, 0, planes)
+    assert torch.equal(dw.cpu(), ref_dw)
 
 
 def test_conv_rejects_bad_shapes_loudly():
@@ -716,7 +728,7 @@ def test_tap_sharing_kernels_equal_the_per_tap_kernels(case, monkeypatch):
         y2 = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, p, p)
         dwp = torch.zeros(Cout, R * R * Cin, device=DEV)
         call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
-             p, p, p, p)
+             p, p, p, p, 0)
         return y1, y2, dwp
 
     halo = run()

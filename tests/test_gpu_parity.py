@@ -614,3 +614,28 @@ def test_cuda_graph_replay_equals_eager_steps():
         assert rel_l2(p, q) < (2e-2 if n.endswith("bias") else 1e-4), n
     for (k, u), (_, v) in zip(s_g.named_buffers(), s_r.named_buffers()):
         assert (int(u) == int(v)) if u.dtype == torch.long else max_rel(u, v) < 1e-4, k
+
+
+def test_deterministic_weight_gradients_are_bit_repeatable():
+    """trunk.set_deterministic(True): split-K partial planes summed in a fixed order instead of fp32
+    atomics -- two runs of the same step give bit-identical gradients for every parameter, and they
+    agree with the default (atomic) path to round-off."""
+    from ssl_cr_histo_b200 import trunk
+    _, _, gm, gh = pair("finetune", ("finetune", 9))
+    x = O.synthetic_patches(6, 96, seed=110).to(DEV)
+    target = torch.tensor([0, 3, 8, 1, 5, 2], device=DEV)
+
+    def grads(model, head):
+        model, head = copy.deepcopy(model).train(), copy.deepcopy(head)
+        F.cross_entropy(head(model(x)), target).backward()
+        return [p.grad.clone() for p in list(model.parameters()) + list(head.parameters())]
+
+    base = grads(gm, gh)
+    trunk.set_deterministic(True)
+    try:
+        a, b = grads(gm, gh), grads(gm, gh)
+    finally:
+        trunk.set_deterministic(False)
+    for (n, _), u, v, w in zip(list(gm.named_parameters()) + list(gh.named_parameters()), a, b, base):
+        assert torch.equal(u, v), n
+        assert rel_l2(u, w) < 1e-5, n
