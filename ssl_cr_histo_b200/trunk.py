@@ -181,11 +181,12 @@ class ResNet18Trunk(nn.Module):
 _SIDE_STREAMS = {}
 OVERLAP_WGRAD = os.environ.get("B2N_OVERLAP_WGRAD", "0") not in ("", "0")
 
-# Weight gradients are split-K sums over pixel slabs.  By default the partial tiles are reduced
-# with fp32 atomics (summation order, hence the last bits, vary from run to run); in deterministic
-# mode every split stores its own plane and the unpack kernel adds the planes in a fixed order:
-# bit-repeatable gradients for ~20 MB of scratch per conv and no measurable time.
-DETERMINISTIC_WGRAD = os.environ.get("B2N_DETERMINISTIC", "0") not in ("", "0")
+# Weight gradients are split-K sums over pixel slabs.  By default every split stores its own plane
+# and the unpack kernel adds the planes in a fixed order: bit-repeatable gradients for ~20 MB of
+# transient scratch per conv and 0.1 ms of a 34 ms step.  B2N_DETERMINISTIC=0 (or
+# set_deterministic(False)) reduces the partial tiles with fp32 atomics into one zeroed plane
+# instead (summation order, hence the last bits, then vary from run to run).
+DETERMINISTIC_WGRAD = os.environ.get("B2N_DETERMINISTIC", "1") not in ("", "0")
 
 
 def set_deterministic(flag: bool) -> None:
