@@ -125,17 +125,47 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------- CUDA arm
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region: NVML through
+    pynvml (sub-millisecond per sample) when available, else nvidia-smi (tens of ms per sample)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index counts CUDA_VISIBLE_DEVICES entries; NVML counts physical GPUs
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = get(self.handle)
+        bits = [getattr(n, "nvmlClocksEventReason" + k, getattr(n, "nvmlClocksThrottleReason" + k, d))
+                for k, d in (("HwSlowdown", 0x8), ("HwThermalSlowdown", 0x40),
+                             ("SwThermalSlowdown", 0x20), ("SwPowerCap", 0x4))]
+        return [str(sm), str(self.max_sm), ""] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
@@ -147,12 +177,12 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names)
+        reasons = [n for i, n in enumerate(self.NAMES)
                    if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 class Env:
