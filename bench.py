@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"],
+                    help="b200: this repo's kernels; reference: the reference's CPU path (oracle port) on the "
+                         "host cores; library: the reference's modules on the GPU through torch + cuDNN")
     ap.add_argument("--batch-size", type=int, default=64, help="labeled items per rank (x3 views)")
     ap.add_argument("--mu", type=int, default=8)
     ap.add_argument("--size", type=int, default=224)
@@ -735,9 +737,30 @@ def run_b200(args):
         env.dist.destroy_process_group()
 
 
+def run_library(args):
+    """The reference's own modules on cuda:0 through torch + cuDNN (see gpu_library_baseline) as a
+    contract-shaped line of its own (single GPU; the reference's multi-GPU mode is nn.DataParallel)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    r = gpu_library_baseline(args, dev, steps=max(args.steps, 2), warmup=max(args.warmup, 2))
+    v = r["three_pass"]
+    print(json.dumps({
+        "impl": "library", "metric": "224x224 histo patches/sec (consistency step)",
+        "value": v.get("value"), "unit": "patches/s", "n_gpus": 1, "steps": max(args.steps, 2),
+        "warmup": max(args.warmup, 2), "ms_per_step": v.get("ms_per_step"), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32 storage, cuDNN TF32 convolutions (torch default)",
+        "data": "synthetic",
+        "config": {"workload": "SSL_CR consistency step (eval_BreastPathQ_SSL_CR.py:76-100), reference modules as "
+                               "written (three trunk passes per model call), BASELINE configs[2]", "how": r["how"]},
+        "single_pass_variant": r["single_pass"], "gpu_launches": 0}))
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "library":
+        run_library(a)
     else:
         run_b200(a)

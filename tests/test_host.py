@@ -35,6 +35,22 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.b2n_version() == 2
 
 
+def test_header_is_plain_c():
+    """include/b2n.h is the drop-in boundary: it must compile as C (no C++ or CUDA types)."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    with tempfile.NamedTemporaryFile("w", suffix=".c") as f:
+        f.write('#include "b2n.h"\nint (*probe)(void) = b2n_version;\nint main(void) { return probe == 0; }\n')
+        f.flush()
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                            "-I", os.path.join(ROOT, "include"), f.name], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_library_has_blackwell_tensor_core_and_tma_sass():
     import shutil
     import subprocess

@@ -74,8 +74,8 @@ def trunk_only(N=4, size=64):
     trace = []
     orig_call = T.call
 
-    def spy(name, *args):
-        orig_call(name, *args)
+    def spy(name, *args, **kw):
+        orig_call(name, *args, **kw)
         if name == "b2n_bn_bwd_apply":
             trace.append(("dy", args[9].clone(), args[0].clone()))
         if name == "b2n_pool_bn_bwd_apply":
