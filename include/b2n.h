@@ -91,10 +91,13 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
  * loss.backward() (pretrain_BreastPathQ.py:60).
  * deterministic != 0: no atomics -- every split-K CTA group stores its own partial plane, so
  * dw_packed must hold b2n_conv_wgrad_planes(...) planes of [Cout][R*S*Cin] floats (no zero-fill
- * needed) and b2n_unpack_wgrad sums them in a fixed order: bit-repeatable gradients. */
+ * needed) and b2n_unpack_wgrad sums them in a fixed order: bit-repeatable gradients.
+ * x_channels (0 = Cin): channels x actually stores per pixel; with Cin = 32 it may be smaller (a
+ * multiple of 4): the remaining reduction channels are zero-filled by the TMA unit instead of being
+ * stored -- the stem's space-to-depth input has 12 real channels. */
 int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
                    int Cout, int R, int S, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                   int pad_w_hi, int deterministic, void* stream);
+                   int pad_w_hi, int deterministic, int x_channels, void* stream);
 /* Planes a deterministic b2n_conv_wgrad of this shape writes on the current device (>= 1; < 0 on
  * error).  Host-side only, no launch. */
 int b2n_conv_wgrad_planes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
@@ -117,7 +120,7 @@ int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int
 /* ---- stem: 7x7/s2 conv as a 4x4/s1 conv over a 2x2 space-to-depth view (tv:197,268) ----- */
 /* x NCHW fp32 (N,3,H,W), H and W even -> NHWC space-to-depth views (12 real channels): the
  * (hi, lo) FP16 pair (N,H/2,W/2,16) for the forward conv and (xs32, may be NULL) the TF32 fp32
- * copy (N,H/2,W/2,32) for the wgrad. */
+ * copy (N,H/2,W/2,12) for the wgrad (b2n_conv_wgrad with Cin = 32, x_channels = 12). */
 int b2n_stem_pack_input(const float* x_nchw, b2n_half* xs_h, b2n_half* xs_l, float* xs32,
                         int* xs_l_nonzero /* optional, caller-zeroed: set to 1 if any lo != 0 */,
                         int N, int H, int W, void* stream);

@@ -20,7 +20,7 @@ P, I, LL, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 # name -> argument ctypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
     "b2n_conv_fwd": [P] * 9 + [I] * 12 + [P, P, P, P, P, P, I, I, P, P] + [I] * 5 + [P] * 6,
-    "b2n_conv_wgrad": [P, P, P] + [I] * 13,
+    "b2n_conv_wgrad": [P, P, P] + [I] * 14,
     "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
     "b2n_pack_weight_dgrad_s2": [P, P, I, I],

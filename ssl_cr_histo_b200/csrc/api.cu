@@ -63,10 +63,11 @@ int b2n_conv_fwd(const float* x, const b2n_half* x_h, const b2n_half* x_l, const
 
 int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int H, int W, int Cin,
                    int Cout, int R, int Sf, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                   int pad_w_hi, int deterministic, void* stream) {
+                   int pad_w_hi, int deterministic, int x_channels, void* stream) {
   if (!x || !dy || !dw_packed) return set_error("b2n_conv_wgrad: null tensor");
   WgradArgs a;
   a.deterministic = deterministic;
+  a.x_channels = x_channels;
   a.x = x; a.dy = dy; a.dw = dw_packed;
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.R = R; a.S = Sf; a.stride = stride;
   a.pad_h_lo = pad_h_lo; a.pad_h_hi = pad_h_hi; a.pad_w_lo = pad_w_lo; a.pad_w_hi = pad_w_hi;

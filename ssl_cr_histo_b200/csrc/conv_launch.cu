@@ -352,8 +352,9 @@ static int launch_wgrad_halo(const WgradArgs& a, int P, int Q, cudaStream_t stre
   p.dw = a.dw;
   CUtensorMap mx, mdy;
   // X: S = 1 with the pad columns inside the bounding box -> traversal = padded-width raster
-  if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.Cin, a.R, 1, a.pad_h_lo, a.pad_h_hi,
-                      a.pad_w_lo, a.pad_w_hi, 1, 32, kWhPX + a.S - 1, kSwizzle128Atom32))
+  if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.x_channels > 0 ? a.x_channels : a.Cin, a.R, 1,
+                      a.pad_h_lo, a.pad_h_hi, a.pad_w_lo, a.pad_w_hi, 1, 32, kWhPX + a.S - 1,
+                      kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
   // dY on the same raster: S - 1 zero-filled positions after the last column of every row
   if (make_im2col_map(&mdy, a.dy, kF32, a.N, P, Q, a.Cout, 1, 1, 0, 0, 0, a.S - 1, 1, 32, kWhPX,
@@ -366,6 +367,9 @@ static int launch_wgrad_halo(const WgradArgs& a, int P, int Q, cudaStream_t stre
 
 int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   if (a.Cin % 32 != 0) return set_error("wgrad: Cin=%d must be a multiple of 32", a.Cin);
+  if (a.x_channels != 0 && (a.x_channels < 0 || a.x_channels > a.Cin || a.x_channels % 4 != 0 || a.Cin != 32))
+    return set_error("wgrad: x_channels=%d needs Cin = 32 and a multiple of 4 channels (16-byte pixel pitch)",
+                     a.x_channels);
   if (a.Cout % 64 != 0) return set_error("wgrad: Cout=%d must be a multiple of 64", a.Cout);
   const int P = (a.H + a.pad_h_lo + a.pad_h_hi - a.R) / a.stride + 1;
   const int Q = (a.W + a.pad_w_lo + a.pad_w_hi - a.S) / a.stride + 1;
@@ -391,8 +395,8 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   p.deterministic = a.deterministic;
 
   CUtensorMap mx, mdy;
-  if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.Cin, a.R, a.S, a.pad_h_lo, a.pad_h_hi,
-                      a.pad_w_lo, a.pad_w_hi, a.stride, 32, px, kSwizzle128Atom32))
+  if (make_im2col_map(&mx, a.x, kF32, a.N, a.H, a.W, a.x_channels > 0 ? a.x_channels : a.Cin, a.R, a.S,
+                      a.pad_h_lo, a.pad_h_hi, a.pad_w_lo, a.pad_w_hi, a.stride, 32, px, kSwizzle128Atom32))
     return set_error("wgrad: %s", tmap_last_error());
   // dY as one 3-D box per stage: (32 channels) x (PX pixels) x (BLOCK_N / 32 channel groups)
   if (make_grouped_map_3d(&mdy, a.dy, (uint64_t)M, a.Cout, px, block_n / 32,

@@ -86,6 +86,8 @@ struct WgradArgs {
   int force_splits = 0;  // 0 = heuristic
   int no_halo = 0;       // force the one-box-per-tap kernel (tests)
   int deterministic = 0; // dw holds wgrad_planes() partial planes, stored without atomics
+  int x_channels = 0;    // channels x stores per pixel (0 = Cin); fewer than Cin: the missing ones are
+                         // zero-filled by the TMA unit (the stem's 12 real of 32 reduction channels)
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t stream);
 // number of [Cout][R*S*Cin] planes a deterministic launch of this shape writes on the current

@@ -17,7 +17,10 @@
 
 namespace b2n {
 
-constexpr int kStemC = 32;   // channels of the fp32 (weight-gradient) copy
+constexpr int kStemC = 32;   // channels of the weight gradient's reduction per tap (12 real)
+constexpr int kStemCStored = 12;  // channels of the fp32 copy actually stored: the weight gradient's
+                                  // TMA map declares 12 channels and requests 32 -- the other 20 are
+                                  // zero-filled by the TMA unit instead of being written and read
 constexpr int kStemC16 = 16; // channels of the FP16 (forward) pair
 
 // x: NCHW (N,3,H,W), H and W even, fp32 or uint8 pixels.  Outputs NHWC: the (hi, lo) FP16 pair
@@ -79,12 +82,10 @@ __global__ void stem_pack_input_kernel(const T* __restrict__ x, uint4* __restric
       dl[0] = pl[0]; dl[1] = pl[1];
     }
     if (xs32 != nullptr) {
-      float4* d = xs32 + t * (kStemC / 4);
+      float4* d = xs32 + t * (kStemCStored / 4);
       d[0] = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
       d[1] = make_float4(tf32_rn(v[4]), tf32_rn(v[5]), tf32_rn(v[6]), tf32_rn(v[7]));
       d[2] = make_float4(tf32_rn(v[8]), tf32_rn(v[9]), tf32_rn(v[10]), tf32_rn(v[11]));
-#pragma unroll
-      for (int k = 3; k < kStemC / 4; ++k) d[k] = make_float4(0, 0, 0, 0);
     }
   }
 }

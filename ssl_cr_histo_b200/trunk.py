@@ -22,7 +22,8 @@ from . import _lib
 from ._lib import call
 
 _LAYER_CFG = [(64, 1), (128, 2), (256, 2), (512, 2)]  # (planes, stride of first block)
-STEM_C = 32    # channels of the fp32 space-to-depth stem input the weight gradient reads (12 real)
+STEM_C = 32    # reduction channels per tap of the stem's weight gradient (12 real)
+STEM_C_STORED = 12  # channels the fp32 space-to-depth copy stores; the TMA unit zero-fills the rest
 STEM_C16 = 16  # channels of its FP16 (hi, lo) pair, the forward conv's operand
 
 
@@ -326,7 +327,7 @@ class _TrunkFn(torch.autograd.Function):
         H2, W2 = H // 2, W // 2
         xs = _Act.__new__(_Act)
         xs.hi = torch.empty(N, H2, W2, STEM_C16, device=dev, dtype=torch.float16)
-        xs.f32 = torch.empty(N, H2, W2, STEM_C, device=dev, dtype=torch.float32) if save else None
+        xs.f32 = torch.empty(N, H2, W2, STEM_C_STORED, device=dev, dtype=torch.float32) if save else None
         lo_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         if u8:
             xs.lo = xs.hi           # never read: lo_flag stays 0
@@ -552,7 +553,7 @@ class _TrunkFn(torch.autograd.Function):
                 planes = _lib.wgrad_planes(N, H, W, C, K, R, S, stride, pad, pad, pad, pad) if det else 1
                 dwp = torch.empty(planes, K, R * S * C, device=dev) if det else dwp_of(conv, K, R * S * C)
                 call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
-                     1 if det else 0,
+                     1 if det else 0, 0,
                      work=(wflops, 0.0, wflops, "wgrad", 4.0 * N * (H * W * C + P * Q * K)))
                 emit(conv.weight, lambda t, acc: call("b2n_unpack_wgrad", dwp, t, K, C, R, S, acc, planes))
             dw = grads[id(conv.weight)]
@@ -669,9 +670,9 @@ class _TrunkFn(torch.autograd.Function):
                     dws = (torch.empty(planes, 64, 16 * STEM_C, device=dev) if det
                            else dwp_of(trunk.conv1, 64, 16 * STEM_C))
                     call("b2n_conv_wgrad", sv["xs"], dy0, dws, N, H2, W2, STEM_C, 64, 4, 4, 1, 2, 1, 2, 1,
-                         1 if det else 0,
+                         1 if det else 0, STEM_C_STORED,
                          work=(2.0 * N * H2 * W2 * 64 * 147, 0.0, 2.0 * N * H2 * W2 * 64 * 16 * STEM_C,
-                               "wgrad", 4.0 * N * H2 * W2 * (STEM_C + 64)))
+                               "wgrad", 4.0 * N * H2 * W2 * (STEM_C_STORED + 64)))
                     emit(trunk.conv1.weight,
                          lambda t, acc: call("b2n_stem_unpack_wgrad", dws, t, 64, acc, planes))
                 dw = grads[id(trunk.conv1.weight)]

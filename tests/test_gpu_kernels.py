@@ -212,7 +212,7 @@ def test_conv_wgrad_bit_exact(case):
     ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, R, R), dy, stride=s, padding=p)
     dwp = torch.zeros(Cout, R * R * Cin, device=DEV)
     call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
-         p, p, p, p, 0)
+         p, p, p, p, 0, 0)
     dw = torch.empty(Cout, Cin, R, R, device=DEV)
     call("b2n_unpack_wgrad", dwp, dw, Cout, Cin, R, R, 0, 1)
     assert torch.equal(dw.cpu(), ref)
@@ -222,7 +222,7 @@ def test_conv_wgrad_bit_exact(case):
     planes = _lib.wgrad_planes(N, H, W, Cin, Cout, R, R, s, p, p, p, p)
     part = torch.full((planes, Cout, R * R * Cin), float("nan"), device=DEV)
     call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), part, N, H, W, Cin, Cout, R, R, s,
-         p, p, p, p, 1)
+         p, p, p, p, 1, 0)
     call("b2n_unpack_wgrad", part, dw, Cout, Cin, R, R, 0, planes)
     assert torch.equal(dw.cpu(), ref)
 
@@ -295,7 +295,7 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     x = ints((N, 3, H, W), 0, 255, 31)                       # uint8-valued patches
     w = ints((64, 3, 7, 7), -2, 2, 32, 0.25)
     ref = F.conv2d(x, w, None, 2, 3)
-    xs = torch.empty(N, H // 2, W // 2, 32, device=DEV)      # fp32 copy (wgrad): 32 channels
+    xs = torch.empty(N, H // 2, W // 2, 12, device=DEV)      # fp32 copy (wgrad): the 12 real channels
     xs_h = torch.empty(N, H // 2, W // 2, 16, device=DEV, dtype=torch.half)   # FP16 pair: 16
     xs_l = torch.empty_like(xs_h)
     flag = torch.zeros(1, device=DEV, dtype=torch.int32)
@@ -317,7 +317,7 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     dy = ints(tuple(ref.shape), -1, 1, 33)
     ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=3)
     dws = torch.zeros(64, 16 * 32, device=DEV)
-    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 0)
+    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 0, 12)
     dw = torch.empty(64, 3, 7, 7, device=DEV)
     call("b2n_stem_unpack_wgrad", dws, dw, 64, 0, 1)
     assert torch.equal(dw.cpu(), ref_dw)
@@ -325,7 +325,17 @@ def test_stem_space_to_depth_conv_and_wgrad(size):
     assert torch.equal(dw.cpu(), 2 * ref_dw)
     planes = _lib.wgrad_planes(N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1)
     part = torch.full((planes, 64, 16 * 32), float("nan"), device=DEV)
-    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), part, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 1)
+    call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), part, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 1, 12)
+    # the generic (one box per tap) kernel with the same 12-of-32 stored channels
+    import os
+    os.environ["B2N_NO_HALO"] = "1"
+    try:
+        dws.zero_()
+        call("b2n_conv_wgrad", xs, to_nhwc(dy).to(DEV), dws, N, H // 2, W // 2, 32, 64, 4, 4, 1, 2, 1, 2, 1, 0, 12)
+        call("b2n_stem_unpack_wgrad", dws, dw, 64, 0, 1)
+    finally:
+        del os.environ["B2N_NO_HALO"]
+    assert torch.equal(dw.cpu(), ref_dw)
     call("b2n_stem_unpack_wgrad", part, dw, 64, 0, planes)
     assert torch.equal(dw.cpu(), ref_dw)
 
@@ -728,7 +738,7 @@ def test_tap_sharing_kernels_equal_the_per_tap_kernels(case, monkeypatch):
         y2 = conv((xh.to(DEV), xl.to(DEV)), pack_fwd(w, split=True), N, H, W, Cin, Cout, R, s, p, p)
         dwp = torch.zeros(Cout, R * R * Cin, device=DEV)
         call("b2n_conv_wgrad", to_nhwc(x).to(DEV), to_nhwc(dy).to(DEV), dwp, N, H, W, Cin, Cout, R, R, s,
-             p, p, p, p, 0)
+             p, p, p, p, 0, 0)
         return y1, y2, dwp
 
     halo = run()
