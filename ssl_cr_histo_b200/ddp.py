@@ -22,9 +22,11 @@ import torch.distributed as dist
 
 class GradAllReducer:
     """``params``: every trainable parameter of the step, in ``named_parameters()`` order (model
-    first, heads after) -- the arena reverses it.  ``passes``: how many times each parameter's
-    gradient is written per step (3 for ``TripletNet``'s three trunk passes over shared weights, 1
-    otherwise; only matters for ``overlap``).  ``sync_initial``: broadcast rank 0's parameters (and,
+    first, heads after) -- the arena reverses it.  With ``overlap`` the reducer has to know how many
+    writers feed each slot per step (three for the trunk under ``TripletNet``'s three passes over
+    shared weights, one for its heads): it counts them during the first step (which is reduced
+    without overlap) and starts buckets early from the second step on; ``passes`` is only the
+    initial guess.  ``sync_initial``: broadcast rank 0's parameters (and,
     via ``sync_buffers``, the floating-point buffers of the given modules) so that replicas that
     were built from different seeds still start identical -- DataParallel's replicate step, done
     once instead of every forward."""
@@ -61,6 +63,8 @@ class GradAllReducer:
             p._b2n_grad_slot = slot
             p._b2n_grad_sink = self if self.overlap else None
         self._pending = [0] * len(self.buckets)
+        self._expected = None           # writers per parameter and step, learned in the first step
+        self._seen = {}
         self._works = []
         self._stream = torch.cuda.Stream(device=dev) if self.overlap and dev.type == "cuda" else None
         self._arm()
@@ -75,7 +79,13 @@ class GradAllReducer:
 
     def _arm(self):
         for b, (_, _, members) in enumerate(self.buckets):
-            self._pending[b] = self.passes * len(members)
+            if self._expected is None:
+                self._pending[b] = 1 << 30          # learning step: launched by all_reduce()
+            else:
+                counts = [self._expected.get(id(p), 0) for p in members]
+                # a member nobody reports (a module outside this package) keeps the bucket manual
+                self._pending[b] = sum(counts) if all(counts) else 1 << 30
+        self._seen = {}
 
     # ------------------------------------------------------------------ initial state
     def sync_parameters(self) -> None:
@@ -113,6 +123,7 @@ class GradAllReducer:
         b = self._bucket_of.get(id(p))
         if b is None or not self.overlap:
             return
+        self._seen[id(p)] = self._seen.get(id(p), 0) + 1
         self._pending[b] -= 1
         if self._pending[b] == 0:
             self._launch(b)
@@ -145,6 +156,8 @@ class GradAllReducer:
                                        "reduced; construct GradAllReducer(overlap=False)")
                 slot.add_(p.grad)
                 p.grad = slot
+        if self.overlap and self._expected is None and self._seen:
+            self._expected = dict(self._seen)
         if self.world > 1:
             if self.overlap:
                 for b in range(len(self.buckets)):

@@ -175,12 +175,15 @@ def _ddp_worker(rank, world, port, out):
     assert lin.weight._b2n_grad_slot.data_ptr() == lin.weight.grad.data_ptr()
     data = torch.arange(40, dtype=torch.float32).view(8, 5) / 10.0
     shard = ddp.shard(data, rank, world)
-    for step in range(2):                                        # re-armed by zero_grad
+    for step in range(3):                                        # re-armed by zero_grad
         red.zero_grad()
         lin2(lin(shard)).pow(2).mean().backward()                # autograd accumulates into the slots
-        for p in reversed(params):                               # what the package's backward reports
+        for p in reversed(params):                               # what the package's backward reports:
+            red.ready(p)                                         # lin2 once, lin twice per step
+        for p in lin.parameters():
             red.ready(p)
-        assert all(n == -1 for n in red._pending)                # both buckets already in flight
+        # step 0 only counts the writers per slot; from step 1 on both buckets are already in flight
+        assert all(n == -1 for n in red._pending) == (step > 0)
         red.all_reduce()
     out[rank] = torch.cat([p.grad.flatten() for p in params]).clone()
     assert lin.weight.grad.data_ptr() == red._slots[id(lin.weight)].data_ptr()   # still in the arena
