@@ -158,10 +158,11 @@ def test_step_goldens_losses_and_logits():
 
 
 # ------------------------------------------------------------------ oracle, same inputs
-@pytest.mark.parametrize("N,size", [(8, 224), (6, 96)])
+@pytest.mark.parametrize("N,size", [(8, 224), (6, 96), (3, 256)])
 def test_rsp_pretrain_step_parity(N, size):
     """cfg2 shape class (pretrain_BreastPathQ.py:53-68): logits / loss / argmax / BN buffers /
-    gradients / the SGD-Nesterov-updated weights."""
+    gradients / the SGD-Nesterov-updated weights.  256 is the reference's default tile size
+    (pretrain_BreastPathQ.py:188-189)."""
     i1, i2, i3 = (O.synthetic_patches(N, size, seed=s) for s in (0, 1, 2))
     target = torch.randint(0, 6, (N,), generator=torch.Generator().manual_seed(5))
     om, oh, gm, gh = pair("triplet", ("classifier", 6))
