@@ -112,6 +112,17 @@ int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, 
  * over dY, packs stored back to back [C][ntaps*K] in class order (0,0), (0,1), (1,0), (1,1);
  * 9*C*K floats. */
 int b2n_pack_weight_dgrad_s2(const float* w, float* w_packed, int K, int C, void* stream);
+/* The same nine (class, tap) blocks as one K-major matrix [C][9*K], and the merged launch that uses
+ * it: all four parity classes of the stride-2 3x3/pad-1 data gradient from ONE pass over
+ * dy [N,P,Q,K] (four TMEM accumulators per 128-pixel tile):
+ *   dx[n, 2i+ph, 2j+pw, c] = sum_{a <= ph, b <= pw, k} dy[n, i+a, j+b, k] * w[k][c][rr(ph,a)][ss(pw,b)]
+ * dx is [N,H,W,C] with P = ceil(H/2), Q = ceil(W/2); resid (optional, may alias dx) is added on the
+ * even-even pixels (the 1x1 shortcut conv's gradient); gate (optional) zeroes dx where gate <= 0.
+ * K a multiple of 32, C of 64.  Replaces cudnnConvolutionBackwardData of the three stride-2 convs
+ * (tv:92 in layer{2,3,4}.0) reached from loss.backward(). */
+int b2n_pack_weight_dgrad_s2m(const float* w, float* w_packed, int K, int C, void* stream);
+int b2n_conv_dgrad_s2(const float* dy, const float* w_packed, float* dx, int N, int P, int Q, int K,
+                      int C, int H, int W, const float* resid, const float* gate, void* stream);
 /* accumulate != 0: dw += (several passes over shared weights feed one gradient slot, e.g. the
  * three trunk passes of TripletNet.forward or a flat all-reduce arena). */
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, int accumulate,

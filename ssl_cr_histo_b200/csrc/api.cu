@@ -74,6 +74,18 @@ int b2n_conv_wgrad(const float* x, const float* dy, float* dw_packed, int N, int
   return counted(launch_wgrad(a, S(stream)));
 }
 
+int b2n_conv_dgrad_s2(const float* dy, const float* w_packed, float* dx, int N, int P, int Q, int K,
+                      int C, int H, int W, const float* resid, const float* gate, void* stream) {
+  ConvArgs a;
+  a.x = dy; a.w = w_packed; a.out = dx;
+  a.N = N; a.H = P; a.W = Q; a.Cin = K; a.Cout = C; a.o_H = H; a.o_W = W;
+  a.resid = resid; a.gate = gate;
+  return counted(launch_conv_dgrad_s2(a, S(stream)));
+}
+int b2n_pack_weight_dgrad_s2m(const float* w, float* wp, int K, int C, void* stream) {
+  return counted(launch_pack_dgrad_s2m(w, wp, K, C, S(stream)));
+}
+
 int b2n_conv_wgrad_planes(int N, int H, int W, int Cin, int Cout, int R, int Sf, int stride,
                           int pad_h_lo, int pad_h_hi, int pad_w_lo, int pad_w_hi) {
   WgradArgs a;

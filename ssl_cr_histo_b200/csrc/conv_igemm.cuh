@@ -33,6 +33,13 @@
 // layers.  The S - 1 raster positions per image row that fall on pad columns produce garbage
 // accumulator rows which the epilogue drops.
 //
+// S2M = true is the merged stride-2 3x3 data gradient: the four output-parity classes of
+// dx[2i+ph, 2j+pw] (1, 2, 2 and 4 taps over the 2x2 neighbourhood dY[i..i+1, j..j+1], see pack.cu)
+// are four accumulators of ONE tile of 128 dY pixels.  The K loop runs over the nine (class, tap)
+// pairs x channel slices, each step one activation box (the tap) and one weight slab, the MMA
+// going to its class's accumulator; the epilogue then stores the four interleaved quarters.
+// dY is read from HBM once instead of once per class (the re-fetches of a tap box hit L2).
+//
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
 // torchvision BasicBlock.forward (site-packages/torchvision/models/resnet.py:92-100).
@@ -128,8 +135,20 @@ __host__ __device__ constexpr bool epi_on(int epi, int bit, bool runtime) {
   return epi >= 0 ? (epi & bit) != 0 : runtime;
 }
 
+// (class, tap) schedule of the merged stride-2 data gradient: entry e in 0..8 belongs to class
+// 0 | 1 1 | 2 2 | 3 3 3 3; within a class the taps are (a, b) = (t / ns, t % ns), ns = 1 + (cls & 1)
+__device__ __forceinline__ void s2m_entry(int e, int& cls, int& r, int& s, bool& first) {
+  cls = e < 1 ? 0 : (e < 3 ? 1 : (e < 5 ? 2 : 3));
+  const int start = cls == 0 ? 0 : (cls == 1 ? 1 : (cls == 2 ? 3 : 5));
+  const int t = e - start;
+  const int ns = 1 + (cls & 1);
+  r = t / ns;
+  s = t - r * ns;
+  first = t == 0;
+}
+
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
-          int EPI_WARPS = 4>
+          int EPI_WARPS = 4, bool S2M = false>
 __global__ void __launch_bounds__(conv_threads(EPI_WARPS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
@@ -147,7 +166,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   // of three times per K step -- UMMA operand reads share the SM's 128 B/clk shared-memory port
   // with the TMA writes, and that port, not the tensor pipe, bounds the narrow (N <= 128) tiles.
   constexpr bool STACK = SPLIT && BLOCK_N <= 128;
-  constexpr int ACC_COLS = STACK ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns of one accumulator stage
+  static_assert(!S2M || (!SPLIT && !RES_B && !HALO && EPI < 0 && EPI_WARPS == 4 && BLOCK_N == 64),
+                "merged stride-2 data gradient: TF32, streamed weights, generic epilogue, 64-wide classes");
+  constexpr int NCLS = S2M ? 4 : 1;                        // accumulators (parity classes) per tile
+  constexpr int ACC_COLS = S2M ? NCLS * BLOCK_N : (STACK ? 2 * BLOCK_N : BLOCK_N);  // TMEM columns per stage
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   // streamed stage layout: A_hi | A_lo | B_hi | B_lo   (B part absent when RES_B)
   constexpr int OFF_A_LO = L::A_BYTES;
@@ -175,7 +197,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_k_steps = p.R * p.S * p.kslices;
+  const int num_k_steps = S2M ? 9 * p.kslices : p.R * p.S * p.kslices;
   const bool skip_a_lo = SPLIT && p.a_lo_nonzero != nullptr && *p.a_lo_nonzero == 0;
 
   if (warp == 0 && lane == 0) {
@@ -266,7 +288,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         const int base_h = op * p.stride - p.pad_h;
         // (r, s, channel slice) advance as nested counters: no division per k step
         int r = 0, s = 0, cs = 0, kcoord = 0;
+        int entry = 0;        // S2M: index into the (class, tap) schedule
         for (int ks = 0; ks < num_k_steps; ++ks) {
+          if (S2M && cs == 0) {
+            int cls;
+            bool first;
+            s2m_entry(entry, cls, r, s, first);
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* st = smem + stage * L::STAGE_BYTES;
@@ -290,7 +318,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           kcoord += KELEMS;
           if (++cs == p.kslices) {
             cs = 0;
-            if (++s == p.S) { s = 0; ++r; }
+            if (S2M) ++entry;
+            else if (++s == p.S) { s = 0; ++r; }
           }
         }
       }
@@ -360,7 +389,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           if (++cs == p.kslices) { cs = 0; ++r; }
         }
       } else {
+        int entry = 0, cs_m = 0;     // S2M: position in the (class, tap) x channel-slice schedule
         for (int ks = 0; ks < num_k_steps; ++ks) {
+          uint32_t d_cls = d_tmem;   // accumulator of this step's parity class
+          bool cls_first = ks == 0;  // first MMA of that accumulator in this tile
+          if (S2M) {
+            int cls, rr, ss;
+            bool first;
+            s2m_entry(entry, cls, rr, ss, first);
+            d_cls = d_tmem + cls * BLOCK_N;
+            cls_first = first && cs_m == 0;
+            if (++cs_m == p.kslices) { cs_m = 0; ++entry; }
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -372,7 +412,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             for (int j = 0; j < MMAS_PER_STAGE; ++j) {
               const uint64_t da = desc0 + (a16 + 2 * j);
               const uint64_t db = desc0 + (b16 + 2 * j);
-              if (STACK) {
+              if (S2M) {
+                umma_tf32(d_cls, da, db, idesc, (cls_first && j == 0) ? 0u : 1u);
+              } else if (STACK) {
                 umma_f16(d_tmem, da, db, idesc2, (ks | j) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
                 if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
               } else if (SPLIT) {
@@ -416,9 +458,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
       const long long m = static_cast<long long>(m_tile) * kBlockM + row_in_tile;
+      // (S2M: one pass per parity class -- its accumulator, its interleaved quarter of the output)
+#pragma unroll 1
+      for (int cls = 0; cls < NCLS; ++cls) {
+      const bool f_resid_c = S2M ? (f_resid && cls == 0) : f_resid;   // the 1x1 shortcut's quarter
       bool row_ok = m < p.M_total;
       size_t row_off = static_cast<size_t>(m) * p.Cout;
-      if (HALO) {
+      if (S2M) {
+        const int PQ = p.P * p.Q;
+        const int img = static_cast<int>(m / PQ);
+        const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
+        const int oi = rem / p.Q;
+        const int oh = (cls >> 1) + 2 * oi;
+        const int ow = (cls & 1) + 2 * (rem - oi * p.Q);
+        row_ok = row_ok && oh < p.o_H && ow < p.o_W;
+        row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
+      } else if (HALO) {
         // m indexes the padded-width raster: drop the S - 1 pad columns of every image row
         const int Wp = p.Q + p.S - 1;
         const int PWp = p.P * Wp;
@@ -453,14 +508,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       // (hi in .x/.y, lo in .z/.w) or the bits of the BatchNorm-backward y (mutually exclusive).
       auto prefetch = [&](int ch, float4(&pre_r)[8], float4(&pre_m)[8], uint4(&pre_x)[8]) {
         const int c4 = n_tile * BLOCK_N + ch * 32 + 4 * (lane & 7);
-        if (f_resid) {
+        if (f_resid_c) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl)
             pre_r[sl] = row4[sl] != 0xFFFFFFFFu
                             ? *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(row4[sl]) << 2) + c4)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if ((f_resid && f_mask) || f_gate) {
+        if ((f_resid_c && f_mask) || f_gate) {
           const float* src = f_gate ? p.gate : p.mask;
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl)
@@ -485,7 +540,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                             : make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      const uint32_t t_addr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * ACC_COLS + (S2M ? cls * BLOCK_N : 0) +
+                              (static_cast<uint32_t>(quad * 32) << 16);
       auto process = [&](int ch, const float4(&pre_r)[8], const float4(&pre_m)[8],
                          const uint4(&pre_x)[8]) {
         float v[32];
@@ -551,7 +607,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { st_s[k] += o[k]; st_q[k] += o[k] * o[k]; }
               }
-              if (f_resid) {
+              if (f_resid_c) {
                 const float4 r0 = pre_r[sl];
                 float rr[4] = {r0.x, r0.y, r0.z, r0.w};
                 if (f_mask && !f_gate) {
@@ -683,6 +739,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           process(ch, pr, pm, px);
         }
       }
+      }  // parity classes
       // all TMEM reads of this accumulator stage are complete -> hand it back
       tc_fence_before();
       __syncwarp();

@@ -42,10 +42,10 @@ struct ConvMaps {
 constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
-          int EPI_WARPS = 4>
+          int EPI_WARPS = 4, bool S2M = false>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
   using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS, S2M>;
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
   static PerDeviceMax configured;
@@ -258,6 +258,38 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   }
   return set_error("conv: no kernel variant for BLOCK_N=%d split=%d kbytes=%d", block_n,
                    (int)split, kbytes);
+}
+
+int launch_conv_dgrad_s2(const ConvArgs& a, cudaStream_t stream) {
+  if (!a.x || !a.w || !a.out) return set_error("conv_dgrad_s2: null tensor");
+  if (a.Cin % 32 != 0 || a.Cout % 64 != 0)
+    return set_error("conv_dgrad_s2: dY channels %d must be a multiple of 32, dX channels %d of 64", a.Cin, a.Cout);
+  if (a.N <= 0 || a.H <= 0 || a.W <= 0 || a.o_H <= 0 || a.o_W <= 0 || (a.o_H + 1) / 2 != a.H ||
+      (a.o_W + 1) / 2 != a.W)
+    return set_error("conv_dgrad_s2: dY %dx%d does not belong to a stride-2 conv over %dx%d", a.H, a.W, a.o_H, a.o_W);
+  const long long M = 1ll * a.N * a.H * a.W;
+  if (M > 2000000000ll) return set_error("conv_dgrad_s2: too many pixels");
+  ConvParams p = {};
+  p.M_total = (int)M;
+  p.P = a.H; p.Q = a.W;
+  p.Cout = a.Cout; p.Cin = a.Cin; p.R = 2; p.S = 2; p.stride = 1; p.pad_h = 0; p.pad_w = 0;
+  p.num_m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.num_n_tiles = a.Cout / 64;
+  p.kslices = a.Cin / 32;
+  p.out = a.out; p.resid = a.resid; p.gate = a.gate;
+  p.o_step = 2; p.o_H = a.o_H; p.o_W = a.o_W;
+  ConvMaps m;
+  // the 2x2 neighbourhood dY[i..i+1, j..j+1]: taps (r, s) in {0,1}^2, one pixel of upper padding
+  if (make_im2col_map(&m.a, a.x, kF32, a.N, a.H, a.W, a.Cin, 2, 2, 0, 1, 0, 1, 1, 32, kBlockM, 128))
+    return set_error("conv_dgrad_s2: %s", tmap_last_error());
+  if (make_tiled_map_2d(&m.b, a.w, kF32, a.Cout, 9ull * a.Cin, 9ull * a.Cin, 64, 32, 128))
+    return set_error("conv_dgrad_s2: %s", tmap_last_error());
+  m.a_lo = m.a;
+  m.b_lo = m.b;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = device_sm_count();
+  if (tiles < grid) grid = tiles;
+  return launch_variant<64, 128, 6, false, false, false, -1, 4, true>(m, p, grid, stream);
 }
 
 }  // namespace b2n

@@ -74,6 +74,12 @@ struct ConvArgs {
   const int* a_lo_nonzero = nullptr;  // split mode: device flag, 0 => x_l is all zero (skipped)
 };
 int launch_conv(const ConvArgs& a, cudaStream_t stream);
+// Merged stride-2 3x3/pad-1 data gradient (all four output-parity classes in one launch):
+// x = dY [N,H,W,Cin] (H, W: its spatial size; Cin: its channels = the forward conv's Cout),
+// w = b2n_pack_weight_dgrad_s2m pack [Cout][9*Cin], out = dX [N,o_H,o_W,Cout]; resid (optional) is
+// added on the even-even pixels only (the 1x1 shortcut conv's gradient, already in `out`), gate
+// (optional) zeroes dX where it is <= 0.
+int launch_conv_dgrad_s2(const ConvArgs& a, cudaStream_t stream);
 
 // Weight gradient: dw[k][(r*S+s)*Cin + c] += sum_pixels dy[pix][k] * x[pix shifted by tap][c].
 // dw must be zero-initialised by the caller (split-K partial sums are accumulated atomically).
@@ -148,6 +154,7 @@ int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C
 int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,
                       cudaStream_t stream);
 int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream);
+int launch_pack_dgrad_s2m(const float* src, float* dst, int K, int C, cudaStream_t stream);
 int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S, int accumulate,
                         int planes, cudaStream_t stream);
 int launch_linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* b,

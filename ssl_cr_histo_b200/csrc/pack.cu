@@ -70,6 +70,27 @@ __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, float* __restr
     wd[t] = tf32_rn(w[((static_cast<size_t>(k) * C + c) * 3 + r) * 3 + s]);
   }
 }
+// The same nine (class, tap) blocks as ONE K-major matrix [C][9*K] (uniform row pitch): the B
+// operand of the merged stride-2 data-gradient kernel (conv_igemm.cuh, S2M), whose K loop walks the
+// blocks in this order.
+__global__ void pack_dgrad_s2m_kernel(const float* __restrict__ w, float* __restrict__ wd, int K,
+                                      int C) {
+  const size_t total = static_cast<size_t>(9) * C * K;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(t % K);
+    const int e = static_cast<int>((t / K) % 9);
+    const int c = static_cast<int>(t / (static_cast<size_t>(9) * K));
+    const int cls = e < 1 ? 0 : (e < 3 ? 1 : (e < 5 ? 2 : 3));
+    const int tap = e - (cls == 0 ? 0 : (cls == 1 ? 1 : (cls == 2 ? 3 : 5)));
+    const int ph = cls >> 1, pw = cls & 1;
+    const int ns = pw ? 2 : 1;
+    const int a = tap / ns, b = tap - a * ns;
+    const int r = ph ? (a == 0 ? 2 : 0) : 1;
+    const int s = pw ? (b == 0 ? 2 : 0) : 1;
+    wd[t] = tf32_rn(w[((static_cast<size_t>(k) * C + c) * 3 + r) * 3 + s]);
+  }
+}
 // weight-gradient result back to the parameter layout: dw[k][c][r][s] = dwf[k][(r*S+s)*C + c]
 // (accumulate: += into a gradient slot several passes over the same weights feed)
 // planes > 1: dwf holds that many [K][R*S*C] partial planes (deterministic split-K), summed here
@@ -125,6 +146,12 @@ int launch_unpack_wgrad(const float* src, float* dst, int K, int C, int R, int S
   return 0;
 }
 
+int launch_pack_dgrad_s2m(const float* src, float* dst, int K, int C, cudaStream_t stream) {
+  pack_dgrad_s2m_kernel<<<pack_grid(static_cast<size_t>(9) * C * K), 256, 0, stream>>>(src, dst, K, C);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("launch_pack_dgrad_s2m: %s", cudaGetErrorString(e));
+  return 0;
+}
 int launch_pack_dgrad_s2(const float* src, float* dst, int K, int C, cudaStream_t stream) {
   pack_dgrad_s2_kernel<<<pack_grid(static_cast<size_t>(9) * C * K), 256, 0, stream>>>(src, dst, K, C);
   cudaError_t e = cudaGetLastError();

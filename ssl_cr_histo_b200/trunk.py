@@ -104,6 +104,15 @@ def _pack_dgrad_s2(w):
     return out
 
 
+def _pack_dgrad_s2m(w):
+    """The nine (class, tap) blocks of a stride-2 3x3 data gradient as one [C][9*K] matrix: the
+    weight operand of the merged launch (b2n_conv_dgrad_s2)."""
+    K, C = w.shape[0], w.shape[1]
+    out = torch.empty(C, 9 * K, device=w.device, dtype=torch.float32)
+    call("b2n_pack_weight_dgrad_s2m", w, out, K, C)
+    return out
+
+
 def _pack_stem(w):
     out = torch.empty(2, w.shape[0], 16 * STEM_C16, device=w.device, dtype=torch.float16)
     call("b2n_stem_pack_weight", w, out[0], out[1], w.shape[0])
@@ -181,6 +190,9 @@ class ResNet18Trunk(nn.Module):
 # contending for the SMs), so the default keeps the whole step on one stream.
 _SIDE_STREAMS = {}
 OVERLAP_WGRAD = os.environ.get("B2N_OVERLAP_WGRAD", "0") not in ("", "0")
+# Stride-2 data gradients: one merged launch over dY for the four output-parity classes (default),
+# or -- B2N_NO_S2M=1 -- one launch per class (same arithmetic; dY is then read four times).
+MERGED_S2_DGRAD = os.environ.get("B2N_NO_S2M", "0") in ("", "0")
 
 # Weight gradients are split-K sums over pixel slabs.  By default every split stores its own plane
 # and the unpack kernel adds the planes in a fixed order: bit-repeatable gradients for ~20 MB of
@@ -611,11 +623,19 @@ class _TrunkFn(torch.autograd.Function):
                     wdd = packs.get("b%d.wdd" % bi, dconv.weight, _pack_dgrad)
                     _conv(dyd, wdd, N, ph, pw, cout, cin, 1, 1, 0, 0, out=g_in,
                           placement=(2, 0, 0, h, w))
-                    wcls = packs.get("b%d.w1s2" % bi, blk.conv1.weight, _pack_dgrad_s2)
-                    for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
-                        _conv(dy1, wcls[cls], N, ph, pw, cout, cin, 1 + a0, 1, 0, a0, R_w=1 + b0,
-                              pad_hi_w=b0, out=g_in, resid=g_in if cls == 0 else None,
-                              placement=(2, a0, b0, h, w), gate=in_gate)
+                    if MERGED_S2_DGRAD:
+                        wm = packs.get("b%d.w1s2m" % bi, blk.conv1.weight, _pack_dgrad_s2m)
+                        flops = 2.0 * N * ph * pw * cout * cin * 9
+                        call("b2n_conv_dgrad_s2", dy1, wm, g_in, N, ph, pw, cout, cin, h, w, g_in, in_gate,
+                             work=(flops, 0.0, flops, "dgrad",
+                                   4.0 * N * (ph * pw * cout + h * w * cin * (2 if in_gate is not None else 1)
+                                              + ph * pw * cin)))
+                    else:
+                        wcls = packs.get("b%d.w1s2" % bi, blk.conv1.weight, _pack_dgrad_s2)
+                        for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                            _conv(dy1, wcls[cls], N, ph, pw, cout, cin, 1 + a0, 1, 0, a0, R_w=1 + b0,
+                                  pad_hi_w=b0, out=g_in, resid=g_in if cls == 0 else None,
+                                  placement=(2, a0, b0, h, w), gate=in_gate)
             elif need_in:
                 wd1 = packs.get("b%d.w1d" % bi, blk.conv1.weight, _pack_dgrad)
                 # identity shortcut: add the (already gated) upstream gradient in the epilogue

@@ -287,6 +287,19 @@ def test_conv_dgrad_stride2_parity_classes_bit_exact(shape):
                (2, a0, b0, H, W), gate=gate_t)
         off += n
     assert torch.equal(from_nhwc(g_in.cpu()), torch.where(act > 0, ref, torch.zeros(())))
+    # the merged launch: all four classes from one pass over dY (four TMEM accumulators per tile)
+    wm = torch.empty(Cin, 9 * Cout, device=DEV)
+    call("b2n_pack_weight_dgrad_s2m", w3.to(DEV), wm, Cout, Cin)
+    for gate in (None, gate_t):
+        g_in.fill_(float("nan"))
+        launch(to_nhwc(dy1).to(DEV), pack_dgrad(w1), 1, 1, 0, 0, None, (2, 0, 0, H, W))
+        call("b2n_conv_dgrad_s2", d3, wm, g_in, N, P, Q, Cout, Cin, H, W, g_in, gate)
+        want = ref if gate is None else torch.where(act > 0, ref, torch.zeros(()))
+        assert torch.equal(from_nhwc(g_in.cpu()), want), gate is None
+    # without the shortcut term
+    call("b2n_conv_dgrad_s2", d3, wm, g_in, N, P, Q, Cout, Cin, H, W, None, None)
+    assert torch.equal(from_nhwc(g_in.cpu()),
+                       torch.nn.grad.conv2d_input((N, Cin, H, W), w3, dy3, stride=2, padding=1))
 
 
 @pytest.mark.parametrize("size", [(2, 64, 64), (1, 224, 224), (3, 34, 46)])

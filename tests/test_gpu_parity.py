@@ -658,3 +658,28 @@ def test_example_loop_runs_the_whole_pipeline():
     assert history[0][0] != history[-1][0]
     for (k, v), (_, w) in zip(teacher.state_dict().items(), student.state_dict().items()):
         assert torch.equal(v, w), k
+
+
+def test_merged_stride2_data_gradient_equals_the_per_class_launches():
+    """The three stride-2 blocks' data gradients: one merged launch (four accumulators per tile)
+    against the four per-class launches -- same taps in the same order, so the whole backward pass
+    agrees bit for bit."""
+    from ssl_cr_histo_b200 import trunk
+    _, _, gm, gh = pair("finetune", ("finetune", 9))
+    x = O.synthetic_patches(5, 96, seed=120).to(DEV)
+    target = torch.tensor([0, 3, 8, 1, 5], device=DEV)
+
+    def grads():
+        m, c = copy.deepcopy(gm).train(), copy.deepcopy(gh)
+        F.cross_entropy(c(m(x)), target).backward()
+        return [p.grad.clone() for p in m.parameters()]
+
+    assert trunk.MERGED_S2_DGRAD
+    merged = grads()
+    trunk.MERGED_S2_DGRAD = False
+    try:
+        per_class = grads()
+    finally:
+        trunk.MERGED_S2_DGRAD = True
+    for (n, _), a, b in zip(gm.named_parameters(), merged, per_class):
+        assert torch.equal(a, b), n
