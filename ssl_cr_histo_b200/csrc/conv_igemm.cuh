@@ -436,18 +436,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ========================================================= epilogue
-    const bool f_stats = epi_on(EPI, kEpiStats, p.stats != nullptr && p.bnb_y == nullptr);
-    const bool f_affine = epi_on(EPI, kEpiAffine, p.scale != nullptr);
+    const bool f_stats = !S2M && epi_on(EPI, kEpiStats, p.stats != nullptr && p.bnb_y == nullptr);
+    const bool f_affine = !S2M && epi_on(EPI, kEpiAffine, p.scale != nullptr);
     const bool f_resid = epi_on(EPI, kEpiResid32, p.resid != nullptr);
-    const bool f_mask = epi_on(EPI, kEpiMask, p.mask != nullptr);
-    const bool f_resid16 = epi_on(EPI, kEpiResid16, p.resid_h != nullptr);
-    const bool f_relu = epi_on(EPI, kEpiRelu, p.relu != 0);
-    const bool f_out32 = epi_on(EPI, kEpiOut32, p.out != nullptr);
-    const bool f_out16 = epi_on(EPI, kEpiOut16, p.out_h != nullptr);
-    const bool f_round = epi_on(EPI, kEpiRound, p.round_tf32 != 0);
+    const bool f_mask = !S2M && epi_on(EPI, kEpiMask, p.mask != nullptr);
+    const bool f_resid16 = !S2M && epi_on(EPI, kEpiResid16, p.resid_h != nullptr);
+    const bool f_relu = !S2M && epi_on(EPI, kEpiRelu, p.relu != 0);
+    const bool f_out32 = S2M || epi_on(EPI, kEpiOut32, p.out != nullptr);
+    const bool f_out16 = !S2M && epi_on(EPI, kEpiOut16, p.out_h != nullptr);
+    const bool f_round = !S2M && epi_on(EPI, kEpiRound, p.round_tf32 != 0);
     const bool f_gate = epi_on(EPI, kEpiGate, p.gate != nullptr);
-    const bool f_bnb = epi_on(EPI, kEpiBnBwd, p.bnb_y != nullptr);
-    const bool f_bngate = epi_on(EPI, kEpiBnGate, p.bnb_scale != nullptr);
+    const bool f_bnb = !S2M && epi_on(EPI, kEpiBnBwd, p.bnb_y != nullptr);
+    const bool f_bngate = !S2M && epi_on(EPI, kEpiBnGate, p.bnb_scale != nullptr);
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int ew = warp - 2;    // epilogue warp index (its private staging tile / statistics row)
     const int row_in_tile = quad * 32 + lane;
@@ -458,76 +458,79 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
       const long long m = static_cast<long long>(m_tile) * kBlockM + row_in_tile;
-      // (S2M: one pass per parity class -- its accumulator, its interleaved quarter of the output)
-#pragma unroll 1
-      for (int cls = 0; cls < NCLS; ++cls) {
-      const bool f_resid_c = S2M ? (f_resid && cls == 0) : f_resid;   // the 1x1 shortcut's quarter
-      bool row_ok = m < p.M_total;
-      size_t row_off = static_cast<size_t>(m) * p.Cout;
-      if (S2M) {
-        const int PQ = p.P * p.Q;
-        const int img = static_cast<int>(m / PQ);
-        const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
-        const int oi = rem / p.Q;
-        const int oh = (cls >> 1) + 2 * oi;
-        const int ow = (cls & 1) + 2 * (rem - oi * p.Q);
-        row_ok = row_ok && oh < p.o_H && ow < p.o_W;
-        row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
-      } else if (HALO) {
-        // m indexes the padded-width raster: drop the S - 1 pad columns of every image row
-        const int Wp = p.Q + p.S - 1;
-        const int PWp = p.P * Wp;
-        const int img = static_cast<int>(m / PWp);
-        const int rem = static_cast<int>(m - static_cast<long long>(img) * PWp);
-        const int op = rem / Wp;
-        const int oq = rem - op * Wp;
-        row_ok = row_ok && oq < p.Q;
-        row_off = ((static_cast<size_t>(img) * p.P + op) * p.Q + oq) * p.Cout;
-      } else if (p.o_step != 0 && row_ok) {
-        const int PQ = p.P * p.Q;
-        const int img = static_cast<int>(m / PQ);
-        const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
-        const int oi = rem / p.Q;
-        const int oh = p.o_h0 + oi * p.o_step;
-        const int ow = p.o_w0 + (rem - oi * p.Q) * p.o_step;
-        row_ok = oh < p.o_H && ow < p.o_W;
-        row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
-      }
-      // output row start in float4 units (rows are Cout-aligned); all-ones = row not stored
-      const uint32_t my_row4 = row_ok ? static_cast<uint32_t>(row_off >> 2) : 0xFFFFFFFFu;
-      // after the transpose a lane serves row 4*i + (lane >> 3) of half-round h: slot = 4*h + i
-      uint32_t row4[8];
+      // Output rows of this lane's accumulator row, as float4 indices (all-ones = row not stored),
+      // redistributed for the transposed stores: after the transpose a lane serves row
+      // 4*i + (lane >> 3) of half-round h: slot = 4*h + i.  S2M: per parity class `cls` (its
+      // interleaved quarter of the output).
+      auto row_ctx = [&](int cls, uint32_t(&rows)[8]) {
+        bool row_ok = m < p.M_total;
+        size_t row_off = static_cast<size_t>(m) * p.Cout;
+        if (S2M) {
+          const int PQ = p.P * p.Q;
+          const int img = static_cast<int>(m / PQ);
+          const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
+          const int oi = rem / p.Q;
+          const int oh = (cls >> 1) + 2 * oi;
+          const int ow = (cls & 1) + 2 * (rem - oi * p.Q);
+          row_ok = row_ok && oh < p.o_H && ow < p.o_W;
+          row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
+        } else if (HALO) {
+          // m indexes the padded-width raster: drop the S - 1 pad columns of every image row
+          const int Wp = p.Q + p.S - 1;
+          const int PWp = p.P * Wp;
+          const int img = static_cast<int>(m / PWp);
+          const int rem = static_cast<int>(m - static_cast<long long>(img) * PWp);
+          const int op = rem / Wp;
+          const int oq = rem - op * Wp;
+          row_ok = row_ok && oq < p.Q;
+          row_off = ((static_cast<size_t>(img) * p.P + op) * p.Q + oq) * p.Cout;
+        } else if (p.o_step != 0 && row_ok) {
+          const int PQ = p.P * p.Q;
+          const int img = static_cast<int>(m / PQ);
+          const int rem = static_cast<int>(m - static_cast<long long>(img) * PQ);
+          const int oi = rem / p.Q;
+          const int oh = p.o_h0 + oi * p.o_step;
+          const int ow = p.o_w0 + (rem - oi * p.Q) * p.o_step;
+          row_ok = oh < p.o_H && ow < p.o_W;
+          row_off = ((static_cast<size_t>(img) * p.o_H + oh) * p.o_W + ow) * p.Cout;
+        }
+        const uint32_t my_row4 = row_ok ? static_cast<uint32_t>(row_off >> 2) : 0xFFFFFFFFu;
 #pragma unroll
-      for (int sl = 0; sl < 8; ++sl)
-        row4[sl] = __shfl_sync(0xffffffffu, my_row4, (sl >> 2) * 16 + 4 * (sl & 3) + (lane >> 3));
+        for (int sl = 0; sl < 8; ++sl)
+          rows[sl] = __shfl_sync(0xffffffffu, my_row4, (sl >> 2) * 16 + 4 * (sl & 3) + (lane >> 3));
+      };
+      uint32_t row4[8];
+      if (!S2M) row_ctx(0, row4);
       // Residual operands are fetched up front -- eight independent loads per lane and chunk in
       // flight instead of one load -> use -> store round trip per row group (the stores may alias,
       // so the compiler cannot hoist).  64-wide tiles fetch the whole tile *before* waiting for the
       // accumulator, hiding the HBM latency behind the tile's MMAs.
       // pre_m holds the mask or the gate (mutually exclusive), pre_x the FP16 residual pair
       // (hi in .x/.y, lo in .z/.w) or the bits of the BatchNorm-backward y (mutually exclusive).
-      auto prefetch = [&](int ch, float4(&pre_r)[8], float4(&pre_m)[8], uint4(&pre_x)[8]) {
+      // `rows`: row_ctx of the tile (class); `with_resid`: the fp32 shortcut is added to this chunk
+      auto prefetch = [&](const uint32_t(&rows)[8], bool with_resid, int ch, float4(&pre_r)[8],
+                          float4(&pre_m)[8], uint4(&pre_x)[8]) {
         const int c4 = n_tile * BLOCK_N + ch * 32 + 4 * (lane & 7);
-        if (f_resid_c) {
+        if (with_resid) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl)
-            pre_r[sl] = row4[sl] != 0xFFFFFFFFu
-                            ? *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(row4[sl]) << 2) + c4)
+            pre_r[sl] = rows[sl] != 0xFFFFFFFFu
+                            ? *reinterpret_cast<const float4*>(p.resid + (static_cast<size_t>(rows[sl]) << 2) + c4)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if ((f_resid_c && f_mask) || f_gate) {
+        if ((with_resid && f_mask) || f_gate) {
           const float* src = f_gate ? p.gate : p.mask;
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl)
-            pre_m[sl] = row4[sl] != 0xFFFFFFFFu
-                            ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(row4[sl]) << 2) + c4)
+            pre_m[sl] = rows[sl] != 0xFFFFFFFFu
+                            ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(rows[sl]) << 2) + c4)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (f_resid16) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl) {
-            const bool ok = row4[sl] != 0xFFFFFFFFu;
-            const size_t o = (static_cast<size_t>(row4[sl]) << 2) + c4;
+            const bool ok = rows[sl] != 0xFFFFFFFFu;
+            const size_t o = (static_cast<size_t>(rows[sl]) << 2) + c4;
             const uint2 h = ok ? *reinterpret_cast<const uint2*>(p.resid_h + o) : make_uint2(0u, 0u);
             const uint2 l = ok ? *reinterpret_cast<const uint2*>(p.resid_l + o) : make_uint2(0u, 0u);
             pre_x[sl] = make_uint4(h.x, h.y, l.x, l.y);
@@ -535,17 +538,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         } else if (f_bnb) {
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl)
-            pre_x[sl] = row4[sl] != 0xFFFFFFFFu
-                            ? *reinterpret_cast<const uint4*>(p.bnb_y + (static_cast<size_t>(row4[sl]) << 2) + c4)
+            pre_x[sl] = rows[sl] != 0xFFFFFFFFu
+                            ? *reinterpret_cast<const uint4*>(p.bnb_y + (static_cast<size_t>(rows[sl]) << 2) + c4)
                             : make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      const uint32_t t_addr = tmem_base + acc * ACC_COLS + (S2M ? cls * BLOCK_N : 0) +
-                              (static_cast<uint32_t>(quad * 32) << 16);
-      auto process = [&](int ch, const float4(&pre_r)[8], const float4(&pre_m)[8],
-                         const uint4(&pre_x)[8]) {
+      const uint32_t t_addr = tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
+      // `taddr`: TMEM address of the accumulator (class) this chunk belongs to
+      auto process = [&](const uint32_t(&rows)[8], bool with_resid, uint32_t taddr, int ch,
+                         const float4(&pre_r)[8], const float4(&pre_m)[8], const uint4(&pre_x)[8]) {
         float v[32];
-        tmem_ld_32x32(t_addr + ch * 32, v);
+        tmem_ld_32x32(taddr + ch * 32, v);
         const int n0 = n_tile * BLOCK_N + ch * 32;
         const int c4 = n0 + 4 * (lane & 7);
         // per-channel constants of the BatchNorm-backward statistics (this lane's four channels)
@@ -560,7 +563,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         if (STACK) {  // second accumulator half: the hi * W_lo products
           float v2[32];
-          tmem_ld_32x32(t_addr + BLOCK_N + ch * 32, v2);
+          tmem_ld_32x32(taddr + BLOCK_N + ch * 32, v2);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += v2[i];
@@ -600,14 +603,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             const int c = lane & 7;
             const float4 t = stg[r * 8 + (c ^ (r & 7))];
             const int sl = (L::SROWS / 4) * h + i;
-            if (row4[sl] != 0xFFFFFFFFu) {
-              const size_t off = (static_cast<size_t>(row4[sl]) << 2) + c4;
+            if (rows[sl] != 0xFFFFFFFFu) {
+              const size_t off = (static_cast<size_t>(rows[sl]) << 2) + c4;
               float o[4] = {t.x, t.y, t.z, t.w};
               if (f_stats) {  // BN batch statistics of the raw conv output
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { st_s[k] += o[k]; st_q[k] += o[k] * o[k]; }
               }
-              if (f_resid_c) {
+              if (with_resid) {
                 const float4 r0 = pre_r[sl];
                 float rr[4] = {r0.x, r0.y, r0.z, r0.w};
                 if (f_mask && !f_gate) {
@@ -693,40 +696,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
       };
-      if constexpr (EPI_WARPS == 8) {
+      if constexpr (S2M) {
+        // four parity classes x two 32-column chunks = eight steps; the gate / shortcut operands of
+        // step st + 1 are fetched while step st is processed (the first ones before the accumulator
+        // wait), each class with its own output rows.  Only class (0,0) carries the 1x1 shortcut.
+        uint32_t rows[2][8];
+        float4 pr[2][8], pm[2][8];
+        uint4 px[2][8];
+        row_ctx(0, rows[0]);
+        prefetch(rows[0], f_resid, 0, pr[0], pm[0], px[0]);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          const int cls = st >> 1, ch = st & 1;
+          if (st + 1 < 8) {
+            const int ncls = (st + 1) >> 1;
+            if (((st + 1) & 1) == 0) row_ctx(ncls, rows[ncls & 1]);
+            prefetch(rows[ncls & 1], f_resid && ncls == 0, (st + 1) & 1, pr[(st + 1) & 1], pm[(st + 1) & 1],
+                     px[(st + 1) & 1]);
+          }
+          process(rows[cls & 1], f_resid && cls == 0, t_addr + cls * BLOCK_N, ch, pr[st & 1], pm[st & 1],
+                  px[st & 1]);
+        }
+      } else if constexpr (EPI_WARPS == 8) {
         // one chunk per warp: warps 2..5 take columns 0..31, warps 6..9 columns 32..63
         const int ch = ew >> 2;
         float4 pr[8], pm[8];
         uint4 px[8];
-        prefetch(ch, pr, pm, px);
+        prefetch(row4, f_resid, ch, pr, pm, px);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        process(ch, pr, pm, px);
+        process(row4, f_resid, t_addr, ch, pr, pm, px);
       } else if constexpr (BLOCK_N == 64 && EPI >= 0) {
         float4 pr0[8], pm0[8], pr1[8], pm1[8];
         uint4 px0[8], px1[8];
-        prefetch(0, pr0, pm0, px0);
-        prefetch(1, pr1, pm1, px1);
+        prefetch(row4, f_resid, 0, pr0, pm0, px0);
+        prefetch(row4, f_resid, 1, pr1, pm1, px1);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        process(0, pr0, pm0, px0);
-        process(1, pr1, pm1, px1);
+        process(row4, f_resid, t_addr, 0, pr0, pm0, px0);
+        process(row4, f_resid, t_addr, 1, pr1, pm1, px1);
       } else if constexpr (EPI >= 0) {
         // wide tiles with a compiled-in epilogue: the operands of chunk 0 are fetched before the
         // accumulator wait and those of chunk ch + 1 while chunk ch is processed
         float4 pr[2][8], pm[2][8];
         uint4 px[2][8];
-        prefetch(0, pr[0], pm[0], px[0]);
+        prefetch(row4, f_resid, 0, pr[0], pm[0], px[0]);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         // (two chunks per iteration so that the buffer index stays a compile-time constant
         // without unrolling all eight chunks of a 256-wide tile)
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 32; ch += 2) {
-          prefetch(ch + 1, pr[1], pm[1], px[1]);
-          process(ch, pr[0], pm[0], px[0]);
-          if (ch + 2 < BLOCK_N / 32) prefetch(ch + 2, pr[0], pm[0], px[0]);
-          process(ch + 1, pr[1], pm[1], px[1]);
+          prefetch(row4, f_resid, ch + 1, pr[1], pm[1], px[1]);
+          process(row4, f_resid, t_addr, ch, pr[0], pm[0], px[0]);
+          if (ch + 2 < BLOCK_N / 32) prefetch(row4, f_resid, ch + 2, pr[0], pm[0], px[0]);
+          process(row4, f_resid, t_addr, ch + 1, pr[1], pm[1], px[1]);
         }
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -735,11 +761,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
           float4 pr[8], pm[8];
           uint4 px[8];
-          prefetch(ch, pr, pm, px);
-          process(ch, pr, pm, px);
+          prefetch(row4, f_resid, ch, pr, pm, px);
+          process(row4, f_resid, t_addr, ch, pr, pm, px);
         }
       }
-      }  // parity classes
       // all TMEM reads of this accumulator stage are complete -> hand it back
       tc_fence_before();
       __syncwarp();
