@@ -35,10 +35,10 @@
 //
 // S2M = true is the merged stride-2 3x3 data gradient: the four output-parity classes of
 // dx[2i+ph, 2j+pw] (1, 2, 2 and 4 taps over the 2x2 neighbourhood dY[i..i+1, j..j+1], see pack.cu)
-// are four accumulators of ONE tile of 128 dY pixels.  The K loop runs over the nine (class, tap)
-// pairs x channel slices, each step one activation box (the tap) and one weight slab, the MMA
-// going to its class's accumulator; the epilogue then stores the four interleaved quarters.
-// dY is read from HBM once instead of once per class (the re-fetches of a tap box hit L2).
+// are four accumulators of ONE tile of 128 dY pixels.  The K loop runs over the four taps x channel
+// slices; a stage holds the tap's activation box and the weight slabs of every class that uses the
+// tap (4, 2, 2, 1), each MMA going to its class's accumulator; the epilogue then stores the four
+// interleaved quarters.  dY is read once instead of once per class and per (class, tap) pair.
 //
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
@@ -135,16 +135,17 @@ __host__ __device__ constexpr bool epi_on(int epi, int bit, bool runtime) {
   return epi >= 0 ? (epi & bit) != 0 : runtime;
 }
 
-// (class, tap) schedule of the merged stride-2 data gradient: entry e in 0..8 belongs to class
-// 0 | 1 1 | 2 2 | 3 3 3 3; within a class the taps are (a, b) = (t / ns, t % ns), ns = 1 + (cls & 1)
-__device__ __forceinline__ void s2m_entry(int e, int& cls, int& r, int& s, bool& first) {
-  cls = e < 1 ? 0 : (e < 3 ? 1 : (e < 5 ? 2 : 3));
-  const int start = cls == 0 ? 0 : (cls == 1 ? 1 : (cls == 2 ? 3 : 5));
-  const int t = e - start;
-  const int ns = 1 + (cls & 1);
-  r = t / ns;
-  s = t - r * ns;
-  first = t == 0;
+// Merged stride-2 data gradient: which parity classes use tap t = 2*r + s of the 2x2 neighbourhood,
+// and where their weight blocks sit in the [C][9*K] pack (block e of class cls, see pack.cu):
+//   tap (0,0): classes 0,1,2,3 (blocks 0,1,3,5)   tap (0,1): classes 1,3 (blocks 2,6)
+//   tap (1,0): classes 2,3 (blocks 4,7)            tap (1,1): class 3 (block 8)
+__device__ __forceinline__ int s2m_tap_users(int t) { return t == 0 ? 4 : (t == 3 ? 1 : 2); }
+__device__ __forceinline__ void s2m_user(int t, int i, int& cls, int& block) {
+  // packed as nibbles, user i of tap t
+  const unsigned cls_tab[4] = {0x3210u, 0x31u, 0x32u, 0x3u};
+  const unsigned blk_tab[4] = {0x5310u, 0x62u, 0x74u, 0x8u};
+  cls = (cls_tab[t] >> (4 * i)) & 0xF;
+  block = (blk_tab[t] >> (4 * i)) & 0xF;
 }
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
@@ -154,7 +155,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
+  // (S2M: a stage holds one activation box and up to four weight slabs -- one per class using the tap)
+  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
   static_assert(EPI_WARPS == 4 || (EPI_WARPS == 8 && BLOCK_N == 64), "8 epilogue warps: one per chunk of a 64-wide tile");
   constexpr int KELEMS = KBYTES / (SPLIT ? 2 : 4);  // fp16 pairs (split) or tf32-in-fp32
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
@@ -197,7 +199,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_k_steps = S2M ? 9 * p.kslices : p.R * p.S * p.kslices;
+  const int num_k_steps = S2M ? 4 * p.kslices : p.R * p.S * p.kslices;
   const bool skip_a_lo = SPLIT && p.a_lo_nonzero != nullptr && *p.a_lo_nonzero == 0;
 
   if (warp == 0 && lane == 0) {
@@ -288,16 +290,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         const int base_h = op * p.stride - p.pad_h;
         // (r, s, channel slice) advance as nested counters: no division per k step
         int r = 0, s = 0, cs = 0, kcoord = 0;
-        int entry = 0;        // S2M: index into the (class, tap) schedule
         for (int ks = 0; ks < num_k_steps; ++ks) {
-          if (S2M && cs == 0) {
-            int cls;
-            bool first;
-            s2m_entry(entry, cls, r, s, first);
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* st = smem + stage * L::STAGE_BYTES;
+            if (S2M) {
+              // tap (r, s): its box once, then the slab of every class that uses it
+              const int t = 2 * r + s;
+              const int users = s2m_tap_users(t);
+              constexpr int SLAB = BLOCK_N * KBYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBlockM * KBYTES + users * SLAB));
+              tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
+                                 static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+              for (int i = 0; i < users; ++i) {
+                int cls, block;
+                s2m_user(t, i, cls, block);
+                tma_load_2d(st + OFF_B + i * SLAB, &map_b, &full_bar[stage],
+                            (block * p.kslices + cs) * KELEMS, n_tile * BLOCK_N);
+              }
+            } else {
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             if (p.a_tiled2d)
               tma_load_2d(st, &map_a, &full_bar[stage], cs * KELEMS, m0);
@@ -312,14 +323,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               if (SPLIT)
                 tma_load_2d(st + OFF_B_LO, &map_b_lo, &full_bar[stage], kcoord, n_tile * BLOCK_N);
             }
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           kcoord += KELEMS;
           if (++cs == p.kslices) {
             cs = 0;
-            if (S2M) ++entry;
-            else if (++s == p.S) { s = 0; ++r; }
+            if (++s == p.S) { s = 0; ++r; }
           }
         }
       }
@@ -389,18 +400,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           if (++cs == p.kslices) { cs = 0; ++r; }
         }
       } else {
-        int entry = 0, cs_m = 0;     // S2M: position in the (class, tap) x channel-slice schedule
+        int tap_m = 0, cs_m = 0;     // S2M: position in the tap x channel-slice schedule
         for (int ks = 0; ks < num_k_steps; ++ks) {
-          uint32_t d_cls = d_tmem;   // accumulator of this step's parity class
-          bool cls_first = ks == 0;  // first MMA of that accumulator in this tile
-          if (S2M) {
-            int cls, rr, ss;
-            bool first;
-            s2m_entry(entry, cls, rr, ss, first);
-            d_cls = d_tmem + cls * BLOCK_N;
-            cls_first = first && cs_m == 0;
-            if (++cs_m == p.kslices) { cs_m = 0; ++entry; }
-          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -408,13 +409,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             const uint32_t b16 =
                 RES_B ? resb16 + ks * (L::PLANES * L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
             const uint32_t bl16 = b16 + (L::B_BYTES >> 4);  // lo tile follows hi in both layouts
+            if (S2M) {
+              // every class starts with tap (0,0), channel slice 0: that MMA overwrites its accumulator
+              const int users = s2m_tap_users(tap_m);
+              const bool first = tap_m == 0 && cs_m == 0;
+              for (int i = 0; i < users; ++i) {
+                int cls, block;
+                s2m_user(tap_m, i, cls, block);
+                const uint32_t bi16 = b16 + i * ((BLOCK_N * KBYTES) >> 4);
+#pragma unroll
+                for (int j = 0; j < MMAS_PER_STAGE; ++j)
+                  umma_tf32(d_tmem + cls * BLOCK_N, desc0 + (a16 + 2 * j), desc0 + (bi16 + 2 * j), idesc,
+                            (first && j == 0) ? 0u : 1u);
+              }
+            } else {
   #pragma unroll
             for (int j = 0; j < MMAS_PER_STAGE; ++j) {
               const uint64_t da = desc0 + (a16 + 2 * j);
               const uint64_t db = desc0 + (b16 + 2 * j);
-              if (S2M) {
-                umma_tf32(d_cls, da, db, idesc, (cls_first && j == 0) ? 0u : 1u);
-              } else if (STACK) {
+              if (STACK) {
                 umma_f16(d_tmem, da, db, idesc2, (ks | j) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
                 if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
               } else if (SPLIT) {
@@ -425,11 +438,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                 umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
               }
             }
+            }
             tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             if (ks == num_k_steps - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (S2M && ++cs_m == p.kslices) { cs_m = 0; ++tap_m; }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -44,7 +44,7 @@ constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
           int EPI_WARPS = 4, bool S2M = false>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
-  using L = ConvSmem<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
+  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
   auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS, S2M>;
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
@@ -289,7 +289,7 @@ int launch_conv_dgrad_s2(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
-  return launch_variant<64, 128, 6, false, false, false, -1, 4, true>(m, p, grid, stream);
+  return launch_variant<64, 128, 4, false, false, false, -1, 4, true>(m, p, grid, stream);
 }
 
 }  // namespace b2n
