@@ -69,7 +69,7 @@ def main(epochs=2, steps_per_epoch=3, batch_size=4, mu=2, image_size=64, lambda_
             if reducer is not None:
                 reducer.all_reduce(average=False)
             optimizer.step()                                                                         # :100
-            history.append((float(loss), float(sup), float(cons)))
+            history.append((float(loss.detach()), float(sup), float(cons)))      # the loop's loss.item()
         weights.teacher_handoff_(model_teacher, model_student)                                       # b2n (:515-516)
         weights.teacher_handoff_(classifier_teacher, classifier_student)
         if rank == 0:
