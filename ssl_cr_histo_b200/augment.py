@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import math
 import random as _random
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
