@@ -62,6 +62,12 @@ class _PackCache:
     def __deepcopy__(self, memo):
         return _PackCache()
 
+    def __getstate__(self):        # torch.save(model): the packs are derived data, never pickled
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
     def invalidate(self):
         self.generation += 1
         self.floor = self.generation

@@ -122,6 +122,18 @@ def test_index_based_freezing_and_deepcopy():
     assert "_packs" not in "".join(student.state_dict().keys())
 
 
+def test_pickled_module_drops_the_packed_weight_cache():
+    import io
+    m = net.TripletNet_Finetune("resnet18")
+    m.model._packs.entries["x"] = (None, torch.zeros(3), 1)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    assert m2.model._packs.entries == {} and m2.model._packs.generation == 1
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
 def test_no_cpu_fallback():
     m, c = net.TripletNet("resnet18"), net.Classifier(768, 6)
     x = torch.zeros(1, 3, 32, 32)
