@@ -55,10 +55,6 @@ int b2n_device_ok(void);
  *           v += resid[..] (fp32; only where mask[..] > 0 if mask); v += resid_h + resid_l (FP16
  *           pair); relu; then y (fp32, TF32-rounded if round_tf32) and / or the (hi, lo) FP16 pair
  *           y_h / y_l are stored.
- * Output placement: o_step == 0 -> dense [N,P,Q,Cout]; otherwise output pixel (i, j) of image n
- * goes to (o_h0 + i*o_step, o_w0 + j*o_step) of an [N,o_H,o_W,Cout] tensor (resid / mask are
- * addressed the same way; pixels outside are dropped) -- the parity classes of a stride-2 data
- * gradient (b2n_pack_weight_dgrad_s2).
  *           then (data-gradient launches, both optional): the result is zeroed where
  *           gate[..] <= 0 (the ReLU gate of the activation this gradient belongs to; addressed like
  *           the output; not together with mask), and -- bnb_y given -- it is treated as the gradient
@@ -66,6 +62,10 @@ int b2n_device_ok(void);
  *           gate fmaf(y, scale, shift) > 0 is applied to g, and stats[0][k] += sum g,
  *           stats[1][k] += sum g * (y - bnb_mean[k]) * bnb_invstd[k] (b2n_bn_bwd_reduce's sums,
  *           taken while the tile is still on chip; dense fp32 result only).
+ * Output placement: o_step == 0 -> dense [N,P,Q,Cout]; otherwise output pixel (i, j) of image n
+ * goes to (o_h0 + i*o_step, o_w0 + j*o_step) of an [N,o_H,o_W,Cout] tensor (resid / mask are
+ * addressed the same way; pixels outside are dropped) -- the parity classes of a stride-2 data
+ * gradient (b2n_pack_weight_dgrad_s2).
  * stats (optional, [2][Cout] doubles, caller-zeroed; not together with scale/shift): += per-channel
  * sum / sum of squares of the raw accumulator -- the BatchNorm batch statistics (without bnb_y).
  * Cout a multiple of 64.
