@@ -51,17 +51,18 @@ int b2n_device_ok(void);
  * Stride-1 same-width convs with Cout = 64 whose packed weights fit in shared memory (layer1's
  * 3x3 convs, the 4x4 stem) run a tap-sharing variant: one activation box per filter row, the
  * horizontal taps read through row-shifted UMMA descriptors (same results, ~3x less L2 traffic).
- * epilogue: v = acc; v = v*scale[k] + shift[k] (scale and shift come as a pair);
+ * epilogue, in this order: v = acc; v = v*scale[k] + shift[k] (scale and shift come as a pair);
  *           v += resid[..] (fp32; only where mask[..] > 0 if mask); v += resid_h + resid_l (FP16
- *           pair); relu; then y (fp32, TF32-rounded if round_tf32) and / or the (hi, lo) FP16 pair
- *           y_h / y_l are stored.
- *           then (data-gradient launches, both optional): the result is zeroed where
- *           gate[..] <= 0 (the ReLU gate of the activation this gradient belongs to; addressed like
- *           the output; not together with mask), and -- bnb_y given -- it is treated as the gradient
- *           g w.r.t. relu(bn(y)) of the BatchNorm whose raw input is bnb_y: with bnb_scale/shift the
- *           gate fmaf(y, scale, shift) > 0 is applied to g, and stats[0][k] += sum g,
+ *           pair); relu;
+ *           (data-gradient launches, both optional) v = 0 where gate[..] <= 0 (the ReLU gate of
+ *           the activation this gradient belongs to; addressed like the output; not together with
+ *           mask); and -- bnb_y given -- v is treated as the gradient g w.r.t. relu(bn(y)) of the
+ *           BatchNorm whose raw input is bnb_y: with bnb_scale/shift the gate
+ *           fmaf(y, scale, shift) > 0 is applied to g, and stats[0][k] += sum g,
  *           stats[1][k] += sum g * (y - bnb_mean[k]) * bnb_invstd[k] (b2n_bn_bwd_reduce's sums,
- *           taken while the tile is still on chip; dense fp32 result only).
+ *           taken while the tile is still on chip; dense fp32 result only);
+ *           finally y (fp32, TF32-rounded if round_tf32) and / or the (hi, lo) FP16 pair
+ *           y_h / y_l are stored.
  * Output placement: o_step == 0 -> dense [N,P,Q,Cout]; otherwise output pixel (i, j) of image n
  * goes to (o_h0 + i*o_step, o_w0 + j*o_step) of an [N,o_H,o_W,Cout] tensor (resid / mask are
  * addressed the same way; pixels outside are dropped) -- the parity classes of a stride-2 data
