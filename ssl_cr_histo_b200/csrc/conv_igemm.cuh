@@ -112,7 +112,9 @@ struct ConvSmem {
   static constexpr int STATS_FLOATS = EPI_WARPS * 2 * STATS_C;
   // per epilogue warp: SROWS rows x 32 floats.  Two 16-row half rounds where shared memory is
   // scarce; the 8-warp (stem) variant stages all 32 rows at once -- one barrier, twice the ILP
-  static constexpr int SROWS = EPI_WARPS == 8 ? 32 : 16;
+  // (the TF32 resident-weight variant -- layer1's data gradients, 147 KB of weights -- has no room
+  // for 8 x 32 staging rows and keeps the two half rounds)
+  static constexpr int SROWS = (EPI_WARPS == 8 && SPLIT) ? 32 : 16;
   static constexpr int STAGING_BYTES = EPI_WARPS * SROWS * 128;
   // stats | staging | barriers | tmem pointer, rounded up to keep the ring 1024-byte aligned
   static constexpr int CTRL_BYTES =

@@ -207,6 +207,16 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     return launch_variant<64, 128, 2, true, true, true>(m, p, grid, stream);
   }
   if (halo == 128) {
+    // layer1's data gradients are epilogue-paced (shortcut / gate / BatchNorm-backward operands, 64
+    // columns per tile): 8 epilogue warps, one per 32-column chunk and lane quadrant, 3 stages
+    if (getenv("B2N_DGRAD_EPI4") == nullptr &&
+        ConvSmem<64, 128, 3, false, true, true, 8>::total(ksteps_full) <= kMaxDynSmem) {
+      if (epi == kDgrad) return launch_variant<64, 128, 3, false, true, true, kDgrad, 8>(m, p, grid, stream);
+      if (epi == kDgradRes) return launch_variant<64, 128, 3, false, true, true, kDgradRes, 8>(m, p, grid, stream);
+      if (epi == kDgradResGate) return launch_variant<64, 128, 3, false, true, true, kDgradResGate, 8>(m, p, grid, stream);
+      if (epi == kDgradBn) return launch_variant<64, 128, 3, false, true, true, kDgradBn, 8>(m, p, grid, stream);
+      if (epi == kDgradResGateBn) return launch_variant<64, 128, 3, false, true, true, kDgradResGateBn, 8>(m, p, grid, stream);
+    }
     if (epi == kDgrad) return launch_variant<64, 128, 4, false, true, true, kDgrad>(m, p, grid, stream);
     if (epi == kDgradRes) return launch_variant<64, 128, 4, false, true, true, kDgradRes>(m, p, grid, stream);
     if (epi == kDgradResGate) return launch_variant<64, 128, 4, false, true, true, kDgradResGate>(m, p, grid, stream);
