@@ -25,43 +25,73 @@ struct GemmArgs {
 constexpr int TN = 64, TK = 16;
 
 // RM = rows of the micro-tile (4: 64 x 64 block tile; 2: 32 x 64, for launches whose 64-row grid
-// would leave most of the 148 SMs idle -- the heads' GEMMs have only 704 x 256..1024 outputs)
+// would leave most of the 148 SMs idle -- the heads' GEMMs have only 704 x 256..1024 outputs).
+// The next K slab is fetched into registers while the current one is multiplied, and the
+// micro-tile operands leave shared memory as one 128-bit (64-bit for RM = 2) load each: rows are
+// padded by 4 floats, which keeps them 16-byte aligned and the slab stores at most 2-way conflicted.
+// Every output is still one fmaf chain over k = 0..K-1, so results do not depend on the tiling.
 template <int RM>
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
   constexpr int TM = 16 * RM;
-  __shared__ float As[TK][TM + 1];
-  __shared__ float Bs[TK][TN + 1];
+  constexpr int NA = (TM * TK) / 256, NB = (TN * TK) / 256;
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Bs[TK][TN + 4];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a 4 x 4 micro-tile
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each an RM x 4 micro-tile
   float acc[RM][4] = {};
   const bool a_kfast = g.sak == 1;  // choose the smem fill order that keeps gmem reads coalesced
   const bool b_kfast = g.sbk == 1;
-  for (int k0 = 0; k0 < g.K; k0 += TK) {
+  float ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < (TM * TK) / 256; ++i) {
+    for (int i = 0; i < NA; ++i) {
       const int e = tid + i * 256;
       const int mm = a_kfast ? e / TK : e % TM;
       const int kk = a_kfast ? e % TK : e / TM;
       const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < g.M && k < g.K) ? g.a[m * g.sam + k * g.sak] : 0.f;
+      ra[i] = (m < g.M && k < g.K) ? __ldg(g.a + m * g.sam + k * g.sak) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < (TN * TK) / 256; ++i) {
+    for (int i = 0; i < NB; ++i) {
       const int e = tid + i * 256;
       const int nn = b_kfast ? e / TK : e % TN;
       const int kk = b_kfast ? e % TK : e / TN;
       const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < g.N && k < g.K) ? g.b[k * g.sbk + n * g.sbn] : 0.f;
+      rb[i] = (n < g.N && k < g.K) ? __ldg(g.b + k * g.sbk + n * g.sbn) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int e = tid + i * 256;
+      As[a_kfast ? e % TK : e / TM][a_kfast ? e / TK : e % TM] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int e = tid + i * 256;
+      Bs[b_kfast ? e % TK : e / TN][b_kfast ? e / TK : e % TN] = rb[i];
     }
     __syncthreads();
+    if (k0 + TK < g.K) fetch(k0 + TK);
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float av[RM], bv[4];
+      if constexpr (RM == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+      } else if constexpr (RM == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(&As[kk][ty * 2]);
+        av[0] = t.x; av[1] = t.y;
+      } else {
 #pragma unroll
-      for (int i = 0; i < RM; ++i) av[i] = As[kk][ty * RM + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+        for (int i = 0; i < RM; ++i) av[i] = As[kk][ty * RM + i];
+      }
+      {
+        const float4 t = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+      }
 #pragma unroll
       for (int i = 0; i < RM; ++i)
 #pragma unroll
