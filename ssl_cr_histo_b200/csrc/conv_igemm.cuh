@@ -99,22 +99,27 @@ constexpr int kBlockM = 128;
 constexpr int kHaloMaxS = 4;                       // widest filter row the HALO variant handles
 constexpr int kHaloRows = kBlockM + kHaloMaxS - 1;  // pixels of the largest HALO activation box
 
-template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI_WARPS = 4>
+// EPI_WARPS epilogue warps in EPI_GROUPS groups: a group owns one TMEM accumulator stage and takes
+// every EPI_GROUPS-th tile of the CTA, EPI_WARPS / EPI_GROUPS warps (4, or 8 for 64-wide tiles)
+// share a tile.  NO_STATS: the launch never takes statistics (merged stride-2 data gradient).
+template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI_WARPS = 4,
+          int EPI_GROUPS = 1, bool NO_STATS = false>
 struct ConvSmem {
   static constexpr int PLANES = SPLIT ? 2 : 1;
+  static constexpr int WPT = EPI_WARPS / EPI_GROUPS;  // epilogue warps per tile
   // HALO boxes hold kBlockM + S - 1 pixels; every plane stays 1024-byte aligned
   static constexpr int A_BYTES = HALO ? (kHaloRows * KBYTES + 1023) / 1024 * 1024 : kBlockM * KBYTES;
   static constexpr int B_BYTES = BLOCK_N * KBYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + (RES_B ? 0 : B_BYTES));
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   // one private [sum | sumsq] row per epilogue warp; resident-weight launches have one N tile
-  static constexpr int STATS_C = RES_B ? BLOCK_N : 512;
+  static constexpr int STATS_C = NO_STATS ? 0 : (RES_B ? BLOCK_N : 512);
   static constexpr int STATS_FLOATS = EPI_WARPS * 2 * STATS_C;
   // per epilogue warp: SROWS rows x 32 floats.  Two 16-row half rounds where shared memory is
   // scarce; the 8-warp (stem) variant stages all 32 rows at once -- one barrier, twice the ILP
   // (the TF32 resident-weight variant -- layer1's data gradients, 147 KB of weights -- has no room
   // for 8 x 32 staging rows and keeps the two half rounds)
-  static constexpr int SROWS = (EPI_WARPS == 8 && SPLIT) ? 32 : 16;
+  static constexpr int SROWS = (WPT == 8 && SPLIT) ? 32 : 16;
   static constexpr int STAGING_BYTES = EPI_WARPS * SROWS * 128;
   // stats | staging | barriers | tmem pointer, rounded up to keep the ring 1024-byte aligned
   static constexpr int CTRL_BYTES =
@@ -151,15 +156,21 @@ __device__ __forceinline__ void s2m_user(int t, int i, int& cls, int& block) {
 }
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
-          int EPI_WARPS = 4, bool S2M = false>
+          int EPI_WARPS = 4, bool S2M = false, int EPI_GROUPS = 1>
 __global__ void __launch_bounds__(conv_threads(EPI_WARPS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
   // (S2M: a stage holds one activation box and up to four weight slabs -- one per class using the tap)
-  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS>;
-  static_assert(EPI_WARPS == 4 || (EPI_WARPS == 8 && BLOCK_N == 64), "8 epilogue warps: one per chunk of a 64-wide tile");
+  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS, EPI_GROUPS, S2M>;
+  // Epilogue-paced launches (64-wide tiles: ~0.5-1.7k tensor-pipe cycles against ~500 epilogue
+  // instructions per warp and tile, latency-bound at ~0.3 IPC per scheduler) run TWO epilogue
+  // groups: group g owns accumulator stage g and takes the CTA's tiles g, g + 2, ..., so two tiles
+  // are drained concurrently and the groups' TMEM / shared / global round trips interleave.
+  constexpr int WPT = L::WPT;
+  static_assert(EPI_GROUPS == 1 || EPI_GROUPS == 2, "one epilogue group per TMEM accumulator stage");
+  static_assert(WPT == 4 || (WPT == 8 && BLOCK_N == 64), "8 epilogue warps per tile: one per chunk of a 64-wide tile");
   constexpr int KELEMS = KBYTES / (SPLIT ? 2 : 4);  // fp16 pairs (split) or tf32-in-fp32
   constexpr int MMAS_PER_STAGE = KBYTES / 32;  // one MMA consumes 32 bytes of K (8 tf32 / 16 f16)
   constexpr uint32_t SWZ = (KBYTES == 128) ? kSwz128 : (KBYTES == 64 ? kSwz64 : kSwz32);
@@ -170,8 +181,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   // of three times per K step -- UMMA operand reads share the SM's 128 B/clk shared-memory port
   // with the TMA writes, and that port, not the tensor pipe, bounds the narrow (N <= 128) tiles.
   constexpr bool STACK = SPLIT && BLOCK_N <= 128;
-  static_assert(!S2M || (!SPLIT && !RES_B && !HALO && EPI < 0 && EPI_WARPS == 4 && BLOCK_N == 64),
-                "merged stride-2 data gradient: TF32, streamed weights, generic epilogue, 64-wide classes");
+  static_assert(!S2M || (!SPLIT && !RES_B && !HALO && WPT == 4 && BLOCK_N == 64 &&
+                         (EPI < 0 || (EPI & ~(kEpiOut32 | kEpiResid32 | kEpiGate)) == 0)),
+                "merged stride-2 data gradient: TF32, streamed weights, 64-wide classes, shortcut / gate epilogue");
   constexpr int NCLS = S2M ? 4 : 1;                        // accumulators (parity classes) per tile
   constexpr int ACC_COLS = S2M ? NCLS * BLOCK_N : (STACK ? 2 * BLOCK_N : BLOCK_N);  // TMEM columns per stage
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
@@ -217,7 +229,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], WPT);  // one arrive per epilogue warp of the group draining the stage
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -469,11 +481,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     const int ew = warp - 2;    // epilogue warp index (its private staging tile / statistics row)
     const int row_in_tile = quad * 32 + lane;
     float4* stg = s_stage + ew * (L::SROWS * 8);
-    int acc = 0;
+    const int grp = EPI_GROUPS == 2 ? ew / WPT : 0;   // epilogue group = the accumulator stage it drains
+    int acc = grp;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += EPI_GROUPS * gridDim.x) {
+      // (resident-weight launches have a single N tile)
+      const int n_tile = RES_B ? 0 : tile % p.num_n_tiles;
+      const int m_tile = RES_B ? tile : tile / p.num_n_tiles;
       const long long m = static_cast<long long>(m_tile) * kBlockM + row_in_tile;
       // Output rows of this lane's accumulator row, as float4 indices (all-ones = row not stored),
       // redistributed for the transposed stores: after the transpose a lane serves row
@@ -586,20 +600,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           for (int i = 0; i < 32; ++i) v[i] += v2[i];
         }
         tmem_ld_wait();
-        // per-channel affine while a thread still owns a whole row of the chunk
+        // per-channel affine (eval-mode BatchNorm fold): applied after the transpose, where a lane
+        // owns four channels -- eight constants per lane instead of sixty-four
+        float a_sc[4] = {1.f, 1.f, 1.f, 1.f}, a_sh[4] = {0.f, 0.f, 0.f, 0.f};
         if (f_affine) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 sc = *reinterpret_cast<const float4*>(p.scale + n0 + 4 * i);
-            v[4 * i] *= sc.x; v[4 * i + 1] *= sc.y; v[4 * i + 2] *= sc.z; v[4 * i + 3] *= sc.w;
-          }
-        }
-        if (f_affine) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 sh = *reinterpret_cast<const float4*>(p.shift + n0 + 4 * i);
-            v[4 * i] += sh.x; v[4 * i + 1] += sh.y; v[4 * i + 2] += sh.z; v[4 * i + 3] += sh.w;
-          }
+          const float4 sc = *reinterpret_cast<const float4*>(p.scale + c4);
+          const float4 sh = *reinterpret_cast<const float4*>(p.shift + c4);
+          a_sc[0] = sc.x; a_sc[1] = sc.y; a_sc[2] = sc.z; a_sc[3] = sc.w;
+          a_sh[0] = sh.x; a_sh[1] = sh.y; a_sh[2] = sh.z; a_sh[3] = sh.w;
         }
         // Transpose through the warp's staging tile (16 rows x 128 B per round, 16-byte chunks
         // XOR-swizzled by row) so that global memory is touched row-major: 8 lanes cover the
@@ -623,6 +631,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             if (rows[sl] != 0xFFFFFFFFu) {
               const size_t off = (static_cast<size_t>(rows[sl]) << 2) + c4;
               float o[4] = {t.x, t.y, t.z, t.w};
+              if (f_affine) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = o[k] * a_sc[k] + a_sh[k];
+              }
               if (f_stats) {  // BN batch statistics of the raw conv output
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { st_s[k] += o[k]; st_q[k] += o[k] * o[k]; }
@@ -736,9 +748,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           process(rows[cls & 1], f_resid && cls == 0, t_addr + cls * BLOCK_N, ch, pr[st & 1], pm[st & 1],
                   px[st & 1]);
         }
-      } else if constexpr (EPI_WARPS == 8) {
-        // one chunk per warp: warps 2..5 take columns 0..31, warps 6..9 columns 32..63
-        const int ch = ew >> 2;
+      } else if constexpr (WPT == 8) {
+        // one chunk per warp: the group's first four warps take columns 0..31, the others 32..63
+        const int ch = (ew % WPT) >> 2;
         float4 pr[8], pm[8];
         uint4 px[8];
         prefetch(row4, f_resid, ch, pr, pm, px);
@@ -786,7 +798,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (EPI_GROUPS == 2) {
+        acc_phase ^= 1;   // the group's next tile lands in the same stage
+      } else if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
     if (f_stats || f_bnb) {
       // epilogue-only named barrier (warps 2..5 = 128 threads), then flush CTA partials
