@@ -46,6 +46,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace b2n {
@@ -102,15 +104,19 @@ constexpr int kHaloRows = kBlockM + kHaloMaxS - 1;  // pixels of the largest HAL
 // EPI_WARPS epilogue warps in EPI_GROUPS groups: a group owns one TMEM accumulator stage and takes
 // every EPI_GROUPS-th tile of the CTA, EPI_WARPS / EPI_GROUPS warps (4, or 8 for 64-wide tiles)
 // share a tile.  NO_STATS: the launch never takes statistics (merged stride-2 data gradient).
+// RPS (HALO only): filter rows per pipeline stage -- a stage then holds RPS activation boxes, so a
+// launch whose K rows are short (the stem: 16 channels) pays the per-stage barrier / commit
+// overhead of its MMA issuer once per tile instead of once per filter row.
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI_WARPS = 4,
-          int EPI_GROUPS = 1, bool NO_STATS = false>
+          int EPI_GROUPS = 1, bool NO_STATS = false, int RPS = 1>
 struct ConvSmem {
   static constexpr int PLANES = SPLIT ? 2 : 1;
   static constexpr int WPT = EPI_WARPS / EPI_GROUPS;  // epilogue warps per tile
   // HALO boxes hold kBlockM + S - 1 pixels; every plane stays 1024-byte aligned
   static constexpr int A_BYTES = HALO ? (kHaloRows * KBYTES + 1023) / 1024 * 1024 : kBlockM * KBYTES;
   static constexpr int B_BYTES = BLOCK_N * KBYTES;
-  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + (RES_B ? 0 : B_BYTES));
+  static constexpr int A_STAGE = RPS * A_BYTES;   // one plane's activation boxes of a stage
+  static constexpr int STAGE_BYTES = PLANES * (A_STAGE + (RES_B ? 0 : B_BYTES));
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   // one private [sum | sumsq] row per epilogue warp; resident-weight launches have one N tile
   static constexpr int STATS_C = NO_STATS ? 0 : (RES_B ? BLOCK_N : 512);
@@ -119,7 +125,7 @@ struct ConvSmem {
   // scarce; the 8-warp (stem) variant stages all 32 rows at once -- one barrier, twice the ILP
   // (the TF32 resident-weight variant -- layer1's data gradients, 147 KB of weights -- has no room
   // for 8 x 32 staging rows and keeps the two half rounds)
-  static constexpr int SROWS = (WPT == 8 && SPLIT) ? 32 : 16;
+  static constexpr int SROWS = (WPT == 8 && SPLIT && EPI_GROUPS == 1) ? 32 : 16;
   static constexpr int STAGING_BYTES = EPI_WARPS * SROWS * 128;
   // stats | staging | barriers | tmem pointer, rounded up to keep the ring 1024-byte aligned
   static constexpr int CTRL_BYTES =
@@ -156,14 +162,15 @@ __device__ __forceinline__ void s2m_user(int t, int i, int& cls, int& block) {
 }
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
-          int EPI_WARPS = 4, bool S2M = false, int EPI_GROUPS = 1>
+          int EPI_WARPS = 4, bool S2M = false, int EPI_GROUPS = 1, int RPS = 1>
 __global__ void __launch_bounds__(conv_threads(EPI_WARPS), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
   // (S2M: a stage holds one activation box and up to four weight slabs -- one per class using the tap)
-  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS, EPI_GROUPS, S2M>;
+  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS, EPI_GROUPS, S2M, RPS>;
+  static_assert(RPS == 1 || HALO, "several filter rows per stage: HALO launches only");
   // Epilogue-paced launches (64-wide tiles: ~0.5-1.7k tensor-pipe cycles against ~500 epilogue
   // instructions per warp and tile, latency-bound at ~0.3 IPC per scheduler) run TWO epilogue
   // groups: group g owns accumulator stage g and takes the CTA's tiles g, g + 2, ..., so two tiles
@@ -188,8 +195,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   constexpr int ACC_COLS = S2M ? NCLS * BLOCK_N : (STACK ? 2 * BLOCK_N : BLOCK_N);  // TMEM columns per stage
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   // streamed stage layout: A_hi | A_lo | B_hi | B_lo   (B part absent when RES_B)
-  constexpr int OFF_A_LO = L::A_BYTES;
-  constexpr int OFF_B = L::PLANES * L::A_BYTES;
+  constexpr int OFF_A_LO = L::A_STAGE;
+  constexpr int OFF_B = L::PLANES * L::A_STAGE;
   constexpr int OFF_B_LO = OFF_B + L::B_BYTES;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
@@ -273,17 +280,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         const int op = rem / Wp;
         const int base_w = (rem - op * Wp) - p.pad_w;
         const int base_h = op - p.pad_h;
-        for (int r = 0; r < p.R; ++r) {
+        for (int r0 = 0; r0 < p.R; r0 += RPS) {   // (R is a multiple of RPS: checked by the launcher)
           for (int cs = 0; cs < p.kslices; ++cs) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
               uint8_t* st = smem + stage * L::STAGE_BYTES;
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img, 0,
-                                 static_cast<uint16_t>(r));
-              if (SPLIT && !skip_a_lo)
-                tma_load_im2col_4d(st + OFF_A_LO, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w,
-                                   base_h, img, 0, static_cast<uint16_t>(r));
+              mbar_arrive_expect_tx(&full_bar[stage], RPS * tx_bytes);
+#pragma unroll
+              for (int i = 0; i < RPS; ++i) {
+                tma_load_im2col_4d(st + i * L::A_BYTES, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h,
+                                   img, 0, static_cast<uint16_t>(r0 + i));
+                if (SPLIT && !skip_a_lo)
+                  tma_load_im2col_4d(st + OFF_A_LO + i * L::A_BYTES, &map_a_lo, &full_bar[stage], cs * KELEMS,
+                                     base_w, base_h, img, 0, static_cast<uint16_t>(r0 + i));
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -361,97 +371,147 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint64_t desc0 = make_smem_desc(0, 16, SBO, SWZ);  // address field filled per MMA
     const uint32_t ring16 = smem_u32(smem) >> 4;             // all offsets in 16-byte units
     const uint32_t resb16 = smem_u32(resb) >> 4;
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
     if (RES_B) mbar_wait(bres_bar, 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      if (HALO) {
-        const int nstages = p.R * p.kslices;
-        int r = 0, cs = 0;
-        for (int si = 0; si < nstages; ++si) {
-          mbar_wait(&full_bar[stage], phase);
+    // A descriptor is (shared high word, low word = base + compile-time offset): one 32-bit add.
+    const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+    const uint32_t desc_lo = static_cast<uint32_t>(desc0);
+    constexpr uint32_t PB16 = L::PLANES * L::B_BYTES >> 4;   // one k step of resident weights
+    if constexpr (HALO) {
+      // The issuing thread's own instruction stream paces these tiles (a 128 x 64 MMA is 32-64
+      // tensor-pipe cycles), so the whole tile loop is compiled per filter width S and with the
+      // lo-plane MMAs in or out: the taps of a filter row and the MMAs of a K row are unrolled
+      // with immediate descriptor offsets, nothing but the barrier waits is decided per stage.
+      const int nstages = (p.R / RPS) * p.kslices;
+      const uint32_t tap_step = static_cast<uint32_t>(p.kslices) * PB16;   // next tap of the same filter row
+      const uint32_t row_step = static_cast<uint32_t>(p.S) * tap_step;     // next filter row
+      auto run = [&](auto ns_tag, auto lo_tag) {
+        constexpr int NS = decltype(ns_tag)::value;
+        constexpr bool WITH_LO = decltype(lo_tag)::value;
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          uint32_t b_row = desc_lo + resb16;   // weights of the stage's first filter row, tap 0, slice 0
+          int cs = 0;
+          for (int si = 0; si < nstages; ++si) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = desc_lo + ring16 + stage * (L::STAGE_BYTES >> 4);
+              uint32_t b_lo = b_row + cs * PB16;
 #pragma unroll
-            for (int s = 0; s < kHaloMaxS; ++s) {
-              if (s >= p.S) break;
-              // tap s = the same box, start address advanced by s pixel rows (KBYTES each).  The
-              // 128B swizzle is a function of the absolute smem address (measured: the shifted
-              // descriptor reads correctly with base_offset = 0, not with base_offset = s).
-              const int ks = (r * p.S + s) * p.kslices + cs;
-              const uint32_t b16 = resb16 + ks * (L::PLANES * L::B_BYTES >> 4);
-              const uint32_t bl16 = b16 + (L::B_BYTES >> 4);
+              for (int i = 0; i < RPS; ++i) {
+                uint32_t b_tap = b_lo;
 #pragma unroll
-              for (int j = 0; j < MMAS_PER_STAGE; ++j) {
-                const uint64_t da = desc0 + (a16 + (KBYTES / 16) * s + 2 * j);
-                const uint64_t db = desc0 + (b16 + 2 * j);
-                const uint32_t accum = (si | s | j) != 0 ? 1u : 0u;
-                if (STACK) {
-                  umma_f16(d_tmem, da, db, idesc2, accum);  // [hi*hi | hi*lo]
-                  if (!skip_a_lo)
-                    umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + (KBYTES / 16) * s + 2 * j), db, idesc, 1u);
-                } else if (SPLIT) {
-                  umma_f16(d_tmem, da, db, idesc, accum);
-                  umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
-                  if (!skip_a_lo)
-                    umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + (KBYTES / 16) * s + 2 * j), db, idesc, 1u);
-                } else {
-                  umma_tf32(d_tmem, da, db, idesc, accum);
+                for (int sx = 0; sx < NS; ++sx) {
+                  // tap sx = the same box, start address advanced by sx pixel rows (KBYTES each).
+                  // The 128B swizzle is a function of the absolute smem address (measured: the
+                  // shifted descriptor reads correctly with base_offset = 0, not base_offset = sx).
+#pragma unroll
+                  for (int j = 0; j < MMAS_PER_STAGE; ++j) {
+                    const uint32_t da = a_lo + i * (L::A_BYTES >> 4) + (KBYTES / 16) * sx + 2 * j;
+                    const uint32_t db = b_tap + 2 * j;
+                    const uint32_t accum = (i | sx | j) != 0 ? 1u : (si != 0 ? 1u : 0u);
+                    if (STACK) {
+                      umma_f16_lh(d_tmem, da, db, desc_hi, idesc2, accum);  // [hi*hi | hi*lo]
+                      if (WITH_LO) umma_f16_lh(d_tmem, da + (OFF_A_LO >> 4), db, desc_hi, idesc, 1u);
+                    } else {
+                      umma_tf32_lh(d_tmem, da, db, desc_hi, idesc, accum);
+                    }
+                  }
+                  b_tap += tap_step;
                 }
+                b_lo += row_step;
               }
+              tc_commit(&empty_bar[stage]);
+              if (si == nstages - 1) tc_commit(&tfull_bar[acc]);
             }
-            tc_commit(&empty_bar[stage]);
-            if (si == nstages - 1) tc_commit(&tfull_bar[acc]);
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++cs == p.kslices) { cs = 0; b_row += RPS * row_step; }
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          if (++cs == p.kslices) { cs = 0; ++r; }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+      };
+      using std::integral_constant;
+      if (SPLIT && !skip_a_lo) {
+        if (p.S == 3) run(integral_constant<int, 3>{}, integral_constant<bool, true>{});
+        else if (p.S == 4) run(integral_constant<int, 4>{}, integral_constant<bool, true>{});
+        else if (p.S == 2) run(integral_constant<int, 2>{}, integral_constant<bool, true>{});
+        else run(integral_constant<int, 1>{}, integral_constant<bool, true>{});
       } else {
+        if (p.S == 3) run(integral_constant<int, 3>{}, integral_constant<bool, false>{});
+        else if (p.S == 4) run(integral_constant<int, 4>{}, integral_constant<bool, false>{});
+        else if (p.S == 2) run(integral_constant<int, 2>{}, integral_constant<bool, false>{});
+        else run(integral_constant<int, 1>{}, integral_constant<bool, false>{});
+      }
+    } else {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        // (descriptors as in the HALO loop: a shared high word, low word = base + immediate)
+        // S2M: the MMAs of tap T (compile time: its users and their accumulators), one channel slice
+        auto issue_s2m = [&](auto tap_tag, uint32_t a_lo, uint32_t b_lo, bool first) {
+          constexpr int T = decltype(tap_tag)::value;
+          constexpr int USERS = T == 0 ? 4 : (T == 3 ? 1 : 2);
+          constexpr unsigned CLS = T == 0 ? 0x3210u : (T == 1 ? 0x31u : (T == 2 ? 0x32u : 0x3u));
+#pragma unroll
+          for (int i = 0; i < USERS; ++i) {
+            const uint32_t cls = (CLS >> (4 * i)) & 0xF;
+#pragma unroll
+            for (int j = 0; j < MMAS_PER_STAGE; ++j)
+              umma_tf32_lh(d_tmem + cls * BLOCK_N, a_lo + 2 * j, b_lo + i * ((BLOCK_N * KBYTES) >> 4) + 2 * j,
+                           desc_hi, idesc, (first && j == 0) ? 0u : 1u);
+          }
+        };
+        auto issue_plain = [&](auto lo_tag, uint32_t a_lo, uint32_t b_lo, bool first) {
+          constexpr bool WITH_LO = decltype(lo_tag)::value;
+#pragma unroll
+          for (int j = 0; j < MMAS_PER_STAGE; ++j) {
+            const uint32_t da = a_lo + 2 * j;
+            const uint32_t db = b_lo + 2 * j;
+            const uint32_t accum = j != 0 ? 1u : (first ? 0u : 1u);
+            if (STACK) {
+              umma_f16_lh(d_tmem, da, db, desc_hi, idesc2, accum);  // [hi*hi | hi*lo]
+              if (WITH_LO) umma_f16_lh(d_tmem, da + (OFF_A_LO >> 4), db, desc_hi, idesc, 1u);
+            } else if (SPLIT) {
+              umma_f16_lh(d_tmem, da, db, desc_hi, idesc, accum);
+              umma_f16_lh(d_tmem, da, db + (L::B_BYTES >> 4), desc_hi, idesc, 1u);  // lo tile follows hi
+              if (WITH_LO) umma_f16_lh(d_tmem, da + (OFF_A_LO >> 4), db, desc_hi, idesc, 1u);
+            } else {
+              umma_tf32_lh(d_tmem, da, db, desc_hi, idesc, accum);
+            }
+          }
+        };
         int tap_m = 0, cs_m = 0;     // S2M: position in the tap x channel-slice schedule
+        uint32_t b_res = desc_lo + resb16;   // RES_B: weights of k step ks
         for (int ks = 0; ks < num_k_steps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
-            const uint32_t b16 =
-                RES_B ? resb16 + ks * (L::PLANES * L::B_BYTES >> 4) : a16 + (OFF_B >> 4);
-            const uint32_t bl16 = b16 + (L::B_BYTES >> 4);  // lo tile follows hi in both layouts
+            const uint32_t a_lo = desc_lo + ring16 + stage * (L::STAGE_BYTES >> 4);
+            const uint32_t b_lo = RES_B ? b_res : a_lo + (OFF_B >> 4);
+            using std::integral_constant;
             if (S2M) {
               // every class starts with tap (0,0), channel slice 0: that MMA overwrites its accumulator
-              const int users = s2m_tap_users(tap_m);
               const bool first = tap_m == 0 && cs_m == 0;
-              for (int i = 0; i < users; ++i) {
-                int cls, block;
-                s2m_user(tap_m, i, cls, block);
-                const uint32_t bi16 = b16 + i * ((BLOCK_N * KBYTES) >> 4);
-#pragma unroll
-                for (int j = 0; j < MMAS_PER_STAGE; ++j)
-                  umma_tf32(d_tmem + cls * BLOCK_N, desc0 + (a16 + 2 * j), desc0 + (bi16 + 2 * j), idesc,
-                            (first && j == 0) ? 0u : 1u);
-              }
+              if (tap_m == 0) issue_s2m(integral_constant<int, 0>{}, a_lo, b_lo, first);
+              else if (tap_m == 1) issue_s2m(integral_constant<int, 1>{}, a_lo, b_lo, false);
+              else if (tap_m == 2) issue_s2m(integral_constant<int, 2>{}, a_lo, b_lo, false);
+              else issue_s2m(integral_constant<int, 3>{}, a_lo, b_lo, false);
+            } else if (SPLIT && !skip_a_lo) {
+              issue_plain(integral_constant<bool, true>{}, a_lo, b_lo, ks == 0);
             } else {
-  #pragma unroll
-            for (int j = 0; j < MMAS_PER_STAGE; ++j) {
-              const uint64_t da = desc0 + (a16 + 2 * j);
-              const uint64_t db = desc0 + (b16 + 2 * j);
-              if (STACK) {
-                umma_f16(d_tmem, da, db, idesc2, (ks | j) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
-                if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
-              } else if (SPLIT) {
-                umma_f16(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
-                umma_f16(d_tmem, da, desc0 + (bl16 + 2 * j), idesc, 1u);
-                if (!skip_a_lo) umma_f16(d_tmem, desc0 + (a16 + (OFF_A_LO >> 4) + 2 * j), db, idesc, 1u);
-              } else {
-                umma_tf32(d_tmem, da, db, idesc, (ks | j) != 0 ? 1u : 0u);
-              }
-            }
+              issue_plain(integral_constant<bool, false>{}, a_lo, b_lo, ks == 0);
             }
             tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             if (ks == num_k_steps - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
@@ -459,9 +519,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (S2M && ++cs_m == p.kslices) { cs_m = 0; ++tap_m; }
+          if (RES_B) b_res += PB16;
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ========================================================= epilogue

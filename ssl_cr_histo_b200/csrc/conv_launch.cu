@@ -41,21 +41,24 @@ struct ConvMaps {
 
 constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
-// Two epilogue groups per CTA (conv_igemm.cuh) for the epilogue-paced 64-wide launches.
-// B2N_EPI_GROUPS is a bit mask of the kernel families that use them (default: all), read per call:
-// 1 = stem forward, 2 = merged stride-2 data gradient, 4 = layer-1 data gradients with shortcut /
-// gate operands, 8 = layer-1 conv2 data gradient (BatchNorm-backward sums).  Results are bit-identical
-// either way except for the order of the per-CTA statistics partials.
+// Two epilogue groups per CTA (conv_igemm.cuh) for the launches whose epilogue paces the tile once
+// the MMA issuer is out of the way.  B2N_EPI_GROUPS is a bit mask of the kernel families that use
+// them (default: both), read per call: 1 = stem forward, 2 = merged stride-2 data gradient.
+// (Measured and not kept: layer-1's data gradients gain nothing from a second group -- their tiles
+// are bound by the shared-memory port -- and the first block's shortcut + gate + BatchNorm-sum
+// epilogue spills at the 168 registers ten warps leave per thread.)  Results are bit-identical
+// either way except for the summation order of the per-CTA statistics partials.
 static int epi_groups_mask() {
   const char* e = getenv("B2N_EPI_GROUPS");
-  return e != nullptr ? atoi(e) : 15;
+  return e != nullptr ? atoi(e) : 3;
 }
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
-          int EPI_WARPS = 4, bool S2M = false, int EPI_GROUPS = 1>
+          int EPI_WARPS = 4, bool S2M = false, int EPI_GROUPS = 1, int RPS = 1>
 static int launch_variant(const ConvMaps& m, const ConvParams& p, int grid, cudaStream_t stream) {
-  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS, EPI_GROUPS, S2M>;
-  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS, S2M, EPI_GROUPS>;
+  using L = ConvSmem<S2M ? 4 * BLOCK_N : BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI_WARPS, EPI_GROUPS, S2M, RPS>;
+  auto kern = conv_igemm_kernel<BLOCK_N, KBYTES, STAGES, SPLIT, RES_B, HALO, EPI, EPI_WARPS, S2M, EPI_GROUPS, RPS>;
+  if (p.R % RPS != 0) return set_error("conv: %d filter rows per stage do not divide R=%d", RPS, p.R);
   const int smem = L::total(p.R * p.S * p.kslices);
   if (smem > kMaxDynSmem) return set_error("conv: %d B of shared memory needed", smem);
   static PerDeviceMax configured;
@@ -219,17 +222,6 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (halo == 128) {
     // layer1's data gradients are epilogue-paced (shortcut / gate / BatchNorm-backward operands, 64
     // columns per tile): 8 epilogue warps, one per 32-column chunk and lane quadrant, 3 stages
-    const int groups = epi_groups_mask();
-    if (getenv("B2N_DGRAD_EPI4") == nullptr && (groups & 4) &&
-        ConvSmem<64, 128, 3, false, true, true, 8, 2>::total(ksteps_full) <= kMaxDynSmem) {
-      // two groups of four warps, each draining every other tile
-      if (epi == kDgradRes) return launch_variant<64, 128, 3, false, true, true, kDgradRes, 8, false, 2>(m, p, grid, stream);
-      if (epi == kDgradResGate) return launch_variant<64, 128, 3, false, true, true, kDgradResGate, 8, false, 2>(m, p, grid, stream);
-      if (epi == kDgradResGateBn) return launch_variant<64, 128, 3, false, true, true, kDgradResGateBn, 8, false, 2>(m, p, grid, stream);
-    }
-    if ((groups & 8) && epi == kDgradBn &&
-        ConvSmem<64, 128, 3, false, true, true, 8, 2>::total(ksteps_full) <= kMaxDynSmem)
-      return launch_variant<64, 128, 3, false, true, true, kDgradBn, 8, false, 2>(m, p, grid, stream);
     if (getenv("B2N_DGRAD_EPI4") == nullptr &&
         ConvSmem<64, 128, 3, false, true, true, 8>::total(ksteps_full) <= kMaxDynSmem) {
       // (measured: 514 -> 448 us and 589 -> 494 us for the shortcut variants; conv2's gradient with
@@ -246,11 +238,18 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     return launch_variant<64, 128, 4, false, true, true>(m, p, grid, stream);
   }
   if (halo == 32 && split) {  // the stem: epilogue-paced, 8 epilogue warps per tile
-    if ((epi_groups_mask() & 1) &&
-        ConvSmem<64, 32, 8, true, true, true, 16, 2>::total(ksteps_full) <= kMaxDynSmem) {
-      // ... in two groups (16 epilogue warps), two tiles drained concurrently
-      if (epi == kTrainFwd) return launch_variant<64, 32, 8, true, true, true, kTrainFwd, 16, false, 2>(m, p, grid, stream);
-      if (epi == kEvalStem) return launch_variant<64, 32, 8, true, true, true, kEvalStem, 16, false, 2>(m, p, grid, stream);
+    // The 4x4 space-to-depth stem: all four filter rows in one pipeline stage (its 16-channel K rows
+    // make a stage of one row only four MMAs, less than the issuer's per-stage overhead), three
+    // stages, and -- B2N_EPI_GROUPS bit 1 -- two epilogue groups of eight warps.
+    const int rps4 = a.R == 4 && getenv("B2N_STEM_RPS1") == nullptr;
+    if (rps4 && (epi_groups_mask() & 1) &&
+        ConvSmem<64, 32, 3, true, true, true, 16, 2, false, 4>::total(ksteps_full) <= kMaxDynSmem) {
+      if (epi == kTrainFwd) return launch_variant<64, 32, 3, true, true, true, kTrainFwd, 16, false, 2, 4>(m, p, grid, stream);
+      if (epi == kEvalStem) return launch_variant<64, 32, 3, true, true, true, kEvalStem, 16, false, 2, 4>(m, p, grid, stream);
+    }
+    if (rps4 && ConvSmem<64, 32, 3, true, true, true, 8, 1, false, 4>::total(ksteps_full) <= kMaxDynSmem) {
+      if (epi == kTrainFwd) return launch_variant<64, 32, 3, true, true, true, kTrainFwd, 8, false, 1, 4>(m, p, grid, stream);
+      if (epi == kEvalStem) return launch_variant<64, 32, 3, true, true, true, kEvalStem, 8, false, 1, 4>(m, p, grid, stream);
     }
     if (epi == kTrainFwd) return launch_variant<64, 32, 8, true, true, true, kTrainFwd, 8>(m, p, grid, stream);
     if (epi == kEvalStem) return launch_variant<64, 32, 8, true, true, true, kEvalStem, 8>(m, p, grid, stream);

@@ -152,19 +152,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x,
       // MN-major: LBO = stride between 32-channel groups (one TMA box), SBO = stride between
       // 4-pixel groups (one swizzle atom); a K=8 step spans two atoms.
       const uint64_t desc0 = make_smem_desc(0, BOX_BYTES, ATOM, kSwz128B32);
-      const uint32_t ring16 = smem_u32(smem) >> 4;
+      // (shared high word, low word = stage base + immediate: see umma_tf32_lh)
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t ring_lo = static_cast<uint32_t>(desc0) + (smem_u32(smem) >> 4);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < num_slabs; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a16 = ring16 + stage * (L::STAGE_BYTES >> 4);
-          const uint32_t b16 = a16 + (L::A_BYTES >> 4);
+          const uint32_t a_lo = ring_lo + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (L::A_BYTES >> 4);
 #pragma unroll
           for (int j = 0; j < PX / 8; ++j)
-            umma_tf32(tmem_base, desc0 + (a16 + j * (2 * ATOM >> 4)), desc0 + (b16 + j * (2 * ATOM >> 4)),
-                      idesc, (it | j) != 0 ? 1u : 0u);
+            umma_tf32_lh(tmem_base, a_lo + j * (2 * ATOM >> 4), b_lo + j * (2 * ATOM >> 4), desc_hi,
+                         idesc, j != 0 ? 1u : (it != 0 ? 1u : 0u));
           tc_commit(&empty_bar[stage]);
           if (it == num_slabs - 1) tc_commit(tfull_bar);
         }

@@ -132,21 +132,30 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x,
       const uint64_t desc_a0 = make_smem_desc(0, 128, ATOM, kSwz128B32);
       // B: two 32-channel dY boxes, group stride = one box
       const uint64_t desc_b0 = make_smem_desc(0, kWhYBox, ATOM, kSwz128B32);
+      // (both descriptors share their high word -- SBO and layout; the leading-dimension strides
+      // live in the low words -- and a descriptor is the stage base + an immediate: see umma_tf32_lh)
+      const uint32_t desc_hi = static_cast<uint32_t>(desc_a0 >> 32);
       const uint32_t ring16 = smem_u32(smem) >> 4;
+      const uint32_t a_ring = static_cast<uint32_t>(desc_a0) + ring16;
+      const uint32_t b_ring = static_cast<uint32_t>(desc_b0) + ring16 + ((NACC * kWhXBox) >> 4);
+      const int nacc = p.nacc;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < num_slabs; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t s16 = ring16 + stage * (L::STAGE_BYTES >> 4);
-          const uint32_t b16 = s16 + ((NACC * kWhXBox) >> 4);
-          for (int a = 0; a < p.nacc; ++a) {
-            const uint32_t a16 = s16 + a * (kWhXBox >> 4);
+          const uint32_t a_lo = a_ring + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_ring + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t acc0 = it != 0 ? 1u : 0u;
 #pragma unroll
-            for (int j = 0; j < kWhPX / 8; ++j)
-              umma_tf32(tmem_base + a * 64, desc_a0 + (a16 + j * (2 * ATOM >> 4)),
-                        desc_b0 + (b16 + j * (2 * ATOM >> 4)), idesc, (it | j) != 0 ? 1u : 0u);
+          for (int a = 0; a < NACC; ++a) {
+            if (a < nacc) {
+#pragma unroll
+              for (int j = 0; j < kWhPX / 8; ++j)
+                umma_tf32_lh(tmem_base + a * 64, a_lo + a * (kWhXBox >> 4) + j * (2 * ATOM >> 4),
+                             b_lo + j * (2 * ATOM >> 4), desc_hi, idesc, j != 0 ? 1u : acc0);
+            }
           }
           tc_commit(&empty_bar[stage]);
           if (it == num_slabs - 1) tc_commit(tfull_bar);

@@ -394,7 +394,7 @@ static int run_tma_batch() {
 static int run_tma_rate() {
   const int N = 32, H = 56, W = 56;  // 32 x 56 x 56 pixels, L2 resident for every row width below
   struct Cfg { int row_bytes, rows; };
-  for (Cfg cfg : {Cfg{128, 64}, Cfg{128, 130}, Cfg{32, 131}}) {
+  for (Cfg cfg : {Cfg{128, 64}, Cfg{128, 130}, Cfg{32, 131}, Cfg{32, 259}, Cfg{32, 515}, Cfg{32, 67}, Cfg{128, 259}}) {
     const int row_bytes = cfg.row_bytes, rows = cfg.rows;
     const int C = row_bytes / 4;  // fp32 channels per pixel == one K row
     const size_t pixels = (size_t)N * H * W;
@@ -403,8 +403,8 @@ static int run_tma_rate() {
     CK(cudaMemset(dx, 0, pixels * C * 4));
     long long* dclk;
     CK(cudaMalloc(&dclk, 148 * 8));
-    for (int depth : {1, 2, 4, 8, 12}) {
-      for (int mode = 0; mode < 2; ++mode) {
+    for (int depth : {1, 2, 4, 8}) {
+      for (int mode = (rows > 256 ? 1 : 0); mode < 2; ++mode) {   // tiled boxes hold at most 256 rows
         CUtensorMap map;
         int rc = mode ? make_im2col_map(&map, dx, kF32, N, H, W, C, 3, 1, 1, 1, 1, 1, 1, C, rows, row_bytes)
                       : make_tiled_map_2d(&map, dx, kF32, pixels, C, C, rows, C, row_bytes);

@@ -216,93 +216,64 @@ __global__ void bn_relu_maxpool_kernel(const float4* __restrict__ y, const float
   }
 }
 
-// Same computation as a bulk-copy pipeline: a persistent block walks bands = (image, pooled row,
-// column part); one thread streams the (up to) three row segments of y the band's windows cover
-// into a slot of a kPoolSlots-deep shared-memory ring with 1-D bulk copies (TMA), kPoolSlots - 1
-// bands ahead of the one being reduced.  (One outstanding band per SM -- the first version of this
-// kernel, whole rows in two slots -- serialises memory latency and transfer: 4.8 TB/s.  Column
-// parts make the slots small enough for a deeper ring.)  Adjacent pooled rows share one y row and
-// adjacent parts one column: those are re-read from L2.
+// Same computation as a bulk-copy pipeline: a persistent block walks pooled rows (n, p); one
+// thread streams the (up to) three rows of y the row's windows cover into a double-buffered
+// shared-memory slot with a single 1-D bulk copy (TMA), so the next row's ~86 KB are in flight
+// while this one is reduced.  Adjacent pooled rows share one y row: it is re-read from L2.
 constexpr int kPoolRowThreads = 512;
-constexpr int kPoolSlots = 4;
 
 __global__ void __launch_bounds__(kPoolRowThreads, 1)
 bn_relu_maxpool_rows_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                             const float* __restrict__ shift, float4* __restrict__ a32,
                             uint2* __restrict__ a_h, uint2* __restrict__ a_l,
-                            uchar4* __restrict__ idx, int N, int H, int W, int P, int Q, int C,
-                            int parts, int qs, int maxcols) {
+                            uchar4* __restrict__ idx, int N, int H, int W, int P, int Q, int C) {
   extern __shared__ uint8_t pool_smem_raw[];
   uint8_t* smem = pool_smem_raw + ((128u - (smem_u32(pool_smem_raw) & 127u)) & 127u);
   const int tid = threadIdx.x;
   const int C4 = C >> 2;
-  const uint32_t seg_bytes = static_cast<uint32_t>(maxcols) * C * 4;  // pitch of one row segment
-  const uint32_t slot_bytes = 3 * seg_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPoolSlots * slot_bytes);
-  const int nbands = N * P * parts;
+  const uint32_t row_bytes = static_cast<uint32_t>(W) * C * 4;
+  const uint32_t slot_bytes = 3 * row_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * slot_bytes);
+  const int nbands = N * P;
   if (tid == 0) {
-    for (int i = 0; i < kPoolSlots; ++i) mbar_init(&full_bar[i], 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
     fence_barrier_init();
   }
   __syncthreads();
-  // band -> (n, p, pooled columns [q0, q1), y rows [h_lo, h_hi], y columns [w_lo, w_hi])
-  struct Band { int n, p, q0, q1, h_lo, h_hi, w_lo, w_hi; };
-  auto decode = [&](int band) {
-    Band b;
-    const int part = band % parts;
-    const int np = band / parts;
-    b.n = np / P;
-    b.p = np - b.n * P;
-    b.q0 = part * qs;
-    b.q1 = b.q0 + qs < Q ? b.q0 + qs : Q;
-    b.h_lo = 2 * b.p - 1 < 0 ? 0 : 2 * b.p - 1;
-    b.h_hi = 2 * b.p + 1 > H - 1 ? H - 1 : 2 * b.p + 1;
-    b.w_lo = 2 * b.q0 - 1 < 0 ? 0 : 2 * b.q0 - 1;
-    b.w_hi = 2 * b.q1 - 1 > W - 1 ? W - 1 : 2 * b.q1 - 1;
-    return b;
-  };
   auto issue = [&](int band, int slot) {
-    const Band b = decode(band);
-    const uint32_t bytes = static_cast<uint32_t>(b.w_hi - b.w_lo + 1) * C * 4;
-    mbar_arrive_expect_tx(&full_bar[slot], static_cast<uint32_t>(b.h_hi - b.h_lo + 1) * bytes);
-    for (int h = b.h_lo; h <= b.h_hi; ++h)
-      bulk_load_1d(smem + slot * slot_bytes + (h - b.h_lo) * seg_bytes,
-                   y + ((static_cast<size_t>(b.n) * H + h) * W + b.w_lo) * C, bytes, &full_bar[slot]);
+    const int n = band / P, p = band - n * P;
+    const int h_lo = 2 * p - 1 < 0 ? 0 : 2 * p - 1;
+    const int h_hi = 2 * p + 1 > H - 1 ? H - 1 : 2 * p + 1;
+    const uint32_t bytes = static_cast<uint32_t>(h_hi - h_lo + 1) * row_bytes;
+    mbar_arrive_expect_tx(&full_bar[slot], bytes);
+    bulk_load_1d(smem + slot * slot_bytes, y + (static_cast<size_t>(n) * H + h_lo) * W * C, bytes,
+                 &full_bar[slot]);
   };
-  if (tid == 0) {
-    for (int j = 0; j < kPoolSlots - 1; ++j) {
-      const long long band = static_cast<long long>(blockIdx.x) + static_cast<long long>(j) * gridDim.x;
-      if (band < nbands) issue(static_cast<int>(band), j);
-    }
-  }
   int k = 0;
+  if (tid == 0 && static_cast<int>(blockIdx.x) < nbands) issue(blockIdx.x, 0);
   for (int band = blockIdx.x; band < nbands; band += gridDim.x, ++k) {
-    const int slot = k % kPoolSlots;
-    // slot (k - 1) % kPoolSlots was released by the __syncthreads that ended the previous iteration
-    if (tid == 0) {
-      const long long ahead = static_cast<long long>(band) + static_cast<long long>(kPoolSlots - 1) * gridDim.x;
-      if (ahead < nbands) issue(static_cast<int>(ahead), (k + kPoolSlots - 1) % kPoolSlots);
-    }
-    mbar_wait(&full_bar[slot], (k / kPoolSlots) & 1);
-    const Band b = decode(band);
+    const int slot = k & 1;
+    if (tid == 0 && band + static_cast<int>(gridDim.x) < nbands) issue(band + gridDim.x, slot ^ 1);
+    mbar_wait(&full_bar[slot], (k >> 1) & 1);
+    const int n = band / P, p = band - n * P;
+    const int h_lo = 2 * p - 1 < 0 ? 0 : 2 * p - 1;
     const float4* ys = reinterpret_cast<const float4*>(smem + slot * slot_bytes);
-    const int nq = b.q1 - b.q0;
-    for (int i = tid; i < nq * C4; i += kPoolRowThreads) {
-      const int qi = i / C4, c4 = i - qi * C4;
-      const int q = b.q0 + qi;
+    for (int i = tid; i < Q * C4; i += kPoolRowThreads) {
+      const int q = i / C4, c4 = i - q * C4;
       const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
       const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
       float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
       unsigned char bi[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int h = 2 * b.p - 1 + r;
+        const int h = 2 * p - 1 + r;
         if (h < 0 || h >= H) continue;
 #pragma unroll
         for (int sx = 0; sx < 3; ++sx) {
           const int w = 2 * q - 1 + sx;
           if (w < 0 || w >= W) continue;
-          const float4 v = ys[((h - b.h_lo) * maxcols + (w - b.w_lo)) * C4 + c4];
+          const float4 v = ys[((h - h_lo) * W + w) * C4 + c4];
           const float z[4] = {fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), fmaxf(fmaf(v.y, sc.y, sh.y), 0.f),
                               fmaxf(fmaf(v.z, sc.z, sh.z), 0.f), fmaxf(fmaf(v.w, sc.w, sh.w), 0.f)};
 #pragma unroll
@@ -310,7 +281,7 @@ bn_relu_maxpool_rows_kernel(const float* __restrict__ y, const float* __restrict
             if (z[kk] > best[kk]) { best[kk] = z[kk]; bi[kk] = static_cast<unsigned char>(r * 3 + sx); }
         }
       }
-      const size_t t = ((static_cast<size_t>(b.n) * P + b.p) * Q + q) * C4 + c4;
+      const size_t t = (static_cast<size_t>(band) * Q) * C4 + i;
       if (a_h != nullptr) {
         uint2 ph, pl;
         __half2* h2 = reinterpret_cast<__half2*>(&ph);
@@ -388,40 +359,27 @@ int launch_bn_relu_maxpool(const float* y, const float* scale, const float* shif
   if (C % 4 != 0) return set_error("bn_relu_maxpool: C %% 4 != 0");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 4);
-  // pipelined variant: the fewest column parts whose kPoolSlots slots of three row segments fit in
-  // shared memory (224-pixel patches: 2 parts of 57 columns, 4 x 43 KB)
-  if ((C * 4) % 16 == 0 && getenv("B2N_NO_POOL_PIPE") == nullptr) {
-    int parts = 1, qs = Q, maxcols = W;
-    size_t smem = 0;
-    for (;; parts *= 2) {
-      qs = (Q + parts - 1) / parts;
-      maxcols = 2 * qs + 1 < W ? 2 * qs + 1 : W;
-      smem = static_cast<size_t>(kPoolSlots) * 3 * maxcols * C * 4 + kPoolSlots * 8 + 128;
-      if (smem <= 200 * 1024 || qs == 1) break;
+  // pipelined variant when two slots of three y rows fit in shared memory
+  const size_t smem = 2 * 3 * static_cast<size_t>(W) * C * 4 + 16 + 128;
+  if ((static_cast<size_t>(W) * C * 4) % 16 == 0 && smem <= 227 * 1024 && getenv("B2N_NO_POOL_PIPE") == nullptr) {
+    static PerDeviceMax configured;
+    int dev;
+    if (smem > 48 * 1024 && configured.needs((int)smem, &dev)) {
+      cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_rows_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return set_error("bn_relu_maxpool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured.set(dev, (int)smem);
     }
-    parts = (Q + qs - 1) / qs;   // no empty parts
-    if (smem <= 227 * 1024) {
-      static PerDeviceMax configured;
-      int dev;
-      if (smem > 48 * 1024 && configured.needs((int)smem, &dev)) {
-        cudaError_t e = cudaFuncSetAttribute(bn_relu_maxpool_rows_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error("bn_relu_maxpool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured.set(dev, (int)smem);
-      }
-      int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-      if (per_sm > 2) per_sm = 2;
-      long long grid = static_cast<long long>(device_sm_count()) * per_sm;
-      const long long nbands = static_cast<long long>(N) * P * parts;
-      if (nbands > 2000000000ll) return set_error("bn_relu_maxpool: too many bands");
-      if (grid > nbands) grid = nbands;
-      bn_relu_maxpool_rows_kernel<<<(unsigned)grid, kPoolRowThreads, smem, stream>>>(
-          y, scale, shift, reinterpret_cast<float4*>(a32), reinterpret_cast<uint2*>(a_h),
-          reinterpret_cast<uint2*>(a_l), reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C, parts, qs, maxcols);
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) return set_error("bn_relu_maxpool: %s", cudaGetErrorString(e));
-      return 0;
-    }
+    int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;
+    int grid = device_sm_count() * per_sm;
+    if (grid > N * P) grid = N * P;
+    bn_relu_maxpool_rows_kernel<<<grid, kPoolRowThreads, smem, stream>>>(
+        y, scale, shift, reinterpret_cast<float4*>(a32), reinterpret_cast<uint2*>(a_h),
+        reinterpret_cast<uint2*>(a_l), reinterpret_cast<uchar4*>(idx), N, H, W, P, Q, C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("bn_relu_maxpool: %s", cudaGetErrorString(e));
+    return 0;
   }
   bn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
       reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a32),
@@ -450,18 +408,16 @@ int launch_maxpool_relu_bwd(const float* ga, const unsigned char* idx, const flo
 // --------------------------------- fused maxpool + ReLU + BatchNorm backward (the stem's tail)
 // The stem's BN output is 1/3 of all conv-output elements of the trunk, so materialising
 // gz = d(maxpool o relu) and then running the generic two-pass BN backward over it costs three
-// extra sweeps of that tensor.  Here gz never exists in memory: a persistent block walks bands =
-// (image, two image rows 2b / 2b+1, column part); for every band one thread issues 1-D bulk copies
-// (TMA) into a slot of a kBandSlots-deep shared-memory ring -- the band's segments of y, and of the
-// pooled gradients and recorded argmax codes of pooled rows b and b+1 (the only rows whose 3x3/s2
-// windows reach the band) -- kBandSlots - 1 bands ahead of the one being swept (a single band in
-// flight per SM serialises memory latency and transfer, see bn_relu_maxpool_rows_kernel).  gz is
-// rebuilt per position from its (at most four) candidate windows in maxpool_relu_bwd_kernel's order:
+// extra sweeps of that tensor.  Here gz never exists in memory: a persistent block walks bands of
+// two image rows (2b, 2b+1); for every band one thread issues three 1-D bulk copies (TMA) into a
+// double-buffered shared-memory slot -- the band of y, and the pooled gradients and recorded
+// argmax codes of pooled rows b and b+1 (the only rows whose 3x3/s2 windows reach the band) --
+// so the next band's ~100 KB are in flight while this one is swept.  gz is rebuilt per position
+// from its (at most four) candidate windows in maxpool_relu_bwd_kernel's order:
 //   reduce: sums[0][c] += sum gz', sums[1][c] += sum gz' * xhat       (gz' = gz * [scale*y+shift > 0])
 //   apply : dy = gamma*invstd*(gz' - sums0/rows - xhat*sums1/rows); dgamma = sums1, dbeta = sums0
 // The reduce pass issues one atomic per channel per block.
 constexpr int kBandThreads = 512;
-constexpr int kBandSlots = 4;
 
 template <bool APPLY, bool ROUND>
 __global__ void __launch_bounds__(kBandThreads, 1)
@@ -471,21 +427,18 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         double* __restrict__ sums, float4* __restrict__ dy, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int N, int H, int W, int P, int Q, int C,
-                        double inv_count, int accumulate, int parts, int wc, int nqmax) {
+                        double inv_count, int accumulate) {
   extern __shared__ uint8_t band_smem_raw[];
   uint8_t* smem = band_smem_raw + ((128u - (smem_u32(band_smem_raw) & 127u)) & 127u);
   const int tid = threadIdx.x;
   const int C4 = C >> 2;
   const int c4 = tid % C4;  // constant per thread: kBandThreads % C4 == 0
   const int HB = (H + 1) >> 1;
-  const int nbands = N * HB * parts;
-  // slot layout: y band [2][wc][C] fp32 | pooled gradients [2][nqmax][C] fp32 | argmax codes
-  // [2][nqmax][C] u8 (wc image columns per part, nqmax pooled columns reach them)
-  const uint32_t y_row = static_cast<uint32_t>(wc) * C * 4, g_row = static_cast<uint32_t>(nqmax) * C * 4,
-                 i_row = static_cast<uint32_t>(nqmax) * C;
-  const uint32_t y_bytes = 2 * y_row, g_bytes = 2 * g_row, i_bytes = 2 * i_row;
-  const uint32_t slot_bytes = y_bytes + g_bytes + i_bytes;  // multiple of 16 (C % 16 == 0, checked)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBandSlots * slot_bytes);
+  const int nbands = N * HB;
+  // slot layout: y band [2][W][C] fp32 | pooled gradients [2][Q][C] fp32 | argmax codes [2][Q][C] u8
+  const uint32_t y_bytes = 2u * W * C * 4, g_bytes = 2u * Q * C * 4, i_bytes = 2u * Q * C;
+  const uint32_t slot_bytes = y_bytes + g_bytes + i_bytes;  // multiple of 16 (C % 4 == 0, checked)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * slot_bytes);
 
   const float4 sc = *reinterpret_cast<const float4*>(scale + 4 * c4);
   const float4 sh = *reinterpret_cast<const float4*>(shift + 4 * c4);
@@ -510,74 +463,44 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
   float4 s1 = make_float4(0, 0, 0, 0), s2 = s1;
 
   if (tid == 0) {
-    for (int i = 0; i < kBandSlots; ++i) mbar_init(&full_bar[i], 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
     fence_barrier_init();
   }
   __syncthreads();
 
-  // band -> image n, row pair hb, image columns [w0, w1), pooled columns [qa, qb]
-  struct Band { int n, hb, w0, w1, qa, qb; };
-  auto decode = [&](int band) {
-    Band b;
-    const int part = band % parts;
-    const int nh = band / parts;
-    b.n = nh / HB;
-    b.hb = nh - b.n * HB;
-    b.w0 = part * wc;
-    b.w1 = b.w0 + wc < W ? b.w0 + wc : W;
-    b.qa = b.w0 >> 1;                       // windows 2q-1 <= w <= 2q+1 of the part's columns
-    b.qb = b.w1 >> 1 < Q - 1 ? b.w1 >> 1 : Q - 1;
-    return b;
-  };
   // one thread streams a band into a slot; rows / pooled rows beyond the image are not copied
   auto issue = [&](int band, int slot) {
-    const Band b = decode(band);
-    const int h0 = 2 * b.hb;
-    const uint32_t rows = h0 + 1 < H ? 2u : 1u, prow = b.hb + 1 < P ? 2u : 1u;
-    const uint32_t yb = static_cast<uint32_t>(b.w1 - b.w0) * C * 4;
-    const uint32_t gb = static_cast<uint32_t>(b.qb - b.qa + 1) * C * 4, ib = gb >> 2;
+    const int n = band / HB, hb = band - n * HB, h0 = 2 * hb;
+    const uint32_t rows = h0 + 1 < H ? 2u : 1u, prow = hb + 1 < P ? 2u : 1u;
     uint8_t* dst = smem + slot * slot_bytes;
-    mbar_arrive_expect_tx(&full_bar[slot], rows * yb + prow * (gb + ib));
-    for (uint32_t r = 0; r < rows; ++r)
-      bulk_load_1d(dst + r * y_row,
-                   reinterpret_cast<const float*>(y) + ((static_cast<size_t>(b.n) * H + h0 + r) * W + b.w0) * C,
-                   yb, &full_bar[slot]);
-    for (uint32_t r = 0; r < prow; ++r) {
-      const size_t po = ((static_cast<size_t>(b.n) * P + b.hb + r) * Q + b.qa) * C;
-      bulk_load_1d(dst + y_bytes + r * g_row, reinterpret_cast<const float*>(ga) + po, gb, &full_bar[slot]);
-      bulk_load_1d(dst + y_bytes + g_bytes + r * i_row, reinterpret_cast<const unsigned char*>(idx) + po, ib,
-                   &full_bar[slot]);
-    }
+    const size_t po = (static_cast<size_t>(n) * P + hb) * Q * C;
+    mbar_arrive_expect_tx(&full_bar[slot], rows * (y_bytes / 2) + prow * (g_bytes / 2) + prow * (i_bytes / 2));
+    bulk_load_1d(dst, reinterpret_cast<const float*>(y) + (static_cast<size_t>(n) * H + h0) * W * C,
+                 rows * (y_bytes / 2), &full_bar[slot]);
+    bulk_load_1d(dst + y_bytes, reinterpret_cast<const float*>(ga) + po, prow * (g_bytes / 2), &full_bar[slot]);
+    bulk_load_1d(dst + y_bytes + g_bytes, reinterpret_cast<const unsigned char*>(idx) + po,
+                 prow * (i_bytes / 2), &full_bar[slot]);
   };
 
-  if (tid == 0) {
-    for (int j = 0; j < kBandSlots - 1; ++j) {
-      const long long band = static_cast<long long>(blockIdx.x) + static_cast<long long>(j) * gridDim.x;
-      if (band < nbands) issue(static_cast<int>(band), j);
-    }
-  }
   int k = 0;
+  if (tid == 0 && static_cast<int>(blockIdx.x) < nbands) issue(blockIdx.x, 0);
   for (int band = blockIdx.x; band < nbands; band += gridDim.x, ++k) {
-    const int slot = k % kBandSlots;
-    // slot (k - 1) % kBandSlots was released by the __syncthreads that ended the previous iteration
-    if (tid == 0) {
-      const long long ahead = static_cast<long long>(band) + static_cast<long long>(kBandSlots - 1) * gridDim.x;
-      if (ahead < nbands) issue(static_cast<int>(ahead), (k + kBandSlots - 1) % kBandSlots);
-    }
-    mbar_wait(&full_bar[slot], (k / kBandSlots) & 1);
-    const Band b = decode(band);
-    const int h0 = 2 * b.hb, hb = b.hb;
-    const int nw = b.w1 - b.w0;
+    const int slot = k & 1;
+    // slot ^ 1 was released by the __syncthreads that ended the previous iteration
+    if (tid == 0 && band + static_cast<int>(gridDim.x) < nbands) issue(band + gridDim.x, slot ^ 1);
+    mbar_wait(&full_bar[slot], (k >> 1) & 1);
+    const int n = band / HB, hb = band - n * HB, h0 = 2 * hb;
     const float4* y_s = reinterpret_cast<const float4*>(smem + slot * slot_bytes);
     const float4* g_s = reinterpret_cast<const float4*>(smem + slot * slot_bytes + y_bytes);
     const uchar4* id_s = reinterpret_cast<const uchar4*>(smem + slot * slot_bytes + y_bytes + g_bytes);
-    const int band_n = (h0 + 1 < H ? 2 : 1) * nw * C4;  // float4 elements of this band
+    const int band_n = (h0 + 1 < H ? 2 : 1) * W * C4;  // float4 elements of this band
+    const size_t t0 = (static_cast<size_t>(n) * H + h0) * W * C4;
 #pragma unroll 2
     for (int i = tid; i < band_n; i += kBandThreads) {
-      const int hh = i / (nw * C4);
-      const int wi = (i - hh * nw * C4) / C4;
-      const int w = b.w0 + wi;
-      const float4 v = y_s[(hh * wc + wi) * C4 + c4];
+      const int hh = i / (W * C4);
+      const int w = (i - hh * W * C4) / C4;
+      const float4 v = y_s[i];
       // branch-free gather over the four candidate windows (pr, q) in maxpool_relu_bwd_kernel's
       // order; candidates that do not exist get a code no recorded argmax can equal
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -588,7 +511,7 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
         const int q = (cand & 1) ? q_hi : q_lo;
         const bool valid = pr <= hh && hb + pr < P && (!(cand & 1) || q_hi != q_lo) && q < Q;
         const int code = valid ? (hh + 1 - 2 * pr) * 3 + (w - (2 * q - 1)) : 254;
-        const int sidx = ((valid ? pr : 0) * nqmax + ((q < Q ? q : Q - 1) - b.qa)) * C4 + c4;
+        const int sidx = ((valid ? pr : 0) * Q + (q < Q ? q : Q - 1)) * C4 + c4;
         const uchar4 id = id_s[sidx];
         const float4 gq = g_s[sidx];
         acc[0] += id.x == code ? gq.x : 0.f;
@@ -607,7 +530,7 @@ pool_bn_bwd_band_kernel(const float4* __restrict__ ga, const uchar4* __restrict_
         float4 o = make_float4(gi.x * (g.x - m1.x - xh.x * m2.x), gi.y * (g.y - m1.y - xh.y * m2.y),
                                gi.z * (g.z - m1.z - xh.z * m2.z), gi.w * (g.w - m1.w - xh.w * m2.w));
         if (ROUND) o = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
-        dy[((static_cast<size_t>(b.n) * H + h0 + hh) * W + w) * C4 + c4] = o;
+        dy[t0 + i] = o;
       } else {
         s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
         s2.x += g.x * xh.x; s2.y += g.y * xh.y; s2.z += g.z * xh.z; s2.w += g.w * xh.w;
@@ -640,20 +563,13 @@ static int launch_band(const float* ga, const unsigned char* idx, const float* y
   if (C % 16 != 0 || kBandThreads % C4 != 0)
     return set_error("pool_bn_bwd: unsupported C=%d", C);
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  // the fewest column parts whose kBandSlots slots fit in shared memory (224-pixel patches: 2 parts
-  // of 56 columns, 4 x 47 KB)
-  int parts = 1, wc = W, nqmax = Q;
-  size_t smem = 0;
-  for (;; parts *= 2) {
-    wc = (W + parts - 1) / parts;
-    nqmax = wc / 2 + 2 < Q ? wc / 2 + 2 : Q;
-    const size_t slot = static_cast<size_t>(2) * wc * C * 4 + static_cast<size_t>(2) * nqmax * C * 5;
-    smem = kBandSlots * slot + kBandSlots * 8 + 128;
-    if (smem <= 200 * 1024 || wc == 1) break;
-  }
-  parts = (W + wc - 1) / wc;   // no empty parts
+  // bulk copies need 16-byte sizes: one image row of y, one pooled row of gradients / codes
+  if ((W * C * 4) % 16 != 0 || (Q * C) % 16 != 0)
+    return set_error("pool_bn_bwd: row sizes must be multiples of 16 bytes (W=%d, C=%d)", W, C);
+  const size_t slot = static_cast<size_t>(2) * W * C * 4 + static_cast<size_t>(2) * Q * C * 5;
+  size_t smem = 2 * slot + 16 + 128;
   if (smem < kBandThreads * 8 * sizeof(float) + 128) smem = kBandThreads * 8 * sizeof(float) + 128;
-  if (smem > 227 * 1024) return set_error("pool_bn_bwd: channel count too large (W=%d, C=%d)", W, C);
+  if (smem > 227 * 1024) return set_error("pool_bn_bwd: image row too wide (W=%d, C=%d)", W, C);
   auto kern = pool_bn_bwd_band_kernel<APPLY, ROUND>;
   static PerDeviceMax configured;
   int dev;
@@ -662,19 +578,17 @@ static int launch_band(const float* ga, const unsigned char* idx, const float* y
     if (e != cudaSuccess) return set_error("pool_bn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured.set(dev, (int)smem);
   }
-  const long long nbands = static_cast<long long>(N) * ((H + 1) / 2) * parts;
-  if (nbands > 2000000000ll) return set_error("pool_bn_bwd: too many bands");
+  const int nbands = N * ((H + 1) / 2);
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
-  long long grid = static_cast<long long>(device_sm_count()) * per_sm;
+  int grid = device_sm_count() * per_sm;
   if (grid > nbands) grid = nbands;
   const double inv_count = 1.0 / (static_cast<double>(N) * H * W);
-  kern<<<(unsigned)grid, kBandThreads, smem, stream>>>(
+  kern<<<grid, kBandThreads, smem, stream>>>(
       reinterpret_cast<const float4*>(ga), reinterpret_cast<const uchar4*>(idx),
       reinterpret_cast<const float4*>(y), scale, shift, mean, invstd, gamma, sums,
-      reinterpret_cast<float4*>(dy), dgamma, dbeta, N, H, W, P, Q, C, inv_count, accumulate, parts, wc,
-      nqmax);
+      reinterpret_cast<float4*>(dy), dgamma, dbeta, N, H, W, P, Q, C, inv_count, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("pool_bn_bwd: %s", cudaGetErrorString(e));
   return 0;

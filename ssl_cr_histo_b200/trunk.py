@@ -206,7 +206,6 @@ MERGED_S2_DGRAD = os.environ.get("B2N_NO_S2M", "0") in ("", "0")
 # set_deterministic(False)) reduces the partial tiles with fp32 atomics into one zeroed plane
 # instead (summation order, hence the last bits, then vary from run to run).
 DETERMINISTIC_WGRAD = os.environ.get("B2N_DETERMINISTIC", "1") not in ("", "0")
-STEM_FUSED_BWD = os.environ.get("B2N_NO_STEM_FUSED", "0") in ("", "0")
 
 
 def set_deterministic(flag: bool) -> None:
@@ -579,12 +578,14 @@ class _TrunkFn(torch.autograd.Function):
             if side is not None and dw is not None:
                 dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
 
-        # The stem's maxpool + ReLU + BN backward runs as band sweeps over the stem output (below;
-        # B2N_NO_STEM_FUSED=1 selects the unfused three-kernel chain).  Its reduction sweep is not
-        # needed at all: xhat at a window's argmax is (a - beta) / gamma of the pooled activation a,
-        # so the first block's data-gradient epilogue takes both sums.
+        # The stem's maxpool + ReLU + BN backward runs as two band sweeps over the stem output (below)
+        # when two double-buffered band slots (2 rows of y + 2 pooled rows of gradients / codes) fit
+        # in shared memory: patches up to ~300 px wide; wider ones take the unfused chain.  Its
+        # reduction sweep is not needed at all: xhat at a window's argmax is (a - beta) / gamma of
+        # the pooled activation a, so the first block's data-gradient epilogue takes both sums.
         H2s, W2s = sv["H"] // 2, sv["W"] // 2
-        stem_fused = min_unit == 0 and STEM_FUSED_BWD
+        q2 = (W2s - 1) // 2 + 1
+        stem_fused = min_unit == 0 and 2 * (2 * W2s * 64 * 4 + 2 * q2 * 64 * 5) + 1024 <= 227 * 1024
         stem_sums_done = False
 
         last = sv["blocks"][-1]
