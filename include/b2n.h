@@ -109,6 +109,13 @@ int b2n_conv_wgrad_planes(int N, int H, int W, int Cin, int Cout, int R, int S, 
 int b2n_pack_weight_fwd(const float* w, b2n_half* w_h, b2n_half* w_l, int K, int C, int R, int S,
                         void* stream);
 int b2n_pack_weight_dgrad(const float* w, float* w_packed, int K, int C, int R, int S, void* stream);
+/* n packs in one launch (64 per launch): HOST arrays of device pointers and shapes, as
+ * b2n_lerp_multi.  kind[i] = 0: b2n_pack_weight_fwd of w[i] into (dst0[i], dst1[i]) = (hi, lo);
+ * 1: b2n_pack_weight_dgrad into dst0[i]; 2: b2n_pack_weight_dgrad_s2m into dst0[i] (3x3 only).
+ * A training step repacks every conv weight of the trunk after its optimizer step
+ * (pretrain_BreastPathQ.py:61): ~40 packs of a few microseconds each. */
+int b2n_pack_weights_multi(const float* const* w, void* const* dst0, void* const* dst1, const int* kind,
+                           const int* K, const int* C, const int* R, const int* S, int n, void* stream);
 /* Stride-2 3x3/pad-1 data gradient by output parity: four stride-1 tap subsets (1, 2, 2, 4 taps)
  * over dY, packs stored back to back [C][ntaps*K] in class order (0,0), (0,1), (1,0), (1,1);
  * 9*C*K floats. */
@@ -159,6 +166,12 @@ int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, 
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                      const float* running_var, float* scale, float* shift, int C, float eps,
                      void* stream);
+/* the same for n layers in one launch (32 per launch; HOST arrays of device pointers, channel
+ * counts and epsilons): all twenty BatchNorm layers of an eval-mode trunk pass */
+int b2n_bn_fold_eval_multi(const float* const* gamma, const float* const* beta,
+                           const float* const* running_mean, const float* const* running_var,
+                           float* const* scale, float* const* shift, const int* C, const float* eps,
+                           int n, void* stream);
 /* v = [relu](scale*y + shift + residual); residual = res32, or res_scale*res32 + res_shift when
  * res_scale is given (downsample-branch BN), or the FP16 pair res_h + res_l (identity shortcut).
  * Outputs, each optional: out32 (fp32, TF32-rounded if round_tf32: the backward pass' operand and

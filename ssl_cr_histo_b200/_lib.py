@@ -23,6 +23,7 @@ _SIGNATURES = {
     "b2n_conv_wgrad": [P, P, P] + [I] * 14,
     "b2n_pack_weight_fwd": [P, P, P, I, I, I, I],
     "b2n_pack_weight_dgrad": [P, P, I, I, I, I],
+    "b2n_pack_weights_multi": [P] * 8 + [I],
     "b2n_pack_weight_dgrad_s2": [P, P, I, I],
     "b2n_pack_weight_dgrad_s2m": [P, P, I, I],
     "b2n_conv_dgrad_s2": [P, P, P, I, I, I, I, I, I, I, P, P],
@@ -33,6 +34,7 @@ _SIGNATURES = {
     "b2n_stem_unpack_wgrad": [P, P, I, I, I],
     "b2n_bn_finalize": [P] * 10 + [I, D, F, F, I],
     "b2n_bn_fold_eval": [P] * 6 + [I, F],
+    "b2n_bn_fold_eval_multi": [P] * 8 + [I],
     "b2n_bn_apply": [P] * 11 + [LL, I, I, I],
     "b2n_bn_bwd_reduce": [P] * 8 + [LL, I],
     "b2n_bn_bwd_apply": [P] * 12 + [LL, I, I, I],

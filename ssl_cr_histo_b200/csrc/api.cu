@@ -98,6 +98,13 @@ int b2n_pack_weight_fwd(const float* w, b2n_half* wp_h, b2n_half* wp_l, int K, i
                         void* stream) {
   return counted(launch_pack_fwd(w, H16(wp_h), H16(wp_l), K, C, R, Sf, S(stream)));
 }
+int b2n_pack_weights_multi(const float* const* w, void* const* dst0, void* const* dst1, const int* kind,
+                           const int* K, const int* C, const int* R, const int* Sf, int n, void* stream) {
+  if (n < 0 || (n > 0 && (!w || !dst0 || !dst1 || !kind || !K || !C || !R || !Sf)))
+    return set_error("b2n_pack_weights_multi: bad args");
+  if (n == 0) return 0;
+  return counted(launch_pack_multi(w, dst0, dst1, kind, K, C, R, Sf, n, S(stream)), (n + 63) / 64);
+}
 int b2n_pack_weight_dgrad(const float* w, float* wp, int K, int C, int R, int Sf, void* stream) {
   return counted(launch_pack_dgrad(w, wp, K, C, R, Sf, S(stream)));
 }
@@ -136,6 +143,15 @@ int b2n_bn_finalize(const double* stats, const float* gamma, const float* beta, 
 int b2n_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                      float* scale, float* shift, int C, float eps, void* stream) {
   return counted(launch_bn_fold_eval(gamma, beta, rm, rv, scale, shift, C, eps, S(stream)));
+}
+int b2n_bn_fold_eval_multi(const float* const* gamma, const float* const* beta, const float* const* rm,
+                           const float* const* rv, float* const* scale, float* const* shift, const int* C,
+                           const float* eps, int n, void* stream) {
+  if (n < 0 || (n > 0 && (!gamma || !beta || !rm || !rv || !scale || !shift || !C || !eps)))
+    return set_error("b2n_bn_fold_eval_multi: bad args");
+  if (n == 0) return 0;
+  return counted(launch_bn_fold_eval_multi(gamma, beta, rm, rv, scale, shift, C, eps, n, S(stream)),
+                 (n + 31) / 32);
 }
 int b2n_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
                  const float* res_scale, const float* res_shift, const b2n_half* res_h,

@@ -55,6 +55,31 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
   shift[c] = beta[c] - rm[c] * sc;
 }
 
+// The same for every BatchNorm layer of a model in one launch (an eval-mode trunk pass folds all
+// twenty): block b of the grid serves 128 channels of the layer that owns it.
+constexpr int kMaxFoldJobs = 32;
+struct FoldJob {
+  const float *gamma, *beta, *rm, *rv;
+  float *scale, *shift;
+  int C;
+  float eps;
+  int block0;
+};
+struct FoldTable {
+  FoldJob job[kMaxFoldJobs];
+  int n;
+};
+__global__ void __launch_bounds__(128) bn_fold_eval_multi_kernel(const __grid_constant__ FoldTable tbl) {
+  int j = 0;
+  while (j + 1 < tbl.n && static_cast<int>(blockIdx.x) >= tbl.job[j + 1].block0) ++j;
+  const FoldJob& q = tbl.job[j];
+  const int c = (blockIdx.x - q.block0) * 128 + threadIdx.x;
+  if (c >= q.C) return;
+  const float sc = q.gamma[c] / sqrtf(q.rv[c] + q.eps);
+  q.scale[c] = sc;
+  q.shift[c] = q.beta[c] - q.rm[c] * sc;
+}
+
 // --------------------------------------------------------------------- apply
 // v = act(scale*y + shift + residual); residual = res32 (identity / raw tensor), or
 // res_scale*res32 + res_shift (the downsample branch's BN), or the (hi, lo) FP16 pair
@@ -194,6 +219,30 @@ int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, 
                                                           eps);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("bn_fold_eval: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int launch_bn_fold_eval_multi(const float* const* gamma, const float* const* beta, const float* const* rm,
+                              const float* const* rv, float* const* scale, float* const* shift,
+                              const int* C, const float* eps, int n, cudaStream_t stream) {
+  for (int base = 0; base < n; base += kMaxFoldJobs) {
+    FoldTable tbl;
+    tbl.n = n - base < kMaxFoldJobs ? n - base : kMaxFoldJobs;
+    int blocks = 0;
+    for (int i = 0; i < tbl.n; ++i) {
+      const int g = base + i;
+      if (!gamma[g] || !beta[g] || !rm[g] || !rv[g] || !scale[g] || !shift[g] || C[g] <= 0)
+        return set_error("bn_fold_eval_multi: bad job %d", g);
+      FoldJob& q = tbl.job[i];
+      q.gamma = gamma[g]; q.beta = beta[g]; q.rm = rm[g]; q.rv = rv[g];
+      q.scale = scale[g]; q.shift = shift[g];
+      q.C = C[g]; q.eps = eps[g]; q.block0 = blocks;
+      blocks += (C[g] + 127) / 128;
+    }
+    bn_fold_eval_multi_kernel<<<blocks, 128, 0, stream>>>(tbl);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("bn_fold_eval_multi: %s", cudaGetErrorString(e));
+  }
   return 0;
 }
 

@@ -106,6 +106,9 @@ int launch_bn_finalize(const double* stats, const float* gamma, const float* bet
                        float* running_mean, float* running_var, float* scale, float* shift,
                        float* mean, float* invstd, float* inv_gamma, int C, double count,
                        float momentum, float eps, int n_updates, cudaStream_t stream);
+int launch_bn_fold_eval_multi(const float* const* gamma, const float* const* beta, const float* const* rm,
+                              const float* const* rv, float* const* scale, float* const* shift,
+                              const int* C, const float* eps, int n, cudaStream_t stream);
 int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                         float* scale, float* shift, int C, float eps, cudaStream_t stream);
 int launch_bn_apply(const float* y, const float* scale, const float* shift, const float* res32,
@@ -149,6 +152,8 @@ int launch_avgpool_fwd(const __half* a_h, const __half* a_l, float* e, int N, in
                        cudaStream_t stream);
 int launch_avgpool_bwd(const float* ge, const float* gate, float* g, int N, int HW, int C,
                        cudaStream_t stream);
+int launch_pack_multi(const float* const* w, void* const* d0, void* const* d1, const int* kind,
+                      const int* K, const int* C, const int* R, const int* S, int n, cudaStream_t stream);
 int launch_pack_fwd(const float* src, __half* dst_h, __half* dst_l, int K, int C, int R, int S,
                     cudaStream_t stream);
 int launch_pack_dgrad(const float* src, float* dst, int K, int C, int R, int S,

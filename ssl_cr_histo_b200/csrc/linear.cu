@@ -202,18 +202,31 @@ int launch_cols_sum(const float* dy, long long ld, float* out, int rows, int wid
   return 0;
 }
 
-// db[o] (+)= sum_n dy[n][o]
-__global__ void colsum_kernel(const float* __restrict__ dy, long long lddy, float* __restrict__ db,
-                              int rows, int out_f, int accumulate) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= out_f) return;
+// db[o] (+)= sum_n dy[n][o].  A block owns 32 columns; its 16 row slices (rows ry, ry + 16, ...)
+// are summed by 16 threads per column and combined in a fixed order: deterministic, and 16 loads
+// in flight per column instead of one serial chain over all rows.
+constexpr int kColsumSlices = 16;
+__global__ void __launch_bounds__(32 * kColsumSlices)
+colsum_kernel(const float* __restrict__ dy, long long lddy, float* __restrict__ db, int rows, int out_f,
+              int accumulate) {
+  __shared__ float part[kColsumSlices][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + cx;
   float acc = 0.f;
-  for (int n = 0; n < rows; ++n) acc += dy[static_cast<size_t>(n) * lddy + o];
-  db[o] = accumulate ? db[o] + acc : acc;
+  if (o < out_f)
+    for (int n = ry; n < rows; n += kColsumSlices) acc += dy[static_cast<size_t>(n) * lddy + o];
+  part[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && o < out_f) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kColsumSlices; ++i) t += part[i][cx];
+    db[o] = accumulate ? db[o] + t : t;
+  }
 }
 int launch_colsum(const float* dy, long long lddy, float* db, int rows, int out_f, int accumulate,
                   cudaStream_t stream) {
-  colsum_kernel<<<(out_f + 127) / 128, 128, 0, stream>>>(dy, lddy, db, rows, out_f, accumulate);
+  colsum_kernel<<<(out_f + 31) / 32, 32 * kColsumSlices, 0, stream>>>(dy, lddy, db, rows, out_f, accumulate);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("colsum: %s", cudaGetErrorString(e));
   return 0;

@@ -72,14 +72,23 @@ class _PackCache:
         self.generation += 1
         self.floor = self.generation
 
-    def get(self, key: str, param: torch.Tensor, maker):
-        tag = (param.data_ptr(), param._version, getattr(param, "_b2n_epoch", 0), _lib.WEIGHT_EPOCH,
-               param.device)
+    @staticmethod
+    def _tag(param: torch.Tensor):
+        return (param.data_ptr(), param._version, getattr(param, "_b2n_epoch", 0), _lib.WEIGHT_EPOCH,
+                param.device)
+
+    def stale(self, key: str, param: torch.Tensor) -> bool:
         hit = self.entries.get(key)
-        if hit is not None and hit[0] == tag and hit[2] >= self.floor:
-            return hit[1]
+        return hit is None or hit[0] != self._tag(param) or hit[2] < self.floor
+
+    def put(self, key: str, param: torch.Tensor, packed) -> None:
+        self.entries[key] = (self._tag(param), packed, self.generation)
+
+    def get(self, key: str, param: torch.Tensor, maker):
+        if not self.stale(key, param):
+            return self.entries[key][1]
         packed = maker(param.detach())
-        self.entries[key] = (tag, packed, self.generation)
+        self.put(key, param, packed)
         return packed
 
 
@@ -123,6 +132,78 @@ def _pack_stem(w):
     out = torch.empty(2, w.shape[0], 16 * STEM_C16, device=w.device, dtype=torch.float16)
     call("b2n_stem_pack_weight", w, out[0], out[1], w.shape[0])
     return out[0], out[1]
+
+
+def _prefill_packs(trunk: "ResNet18Trunk", with_dgrad: bool) -> None:
+    """Build every stale weight pack of the eight blocks in ONE launch (b2n_pack_weights_multi)
+    instead of one 2-8 us kernel per pack as the pass reaches it: a training step repacks all
+    twenty conv weights after its optimizer step (~40 packs with the data-gradient layouts), a
+    graph-captured pass always does.  Same keys / layouts as the lazy ``packs.get`` calls below,
+    which then hit.  (The stem's space-to-depth pack stays a launch of its own.)"""
+    import ctypes
+
+    packs = trunk._packs
+    jobs = []   # (key, weight, kind, value to cache, dst0, dst1)
+
+    def add(key, conv, kind):
+        w = conv.weight
+        if not packs.stale(key, w):
+            return
+        K, C, R, S = w.shape
+        if kind == 0:
+            out = torch.empty(2, K, R * S * C, device=w.device, dtype=torch.float16)
+            jobs.append((key, w, 0, (out[0], out[1]), out[0], out[1]))
+        elif kind == 1:
+            out = torch.empty(C, R * S * K, device=w.device, dtype=torch.float32)
+            jobs.append((key, w, 1, out, out, out))
+        else:
+            out = torch.empty(C, 9 * K, device=w.device, dtype=torch.float32)
+            jobs.append((key, w, 2, out, out, out))
+
+    for bi, blk in enumerate(trunk.blocks()):
+        add("b%d.w1" % bi, blk.conv1, 0)
+        add("b%d.w2" % bi, blk.conv2, 0)
+        if blk.downsample is not None:
+            add("b%d.wd" % bi, blk.downsample[0], 0)
+        if with_dgrad:
+            add("b%d.w2d" % bi, blk.conv2, 1)
+            if blk.downsample is not None:
+                add("b%d.wdd" % bi, blk.downsample[0], 1)
+                if MERGED_S2_DGRAD:
+                    add("b%d.w1s2m" % bi, blk.conv1, 2)
+            else:
+                add("b%d.w1d" % bi, blk.conv1, 1)
+    n = len(jobs)
+    if n == 0:
+        return
+    PtrArr, IntArr = ctypes.c_void_p * n, ctypes.c_int * n
+    call("b2n_pack_weights_multi",
+         PtrArr(*[j[1].data_ptr() for j in jobs]), PtrArr(*[j[4].data_ptr() for j in jobs]),
+         PtrArr(*[j[5].data_ptr() for j in jobs]), IntArr(*[j[2] for j in jobs]),
+         IntArr(*[j[1].shape[0] for j in jobs]), IntArr(*[j[1].shape[1] for j in jobs]),
+         IntArr(*[j[1].shape[2] for j in jobs]), IntArr(*[j[1].shape[3] for j in jobs]), n,
+         device=jobs[0][1].device)
+    for key, w, _kind, value, _d0, _d1 in jobs:
+        packs.put(key, w, value)
+
+
+def _fold_eval_all(bns, bufs) -> None:
+    """Eval mode: fold the running statistics of every BatchNorm layer into its (scale, shift)
+    slot of ``bufs`` in one launch (b2n_bn_fold_eval_multi)."""
+    import ctypes
+
+    n = len(bns)
+    PtrArr, IntArr, FltArr = ctypes.c_void_p * n, ctypes.c_int * n, ctypes.c_float * n
+    offs, o = [], 0
+    for b in bns:
+        offs.append(o)
+        o += b.num_features
+    es = bufs.element_size()
+    call("b2n_bn_fold_eval_multi",
+         PtrArr(*[b.weight.data_ptr() for b in bns]), PtrArr(*[b.bias.data_ptr() for b in bns]),
+         PtrArr(*[b.running_mean.data_ptr() for b in bns]), PtrArr(*[b.running_var.data_ptr() for b in bns]),
+         PtrArr(*[bufs[0].data_ptr() + es * x for x in offs]), PtrArr(*[bufs[1].data_ptr() + es * x for x in offs]),
+         IntArr(*[b.num_features for b in bns]), FltArr(*[b.eps for b in bns]), n, device=bufs.device)
 
 
 class ResNet18Trunk(nn.Module):
@@ -238,9 +319,7 @@ def _bn_affine(bn: nn.BatchNorm2d, training: bool, stats, count, n_updates, bufs
         call("b2n_bn_finalize", stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
              st.scale, st.shift, st.mean, st.invstd, st.inv_gamma, C, float(count), momentum, bn.eps,
              n_updates)
-    else:
-        call("b2n_bn_fold_eval", bn.weight, bn.bias, bn.running_mean, bn.running_var, st.scale,
-             st.shift, C, bn.eps)
+    # (eval mode: the slots were filled for all layers at once, _fold_eval_all)
     return st
 
 
@@ -325,10 +404,13 @@ class _TrunkFn(torch.autograd.Function):
             # pack kernels must be part of the graph, whatever the cache holds.
             packs.invalidate()
             trunk._packs_dirty = False
+        _prefill_packs(trunk, with_dgrad=save and all(ctx.needs_input_grad[4:]))
         bns = trunk.bn_layers()
         total_c = sum(b.num_features for b in bns)
         stats_all = torch.zeros(2 * total_c, device=dev, dtype=torch.float64) if training else None
         bufs = torch.empty(4, total_c, device=dev, dtype=torch.float32)
+        if not training:
+            _fold_eval_all(bns, bufs)    # slot order = bn_layers() order = the next_bn() calls below
         slot = [0]
 
         def next_bn(bn):

@@ -482,6 +482,59 @@ def test_bn_relu_maxpool_forward_backward(shape):
     assert torch.equal(dg_f, dg_ref) and torch.equal(db_f, db_ref)
 
 
+def test_multi_tensor_packs_and_folds_equal_the_single_launches():
+    """b2n_pack_weights_multi / b2n_bn_fold_eval_multi (one launch for all conv weights / BatchNorm
+    layers of a pass) write exactly what the per-tensor entry points write -- also past the 64-job
+    (32-layer) tables of one launch."""
+    import ctypes
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 64, 3, 3), (128, 64, 3, 3), (128, 64, 1, 1), (256, 128, 3, 3), (64, 32, 3, 3)] * 14   # 70 jobs
+    ws, kinds, outs, refs = [], [], [], []
+    for i, (K, C, R, S) in enumerate(shapes):
+        w = (torch.randn(K, C, R, S, generator=g) * 0.05).to(DEV)
+        kind = i % 3 if R == 3 else i % 2
+        ws.append(w)
+        kinds.append(kind)
+        if kind == 0:
+            o, r = (torch.empty(2, K, R * S * C, device=DEV, dtype=torch.float16) for _ in range(2))
+            call("b2n_pack_weight_fwd", w, r[0], r[1], K, C, R, S)
+            outs.append((o[0], o[1]))
+        elif kind == 1:
+            o, r = (torch.empty(C, R * S * K, device=DEV) for _ in range(2))
+            call("b2n_pack_weight_dgrad", w, r, K, C, R, S)
+            outs.append((o, o))
+        else:
+            o, r = (torch.empty(C, 9 * K, device=DEV) for _ in range(2))
+            call("b2n_pack_weight_dgrad_s2m", w, r, K, C)
+            outs.append((o, o))
+        refs.append(r)
+    n = len(ws)
+    PtrArr, IntArr = ctypes.c_void_p * n, ctypes.c_int * n
+    call("b2n_pack_weights_multi", PtrArr(*[w.data_ptr() for w in ws]), PtrArr(*[o[0].data_ptr() for o in outs]),
+         PtrArr(*[o[1].data_ptr() for o in outs]), IntArr(*kinds), IntArr(*[w.shape[0] for w in ws]),
+         IntArr(*[w.shape[1] for w in ws]), IntArr(*[w.shape[2] for w in ws]), IntArr(*[w.shape[3] for w in ws]),
+         n, device=torch.device(DEV))
+    for kind, o, r in zip(kinds, outs, refs):
+        if kind == 0:
+            assert torch.equal(o[0], r[0]) and torch.equal(o[1], r[1])
+        else:
+            assert torch.equal(o[0], r)
+    # BatchNorm folds: 40 layers of mixed widths
+    Cs = [64, 128, 256, 512, 96] * 8
+    n = len(Cs)
+    par = [[(torch.rand(C, generator=g) + 0.5).to(DEV) for C in Cs] for _ in range(4)]   # gamma, beta, rm, rv
+    sc, sh = [torch.empty(C, device=DEV) for C in Cs], [torch.empty(C, device=DEV) for C in Cs]
+    PtrArr, IntArr, FltArr = ctypes.c_void_p * n, ctypes.c_int * n, ctypes.c_float * n
+    eps = [1e-5 if i % 2 else 1e-3 for i in range(n)]
+    call("b2n_bn_fold_eval_multi", *[PtrArr(*[t.data_ptr() for t in ts]) for ts in par],
+         PtrArr(*[t.data_ptr() for t in sc]), PtrArr(*[t.data_ptr() for t in sh]), IntArr(*Cs), FltArr(*eps), n,
+         device=torch.device(DEV))
+    for i, C in enumerate(Cs):
+        rs, rh = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        call("b2n_bn_fold_eval", par[0][i], par[1][i], par[2][i], par[3][i], rs, rh, C, eps[i])
+        assert torch.equal(sc[i], rs) and torch.equal(sh[i], rh)
+
+
 def test_avgpool():
     a = torch.randn(5, 49, 512)
     e = torch.empty(5, 512, device=DEV)
