@@ -554,7 +554,8 @@ def profile_launches(env, eager, resident):
     """Per-launch CUDA events around every b2n_conv_fwd / b2n_conv_dgrad_s2 / b2n_conv_wgrad call of
     two eager steps."""
     from ssl_cr_histo_b200 import _lib
-    _lib.PROFILE = {"b2n_conv_fwd": [], "b2n_conv_dgrad_s2": [], "b2n_conv_wgrad": []}
+    _lib.PROFILE = {"b2n_conv_fwd": [], "b2n_conv_dgrad_s2": [], "b2n_conv_dgrad_s2_sc": [],
+                    "b2n_conv_wgrad": []}
     env.timed(lambda: eager(*resident), 2)
     prof, _lib.PROFILE = _lib.PROFILE, None
     torch.cuda.synchronize()

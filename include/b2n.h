@@ -131,6 +131,13 @@ int b2n_pack_weight_dgrad_s2(const float* w, float* w_packed, int K, int C, void
 int b2n_pack_weight_dgrad_s2m(const float* w, float* w_packed, int K, int C, void* stream);
 int b2n_conv_dgrad_s2(const float* dy, const float* w_packed, float* dx, int N, int P, int Q, int K,
                       int C, int H, int W, const float* resid, const float* gate, void* stream);
+/* The same with the block's 1x1 stride-2 shortcut conv folded in (torchvision BasicBlock.downsample,
+ * tv:100-101): its data gradient only reaches the even-even pixels, so dy_sc [N,P,Q,K] times the
+ * shortcut's b2n_pack_weight_dgrad pack w_sc_packed [C][K] is accumulated into that parity class
+ * inside the kernel -- no separate 1x1 launch and no resid round trip through dx. */
+int b2n_conv_dgrad_s2_sc(const float* dy, const float* w_packed, const float* dy_sc, const float* w_sc_packed,
+                         float* dx, int N, int P, int Q, int K, int C, int H, int W, const float* gate,
+                         void* stream);
 /* accumulate != 0: dw += (several passes over shared weights feed one gradient slot, e.g. the
  * three trunk passes of TripletNet.forward or a flat all-reduce arena). */
 int b2n_unpack_wgrad(const float* dw_packed, float* dw, int K, int C, int R, int S, int accumulate,

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "b2n_pack_weight_dgrad_s2": [P, P, I, I],
     "b2n_pack_weight_dgrad_s2m": [P, P, I, I],
     "b2n_conv_dgrad_s2": [P, P, P, I, I, I, I, I, I, I, P, P],
+    "b2n_conv_dgrad_s2_sc": [P, P, P, P, P, I, I, I, I, I, I, I, P],
     "b2n_unpack_wgrad": [P, P, I, I, I, I, I, I],
     "b2n_stem_pack_input": [P, P, P, P, P, I, I, I],
     "b2n_stem_pack_input_u8": [P, P, P, I, I, I],

@@ -82,6 +82,16 @@ int b2n_conv_dgrad_s2(const float* dy, const float* w_packed, float* dx, int N, 
   a.resid = resid; a.gate = gate;
   return counted(launch_conv_dgrad_s2(a, S(stream)));
 }
+int b2n_conv_dgrad_s2_sc(const float* dy, const float* w_packed, const float* dy_sc, const float* w_sc_packed,
+                         float* dx, int N, int P, int Q, int K, int C, int H, int W, const float* gate,
+                         void* stream) {
+  if (!dy_sc || !w_sc_packed) return set_error("b2n_conv_dgrad_s2_sc: null shortcut operand");
+  ConvArgs a;
+  a.x = dy; a.w = w_packed; a.x2 = dy_sc; a.w2 = w_sc_packed; a.out = dx;
+  a.N = N; a.H = P; a.W = Q; a.Cin = K; a.Cout = C; a.o_H = H; a.o_W = W;
+  a.gate = gate;
+  return counted(launch_conv_dgrad_s2(a, S(stream)));
+}
 int b2n_pack_weight_dgrad_s2m(const float* w, float* wp, int K, int C, void* stream) {
   return counted(launch_pack_dgrad_s2m(w, wp, K, C, S(stream)));
 }

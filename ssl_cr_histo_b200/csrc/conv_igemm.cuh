@@ -37,8 +37,14 @@
 // dx[2i+ph, 2j+pw] (1, 2, 2 and 4 taps over the 2x2 neighbourhood dY[i..i+1, j..j+1], see pack.cu)
 // are four accumulators of ONE tile of 128 dY pixels.  The K loop runs over the four taps x channel
 // slices; a stage holds the tap's activation box and the weight slabs of every class that uses the
-// tap (4, 2, 2, 1), each MMA going to its class's accumulator; the epilogue then stores the four
-// interleaved quarters.  dY is read once instead of once per class and per (class, tap) pair.
+// tap (4, 2, 2, 1).  The accumulators sit in TMEM in the order (0,0), (0,1), (1,1), (1,0), which
+// makes the users of every tap ADJACENT: their slabs are stacked in that order and the tap is ONE
+// MMA of width 256 / 128 / 128 / 64 per K step (the activation tile is fetched once per tap, not
+// once per class -- the shared-memory port bounds 64-wide TF32 MMAs).  An optional fifth "tap" is
+// the block's 1x1 stride-2 shortcut conv: its data gradient only reaches the even-even pixels,
+// i.e. class (0,0), so dY_shortcut x W_shortcut is accumulated into that class from a second pair
+// of tensor maps (no separate launch, no read-modify-write of dx).  The epilogue then stores the
+// four interleaved quarters.  dY is read once instead of once per class and per (class, tap) pair.
 //
 // The same kernel serves forward convs (3x3 s1/s2, 1x1 s2, the space-to-depth stem) and
 // data-gradient convs (flipped/transposed weight pack); replaces the cuDNN calls behind
@@ -88,6 +94,8 @@ struct ConvParams {
   // of image n is stored at (o_h0 + i*o_step, o_w0 + j*o_step) of an [*, o_H, o_W, Cout]
   // tensor; pixels falling outside are dropped.  o_step == 0 selects the dense layout.
   int o_step, o_h0, o_w0, o_H, o_W;
+  int s2m_shortcut;         // S2M: a fifth K block -- dY of the 1x1 shortcut conv (map_a_lo) times its
+                            // weight pack (map_b_lo) -- is accumulated into class (0,0)
   int a_tiled2d;            // experiment: A is a plain [M][Cin] matrix loaded in tiled mode
   const int* a_lo_nonzero;  // split mode: device flag; 0 => the activation lo plane is all zero
                             // (integer-valued images) and its loads / MMAs are skipped
@@ -152,14 +160,15 @@ __host__ __device__ constexpr bool epi_on(int epi, int bit, bool runtime) {
 // and where their weight blocks sit in the [C][9*K] pack (block e of class cls, see pack.cu):
 //   tap (0,0): classes 0,1,2,3 (blocks 0,1,3,5)   tap (0,1): classes 1,3 (blocks 2,6)
 //   tap (1,0): classes 2,3 (blocks 4,7)            tap (1,1): class 3 (block 8)
-__device__ __forceinline__ int s2m_tap_users(int t) { return t == 0 ? 4 : (t == 3 ? 1 : 2); }
-__device__ __forceinline__ void s2m_user(int t, int i, int& cls, int& block) {
-  // packed as nibbles, user i of tap t
-  const unsigned cls_tab[4] = {0x3210u, 0x31u, 0x32u, 0x3u};
-  const unsigned blk_tab[4] = {0x5310u, 0x62u, 0x74u, 0x8u};
-  cls = (cls_tab[t] >> (4 * i)) & 0xF;
-  block = (blk_tab[t] >> (4 * i)) & 0xF;
+// Class cls owns accumulator position cls ^ (cls >> 1) (TMEM order 0, 1, 3, 2); a tap's slabs are
+// loaded in position order: tap 0 -> blocks 0,1,5,3 (columns 0..255), tap 1 -> 2,6 (columns 64..191),
+// tap 2 -> 7,4 (columns 128..255), tap 3 -> 8 (columns 128..191); tap 4 = the shortcut (columns 0..63).
+__device__ __forceinline__ int s2m_tap_users(int t) { return t == 0 ? 4 : ((t == 1 || t == 2) ? 2 : 1); }
+__device__ __forceinline__ int s2m_block(int t, int i) {
+  const unsigned blk_tab[4] = {0x3510u, 0x62u, 0x47u, 0x8u};   // nibble i = block of the tap's i-th slab
+  return (blk_tab[t] >> (4 * i)) & 0xF;
 }
+__host__ __device__ constexpr int s2m_class_pos(int cls) { return cls ^ (cls >> 1); }
 
 template <int BLOCK_N, int KBYTES, int STAGES, bool SPLIT, bool RES_B, bool HALO = false, int EPI = -1,
           int EPI_WARPS = 4, bool S2M = false, int EPI_GROUPS = 1, int RPS = 1>
@@ -220,7 +229,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_k_steps = S2M ? 4 * p.kslices : p.R * p.S * p.kslices;
+  const int num_k_steps = S2M ? (4 + p.s2m_shortcut) * p.kslices : p.R * p.S * p.kslices;
   const bool skip_a_lo = SPLIT && p.a_lo_nonzero != nullptr && *p.a_lo_nonzero == 0;
 
   if (warp == 0 && lane == 0) {
@@ -319,18 +328,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
           if (elect_one()) {
             uint8_t* st = smem + stage * L::STAGE_BYTES;
             if (S2M) {
-              // tap (r, s): its box once, then the slab of every class that uses it
+              // tap (r, s): its box once, then the slabs of the classes that use it, stacked in
+              // accumulator order; t == 4 (r == 2): the 1x1 shortcut's dY tile and weight slab
               const int t = 2 * r + s;
               const int users = s2m_tap_users(t);
               constexpr int SLAB = BLOCK_N * KBYTES;
               mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBlockM * KBYTES + users * SLAB));
-              tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
-                                 static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-              for (int i = 0; i < users; ++i) {
-                int cls, block;
-                s2m_user(t, i, cls, block);
-                tma_load_2d(st + OFF_B + i * SLAB, &map_b, &full_bar[stage],
-                            (block * p.kslices + cs) * KELEMS, n_tile * BLOCK_N);
+              if (t < 4) {
+                tma_load_im2col_4d(st, &map_a, &full_bar[stage], cs * KELEMS, base_w, base_h, img,
+                                   static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+                for (int i = 0; i < users; ++i)
+                  tma_load_2d(st + OFF_B + i * SLAB, &map_b, &full_bar[stage],
+                              (s2m_block(t, i) * p.kslices + cs) * KELEMS, n_tile * BLOCK_N);
+              } else {
+                tma_load_im2col_4d(st, &map_a_lo, &full_bar[stage], cs * KELEMS, base_w, base_h, img, 0, 0);
+                tma_load_2d(st + OFF_B, &map_b_lo, &full_bar[stage], cs * KELEMS, n_tile * BLOCK_N);
               }
             } else {
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -459,19 +471,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         // (descriptors as in the HALO loop: a shared high word, low word = base + immediate)
-        // S2M: the MMAs of tap T (compile time: its users and their accumulators), one channel slice
+        // S2M: tap T of one channel slice = one MMA per K step over the stacked slabs of its users
         auto issue_s2m = [&](auto tap_tag, uint32_t a_lo, uint32_t b_lo, bool first) {
           constexpr int T = decltype(tap_tag)::value;
-          constexpr int USERS = T == 0 ? 4 : (T == 3 ? 1 : 2);
-          constexpr unsigned CLS = T == 0 ? 0x3210u : (T == 1 ? 0x31u : (T == 2 ? 0x32u : 0x3u));
+          constexpr uint32_t COL = (T == 0 || T == 4) ? 0 : (T == 1 ? BLOCK_N : 2 * BLOCK_N);   // first accumulator
+          constexpr uint32_t WIDTH = T == 0 ? 4 * BLOCK_N : ((T == 1 || T == 2) ? 2 * BLOCK_N : BLOCK_N);
+          constexpr uint32_t idesc_t = make_idesc_tf32(kBlockM, WIDTH, 0, 0);
 #pragma unroll
-          for (int i = 0; i < USERS; ++i) {
-            const uint32_t cls = (CLS >> (4 * i)) & 0xF;
-#pragma unroll
-            for (int j = 0; j < MMAS_PER_STAGE; ++j)
-              umma_tf32_lh(d_tmem + cls * BLOCK_N, a_lo + 2 * j, b_lo + i * ((BLOCK_N * KBYTES) >> 4) + 2 * j,
-                           desc_hi, idesc, (first && j == 0) ? 0u : 1u);
-          }
+          for (int j = 0; j < MMAS_PER_STAGE; ++j)
+            umma_tf32_lh(d_tmem + COL, a_lo + 2 * j, b_lo + 2 * j, desc_hi, idesc_t, (first && j == 0) ? 0u : 1u);
         };
         auto issue_plain = [&](auto lo_tag, uint32_t a_lo, uint32_t b_lo, bool first) {
           constexpr bool WITH_LO = decltype(lo_tag)::value;
@@ -507,7 +515,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
               if (tap_m == 0) issue_s2m(integral_constant<int, 0>{}, a_lo, b_lo, first);
               else if (tap_m == 1) issue_s2m(integral_constant<int, 1>{}, a_lo, b_lo, false);
               else if (tap_m == 2) issue_s2m(integral_constant<int, 2>{}, a_lo, b_lo, false);
-              else issue_s2m(integral_constant<int, 3>{}, a_lo, b_lo, false);
+              else if (tap_m == 3) issue_s2m(integral_constant<int, 3>{}, a_lo, b_lo, false);
+              else issue_s2m(integral_constant<int, 4>{}, a_lo, b_lo, false);
             } else if (SPLIT && !skip_a_lo) {
               issue_plain(integral_constant<bool, true>{}, a_lo, b_lo, ks == 0);
             } else {
@@ -806,8 +815,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
             prefetch(rows[ncls & 1], f_resid && ncls == 0, (st + 1) & 1, pr[(st + 1) & 1], pm[(st + 1) & 1],
                      px[(st + 1) & 1]);
           }
-          process(rows[cls & 1], f_resid && cls == 0, t_addr + cls * BLOCK_N, ch, pr[st & 1], pm[st & 1],
-                  px[st & 1]);
+          process(rows[cls & 1], f_resid && cls == 0, t_addr + s2m_class_pos(cls) * BLOCK_N, ch, pr[st & 1],
+                  pm[st & 1], px[st & 1]);
         }
       } else if constexpr (WPT == 8) {
         // one chunk per warp: the group's first four warps take columns 0..31, the others 32..63

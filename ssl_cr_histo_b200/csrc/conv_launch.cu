@@ -141,6 +141,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.bnb_scale = a.bnb_scale; p.bnb_shift = a.bnb_shift;
   p.a_lo_nonzero = a.a_lo_nonzero;
   p.a_tiled2d = a.a_tiled2d;
+  p.s2m_shortcut = 0;
   p.o_step = a.o_step; p.o_h0 = a.o_h0; p.o_w0 = a.o_w0; p.o_H = a.o_H; p.o_W = a.o_W;
   if (a.o_step != 0 && a.stats != nullptr) return set_error("conv: stats with strided output");
   if ((a.scale != nullptr) != (a.shift != nullptr))
@@ -322,13 +323,26 @@ int launch_conv_dgrad_s2(const ConvArgs& a, cudaStream_t stream) {
     return set_error("conv_dgrad_s2: %s", tmap_last_error());
   m.a_lo = m.a;
   m.b_lo = m.b;
+  if (a.x2 != nullptr || a.w2 != nullptr) {
+    // fused 1x1 stride-2 shortcut: dY of the shortcut conv (same geometry as dy) and its data-gradient
+    // pack [C][K] feed a fifth K block of class (0,0)
+    if (a.x2 == nullptr || a.w2 == nullptr) return set_error("conv_dgrad_s2: shortcut needs dy_sc and w_sc");
+    if (a.resid != nullptr) return set_error("conv_dgrad_s2: fused shortcut and resid are exclusive");
+    if (make_im2col_map(&m.a_lo, a.x2, kF32, a.N, a.H, a.W, a.Cin, 2, 2, 0, 1, 0, 1, 1, 32, kBlockM, 128))
+      return set_error("conv_dgrad_s2: %s", tmap_last_error());
+    if (make_tiled_map_2d(&m.b_lo, a.w2, kF32, a.Cout, (uint64_t)a.Cin, (uint64_t)a.Cin, 64, 32, 128))
+      return set_error("conv_dgrad_s2: %s", tmap_last_error());
+    p.s2m_shortcut = 1;
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = device_sm_count();
   if (tiles < grid) grid = tiles;
   if (epi_groups_mask() & 2) {
-    // two epilogue groups of four warps; the shortcut + gate combination the network uses is compiled in
+    // two epilogue groups of four warps; the operand combinations the network uses are compiled in
     if (a.resid != nullptr && a.gate != nullptr)
       return launch_variant<64, 128, 4, false, false, false, kEpiOut32 | kEpiResid32 | kEpiGate, 8, true, 2>(m, p, grid, stream);
+    if (a.resid == nullptr && a.gate != nullptr)
+      return launch_variant<64, 128, 4, false, false, false, kEpiOut32 | kEpiGate, 8, true, 2>(m, p, grid, stream);
     return launch_variant<64, 128, 4, false, false, false, -1, 8, true, 2>(m, p, grid, stream);
   }
   return launch_variant<64, 128, 4, false, false, false, -1, 4, true>(m, p, grid, stream);

@@ -42,6 +42,8 @@ struct PerDeviceMax {
 struct ConvArgs {
   const float* x = nullptr;      // plain mode: TF32 operands in fp32 containers
   const float* w = nullptr;
+  const float* x2 = nullptr;     // merged stride-2 data gradient only: dY of the block's 1x1 shortcut
+  const float* w2 = nullptr;     // conv and its data-gradient pack [C][K] (accumulated into class (0,0))
   const __half* x_h = nullptr;   // split mode: error-compensated (hi, lo) FP16 operand pairs
   const __half* x_l = nullptr;
   const __half* w_h = nullptr;

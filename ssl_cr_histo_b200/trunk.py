@@ -280,6 +280,9 @@ OVERLAP_WGRAD = os.environ.get("B2N_OVERLAP_WGRAD", "0") not in ("", "0")
 # Stride-2 data gradients: one merged launch over dY for the four output-parity classes (default),
 # or -- B2N_NO_S2M=1 -- one launch per class (same arithmetic; dY is then read four times).
 MERGED_S2_DGRAD = os.environ.get("B2N_NO_S2M", "0") in ("", "0")
+# ... with the block's 1x1 shortcut gradient accumulated inside that launch (default), or --
+# B2N_NO_S2M_SC=1 -- as a 1x1 launch of its own whose result the merged kernel adds (resid).
+FUSED_S2_SHORTCUT = os.environ.get("B2N_NO_S2M_SC", "0") in ("", "0")
 
 # Weight gradients are split-K sums over pixel slabs.  By default every split stores its own plane
 # and the unpack kernel adds the planes in a fixed order: bit-repeatable gradients for ~20 MB of
@@ -709,15 +712,22 @@ class _TrunkFn(torch.autograd.Function):
                     # tap subsets over dY, each writing (and ReLU-gating) its own quarter of g_in.
                     g_in = torch.empty(N, h, w, cin, device=dev, dtype=torch.float32)
                     wdd = packs.get("b%d.wdd" % bi, dconv.weight, _pack_dgrad)
-                    _conv(dyd, wdd, N, ph, pw, cout, cin, 1, 1, 0, 0, out=g_in,
-                          placement=(2, 0, 0, h, w))
+                    fused_sc = MERGED_S2_DGRAD and FUSED_S2_SHORTCUT
+                    if not fused_sc:
+                        _conv(dyd, wdd, N, ph, pw, cout, cin, 1, 1, 0, 0, out=g_in,
+                              placement=(2, 0, 0, h, w))
                     if MERGED_S2_DGRAD:
                         wm = packs.get("b%d.w1s2m" % bi, blk.conv1.weight, _pack_dgrad_s2m)
-                        flops = 2.0 * N * ph * pw * cout * cin * 9
-                        call("b2n_conv_dgrad_s2", dy1, wm, g_in, N, ph, pw, cout, cin, h, w, g_in, in_gate,
-                             work=(flops, 0.0, flops, "dgrad",
-                                   4.0 * N * (ph * pw * cout + h * w * cin * (2 if in_gate is not None else 1)
-                                              + ph * pw * cin)))
+                        flops = 2.0 * N * ph * pw * cout * cin * (10 if fused_sc else 9)
+                        byt = 4.0 * N * (ph * pw * cout * (2 if fused_sc else 1)
+                                         + h * w * cin * (2 if in_gate is not None else 1)
+                                         + (0 if fused_sc else ph * pw * cin))
+                        if fused_sc:
+                            call("b2n_conv_dgrad_s2_sc", dy1, wm, dyd, wdd, g_in, N, ph, pw, cout, cin, h, w,
+                                 in_gate, work=(flops, 0.0, flops, "dgrad", byt))
+                        else:
+                            call("b2n_conv_dgrad_s2", dy1, wm, g_in, N, ph, pw, cout, cin, h, w, g_in, in_gate,
+                                 work=(flops, 0.0, flops, "dgrad", byt))
                     else:
                         wcls = packs.get("b%d.w1s2" % bi, blk.conv1.weight, _pack_dgrad_s2)
                         for cls, (a0, b0) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):

@@ -296,6 +296,13 @@ def test_conv_dgrad_stride2_parity_classes_bit_exact(shape):
         call("b2n_conv_dgrad_s2", d3, wm, g_in, N, P, Q, Cout, Cin, H, W, g_in, gate)
         want = ref if gate is None else torch.where(act > 0, ref, torch.zeros(()))
         assert torch.equal(from_nhwc(g_in.cpu()), want), gate is None
+    # ... with the 1x1 shortcut gradient accumulated inside the launch (a fifth K block of class (0,0))
+    for gate in (None, gate_t):
+        g_in.fill_(float("nan"))
+        call("b2n_conv_dgrad_s2_sc", d3, wm, to_nhwc(dy1).to(DEV), pack_dgrad(w1), g_in, N, P, Q, Cout, Cin,
+             H, W, gate)
+        want = ref if gate is None else torch.where(act > 0, ref, torch.zeros(()))
+        assert torch.equal(from_nhwc(g_in.cpu()), want), gate is None
     # without the shortcut term
     call("b2n_conv_dgrad_s2", d3, wm, g_in, N, P, Q, Cout, Cin, H, W, None, None)
     assert torch.equal(from_nhwc(g_in.cpu()),
