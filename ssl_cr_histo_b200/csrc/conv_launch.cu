@@ -290,6 +290,10 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
       return launch_variant<128, 128, 5, false, false, false, kDgradBn>(m, p, grid, stream);
     if (block_n == 256 && epi == kDgradBn)
       return launch_variant<256, 128, 4, false, false, false, kDgradBn>(m, p, grid, stream);
+    // ... and conv1's data gradient of layer 2's identity block: shortcut gradient + the input's ReLU
+    // gate (400 -> 335 us; the 256-wide tiles of layers 3-4 measure the same compiled or generic)
+    if (block_n == 128 && epi == kDgradResGate)
+      return launch_variant<128, 128, 5, false, false, false, kDgradResGate>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 5, false, false>(m, p, grid, stream);
     if (block_n == 256) return launch_variant<256, 128, 4, false, false>(m, p, grid, stream);
   }
