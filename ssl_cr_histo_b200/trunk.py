@@ -270,13 +270,19 @@ class ResNet18Trunk(nn.Module):
 
 
 # Weight gradients are off the backward pass' critical path (nothing downstream reads them until
-# the optimizer), so they can be enqueued on a side stream where the tensor-core wgrad kernels
-# overlap the HBM-bound BatchNorm-backward kernels of the layers below.  Opt-in
-# (B2N_OVERLAP_WGRAD=1): on the power-capped B200s measured here it gained 0.3-0.9 ms of a 39 ms
-# step on average but produced occasional +3..+20 ms outliers (two persistent 1-CTA/SM kernels
-# contending for the SMs), so the default keeps the whole step on one stream.
-_SIDE_STREAMS = {}
-OVERLAP_WGRAD = os.environ.get("B2N_OVERLAP_WGRAD", "0") not in ("", "0")
+# the optimizer), so they run on a side stream next to the HBM-bound kernels of the main chain.
+# B2N_OVERLAP_WGRAD=2 (default) is the ordered schedule: a weight gradient is held back until the
+# next element-wise phase of the main chain (BatchNorm-backward reduce / apply, the pooling
+# sweeps), launched on the side stream just before it, and the next tensor-core launch of the main
+# chain waits for it -- a weight gradient only ever shares the SMs with HBM-bound kernels, never
+# with another persistent conv kernel.  Measured on the power-capped B200s: -0.5 ms per cfg3 step
+# at one GPU, -0.4 ms at two (gradients bit-identical to the single-stream pass, also through the
+# overlapped bucket all-reduce: tools/ddp_check.py).  =1 is the first, unordered variant (the weight
+# gradient starts as soon as its operands exist and may share the SMs with the next data-gradient
+# conv: -0.2 ms on average, occasional +3..+20 ms outliers when two persistent 1-CTA/SM kernels
+# contend), =0 keeps the whole pass on one stream.
+_ov = os.environ.get("B2N_OVERLAP_WGRAD", "2")
+OVERLAP_WGRAD = 0 if _ov in ("", "0") else (2 if _ov == "2" else 1)
 # Stride-2 data gradients: one merged launch over dY for the four output-parity classes (default),
 # or -- B2N_NO_S2M=1 -- one launch per class (same arithmetic; dY is then read four times).
 MERGED_S2_DGRAD = os.environ.get("B2N_NO_S2M", "0") in ("", "0")
@@ -338,6 +344,10 @@ class _Act:
         self.f32 = torch.empty(shape, device=dev, dtype=torch.float32) if with_f32 else None
 
 
+# (backward pass, B2N_OVERLAP_WGRAD=2: called before every tensor-core launch of the main chain)
+_BEFORE_CONV = []
+
+
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
           resid=None, resid_pair=None, mask=None, relu=0, rnd=0, stats=None, out=None,
           out_pair=None, want_out=True, alg=1.0, lo_flag=None, pad_hi_w=None, R_w=None,
@@ -373,6 +383,8 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
         work = (nominal * alg, 0.0, nominal, "dgrad", byt)
     # bnb = (y, BN state, gate_from_y): BatchNorm-backward sums of the result, see b2n.h
     by, bst, bgate = bnb if bnb is not None else (None, None, False)
+    if _BEFORE_CONV:
+        _BEFORE_CONV[-1]()
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, S, stride,
          pad_lo, pad_hi, pad_lo, phw, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
          lo_flag, *placement, gate, by, bst.mean if bst else None, bst.invstd if bst else None,
@@ -588,6 +600,44 @@ class _TrunkFn(torch.autograd.Function):
                 make(t, 0)
                 grads[id(p)] = t
 
+        main = torch.cuda.current_stream(dev)
+        # (per-launch timing for bench.py's roofline keeps everything on one stream)
+        side = _side_stream(dev) if OVERLAP_WGRAD and _lib.PROFILE is None else None
+        # Ordered overlap (B2N_OVERLAP_WGRAD=2): weight gradients wait in `pending` until the next
+        # element-wise phase, run on the side stream next to it, and the next tensor-core launch of
+        # the main chain waits for them (side_busy = their completion event).
+        ordered = side is not None and OVERLAP_WGRAD == 2
+        pending, side_busy = [], [None]
+
+        def elementwise_phase():
+            """Called right before the main chain launches HBM-bound kernels: the held-back weight
+            gradients go to the side stream first (their single CTA per SM is placed before the
+            element-wise blocks fill the thread slots)."""
+            if not pending:
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for fn in pending:
+                    fn()
+                done = torch.cuda.Event()
+                done.record(side)
+            side_busy[0] = done
+            pending.clear()
+
+        def before_conv():
+            if side_busy[0] is not None:
+                main.wait_event(side_busy[0])
+                side_busy[0] = None
+
+        del _BEFORE_CONV[:]       # (a hook left behind by a pass that raised is dropped here)
+        del ACTIVE_BACKWARD_STREAMS[:]
+        if ordered:
+            _BEFORE_CONV.append(before_conv)
+        if side is not None:
+            ACTIVE_BACKWARD_STREAMS.extend((main, side))
+
         def bn_backward(g, y, st, bn, rows, C, reduced=False, gate_from_y=False):
             """g: gradient w.r.t. the BN output, already ReLU-gated by its producer (the gate of
             every activation gradient is applied by the kernel that writes it).  ``reduced``: the
@@ -596,6 +646,8 @@ class _TrunkFn(torch.autograd.Function):
             stem's unfused chain)."""
             gsc, gsh = (st.scale, st.shift) if gate_from_y else (None, None)
             sums = sums_of(bn)
+            if ordered:
+                elementwise_phase()
             if not reduced:
                 call("b2n_bn_bwd_reduce", g, None, y, st.mean, st.invstd, gsc, gsh, sums, rows, C)
             dy = torch.empty_like(y)
@@ -619,10 +671,6 @@ class _TrunkFn(torch.autograd.Function):
                 if bg:
                     grads[id(bn.bias)] = dbeta
             return dy
-
-        main = torch.cuda.current_stream(dev)
-        # (per-launch timing for bench.py's roofline keeps everything on one stream)
-        side = _side_stream(dev) if OVERLAP_WGRAD and _lib.PROFILE is None else None
 
         class _on_side:
             """Run the enclosed launches on the side stream once everything enqueued on the main
@@ -652,16 +700,27 @@ class _TrunkFn(torch.autograd.Function):
             K, C, R, S = conv.weight.shape
             P, Q = dy.shape[1], dy.shape[2]
             wflops = 2.0 * N * P * Q * K * R * S * C
-            with _on_side(x_in, dy):
+
+            def run():
                 planes = _lib.wgrad_planes(N, H, W, C, K, R, S, stride, pad, pad, pad, pad) if det else 1
                 dwp = torch.empty(planes, K, R * S * C, device=dev) if det else dwp_of(conv, K, R * S * C)
                 call("b2n_conv_wgrad", x_in, dy, dwp, N, H, W, C, K, R, S, stride, pad, pad, pad, pad,
                      1 if det else 0, 0,
                      work=(wflops, 0.0, wflops, "wgrad", 4.0 * N * (H * W * C + P * Q * K)))
                 emit(conv.weight, lambda t, acc: call("b2n_unpack_wgrad", dwp, t, K, C, R, S, acc, planes))
-            dw = grads[id(conv.weight)]
-            if side is not None and dw is not None:
-                dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
+                dw = grads[id(conv.weight)]
+                if side is not None and dw is not None:
+                    dw.record_stream(main)   # consumed by autograd / the optimizer on the main stream
+
+            if ordered:
+                def deferred():
+                    x_in.record_stream(side)
+                    dy.record_stream(side)
+                    run()
+                pending.append(deferred)
+                return
+            with _on_side(x_in, dy):
+                run()
 
         # The stem's maxpool + ReLU + BN backward runs as two band sweeps over the stem output (below)
         # when two double-buffered band slots (2 rows of y + 2 pooled rows of gradients / codes) fit
@@ -722,6 +781,7 @@ class _TrunkFn(torch.autograd.Function):
                         byt = 4.0 * N * (ph * pw * cout * (2 if fused_sc else 1)
                                          + h * w * cin * (2 if in_gate is not None else 1)
                                          + (0 if fused_sc else ph * pw * cin))
+                        before_conv()
                         if fused_sc:
                             call("b2n_conv_dgrad_s2_sc", dy1, wm, dyd, wdd, g_in, N, ph, pw, cout, cin, h, w,
                                  in_gate, work=(flops, 0.0, flops, "dgrad", byt))
@@ -754,6 +814,8 @@ class _TrunkFn(torch.autograd.Function):
                 # maxpool + ReLU + BN backward fused: one sweep over the stem output (two when the
                 # sums did not come out of the first block's data-gradient epilogue) instead of five
                 sums = sums_of(trunk.bn1)
+                if ordered:
+                    elementwise_phase()
                 if not stem_sums_done:
                     call("b2n_pool_bn_bwd_reduce", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift,
                          bn0.mean, bn0.invstd, sums, N, H2, W2, 64)
@@ -779,6 +841,8 @@ class _TrunkFn(torch.autograd.Function):
                         grads[id(bb)] = dbeta
             else:
                 gz = torch.empty_like(sv["y0"])
+                if ordered:
+                    elementwise_phase()
                 call("b2n_maxpool_relu_bwd", g, sv["idx"], sv["y0"], bn0.scale, bn0.shift, gz, N, H2,
                      W2, 64)
                 dy0 = bn_backward(gz, sv["y0"], bn0, trunk.bn1, N * H2 * W2, 64)
@@ -797,6 +861,10 @@ class _TrunkFn(torch.autograd.Function):
                 if side is not None and dw is not None:
                     dw.record_stream(main)
 
+        if ordered:
+            elementwise_phase()      # weight gradients still held back (nothing left to pair them with)
+            del _BEFORE_CONV[:]
         if side is not None:
             main.wait_stream(side)   # all weight gradients are complete before anyone reads them
+            del ACTIVE_BACKWARD_STREAMS[:]
         return (None, None, None, None) + tuple(grads[id(p)] for p in params)
