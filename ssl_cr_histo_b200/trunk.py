@@ -281,6 +281,10 @@ class ResNet18Trunk(nn.Module):
 # gradient starts as soon as its operands exist and may share the SMs with the next data-gradient
 # conv: -0.2 ms on average, occasional +3..+20 ms outliers when two persistent 1-CTA/SM kernels
 # contend), =0 keeps the whole pass on one stream.
+_SIDE_STREAMS = {}
+# (main, side) streams of the backward pass that is running, when it uses a side stream: a consumer
+# that is started from inside the pass (ddp.GradAllReducer's bucket all-reduce) must wait for both.
+ACTIVE_BACKWARD_STREAMS = []
 _ov = os.environ.get("B2N_OVERLAP_WGRAD", "2")
 OVERLAP_WGRAD = 0 if _ov in ("", "0") else (2 if _ov == "2" else 1)
 # Stride-2 data gradients: one merged launch over dY for the four output-parity classes (default),
