@@ -7,8 +7,8 @@ Tolerances (BASELINE.json north_star / SURVEY.md section 8d):
     error-compensated 3xTF32);
   * RSP argmax: bit-exact, with an asserted top-2 margin floor;
   * BN running statistics: <= 1e-3 relative (measured ~3e-5), counters exact;
-  * gradients: <= 2.5e-2 relative L2 per tensor; the largest value any test here measures is 1.52e-2
-    (gpurun_out/grad_worst.jsonl; 8.9e-3 at full cfg3 size, 1.5e-2 at full cfg2 size).  SURVEY 8(d)
+  * gradients: <= 2.5e-2 relative L2 per tensor; the largest value any test here measures is 1.57e-2
+    (gpurun_out/grad_worst.jsonl; 9.3e-3 at full cfg3 size, 1.6e-2 at full cfg2 size).  SURVEY 8(d)
     asked for 1e-3; tools/grad_gate.py (profiles/r2_grad_gate.md, N=8 at 224x224) shows that no
     implementation meets that against an fp32 oracle: the oracle in float64 -- the exact answer -- is
     itself 4.3e-3 (worst tensor) / 2.5e-3 (median) away from the fp32 oracle, torch + cuDNN in strict

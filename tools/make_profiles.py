@@ -31,17 +31,19 @@ Command (one GPU, eager launches so that every kernel is a separate ncu launch; 
 
 Raw list: `r2_kernels.csv.gz`; machine-readable aggregate: `r2_kernels.json`; readers:
 `tools/kernel_table.py`, `tools/make_profiles.py`.  Per-launch numbers are cold-cache and serialised
-(compare shares and per-kernel rates, not the absolute total: the same build measures 33.6-34.3
-ms/step with CUDA events).  `tensor pipe %` = `sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active`,
+(compare shares and per-kernel rates, not the absolute total: the same build measures 31.0-31.9
+ms/step with CUDA events, where the weight gradients also overlap the element-wise kernels).  `tensor pipe %` = `sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active`,
 time-weighted over the kernel's launches; `achieved GB/s` = measured DRAM bytes / device time (the
 pool's measured copy bandwidth is 6558 GB/s, `MEASURED_PEAKS.json`).  Rows below 0.25 % of the step
 are omitted (they are in the JSON).  Template arguments of `conv_igemm_kernel<BLOCK_N, KBYTES, STAGES,
-SPLIT, RES_B, HALO, EPI, EPI_WARPS>`: SPLIT=1 error-compensated FP16 (hi,lo) forward, SPLIT=0 one TF32
-pass (data gradients); EPI: 65 = BN statistics + fp32 y (train forward), 98 / 162 / 178 / 166 = folded
-BN + ReLU (+ FP16-pair / fp32 shortcut) (eval forward), 3136 = bn1 ReLU gate + BatchNorm-backward
-sums, 580 = shortcut gradient + input ReLU gate, 1604 = the same + the stem BatchNorm's sums, 68 =
-shortcut gradient only; a cut-off trailing argument = generic run-time epilogue (the 1x1 data
-gradients; `<64, 128, 4, 0, 0, 0, ...` = the merged stride-2 data gradient, S2M).
+SPLIT, RES_B, HALO, EPI, EPI_WARPS, S2M, EPI_GROUPS, RPS>`: SPLIT=1 error-compensated FP16 (hi,lo)
+forward, SPLIT=0 one TF32 pass (data gradients); EPI: 65 = BN statistics + fp32 y (train forward), 98 /
+162 / 178 / 166 = folded BN + ReLU (+ FP16-pair / fp32 shortcut) (eval forward), 3136 = bn1 ReLU gate +
+BatchNorm-backward sums, 580 = shortcut gradient + input ReLU gate, 1604 = the same + the stem
+BatchNorm's sums, 68 = shortcut gradient only, 576 = input ReLU gate only (the merged stride-2 data
+gradient with the 1x1 shortcut accumulated in the kernel, S2M = 1); a cut-off trailing argument =
+generic run-time epilogue; EPI_GROUPS = 2: two groups of epilogue warps, one per TMEM accumulator stage;
+RPS = 4: the stem's four filter rows as one pipeline stage.
 
 """
 groups = json.load(open(P + "%s_kernels.json" % tag))
