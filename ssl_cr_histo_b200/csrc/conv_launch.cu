@@ -209,6 +209,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr int kEvalActRes = kEvalAct | kEpiResid16;                    // ... + identity shortcut
   constexpr int kEvalActRes32 = kEvalAct | kEpiResid32;                  // ... + fp32 shortcut (downsample branch)
   constexpr int kEvalStem = kEpiAffine | kEpiRelu | kEpiOut32;
+  constexpr int kEvalDown = kEpiAffine | kEpiOut32;                      // folded BN, no ReLU -> fp32
   constexpr int kDgrad = kEpiOut32;
   constexpr int kDgradRes = kEpiOut32 | kEpiResid32;                     // + (pre-gated) shortcut gradient
   constexpr int kDgradResGate = kDgradRes | kEpiGate;                    // ... then the input's ReLU gate
@@ -279,6 +280,9 @@ int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     if (block_n == 256 && epi == kTrainFwd) return launch_variant<256, 128, 2, true, false, false, kTrainFwd>(m, p, grid, stream);
     if (block_n == 128 && epi == kEvalActRes32) return launch_variant<128, 128, 3, true, false, false, kEvalActRes32>(m, p, grid, stream);
     if (block_n == 256 && epi == kEvalActRes32) return launch_variant<256, 128, 2, true, false, false, kEvalActRes32>(m, p, grid, stream);
+    // eval mode, the 1x1 stride-2 shortcut convs: folded BN only, fp32 result (the block's conv2 adds it)
+    if (block_n == 128 && epi == kEvalDown) return launch_variant<128, 128, 3, true, false, false, kEvalDown>(m, p, grid, stream);
+    if (block_n == 256 && epi == kEvalDown) return launch_variant<256, 128, 2, true, false, false, kEvalDown>(m, p, grid, stream);
     if (block_n == 128) return launch_variant<128, 128, 3, true, false>(m, p, grid, stream);
     if (block_n == 256) return launch_variant<256, 128, 2, true, false>(m, p, grid, stream);
   } else if (split) {

@@ -660,6 +660,38 @@ def test_example_loop_runs_the_whole_pipeline():
         assert torch.equal(v, w), k
 
 
+def test_side_stream_weight_gradients_are_bit_identical_to_the_single_stream_pass():
+    """trunk.OVERLAP_WGRAD: 2 (default) runs every weight gradient on a side stream beside the next
+    element-wise phase of the backward pass, 1 as soon as its operands exist, 0 on the main stream.
+    Same kernels, same operands: the gradients must agree bit for bit, step after step."""
+    from ssl_cr_histo_b200 import trunk
+    _, _, gm, gh = pair("finetune", ("finetune", 9))
+    x = O.synthetic_patches(6, 96, seed=121).to(DEV)
+    target = torch.tensor([0, 3, 8, 1, 5, 2], device=DEV)
+
+    def grads(mode):
+        old, trunk.OVERLAP_WGRAD = trunk.OVERLAP_WGRAD, mode
+        try:
+            m, c = copy.deepcopy(gm).train(), copy.deepcopy(gh)
+            out = []
+            for _ in range(2):
+                m.zero_grad(set_to_none=True); c.zero_grad(set_to_none=True)
+                F.cross_entropy(c(m(x)), target).backward()
+                torch.cuda.synchronize()
+                out.append([p.grad.clone() for p in m.parameters()])
+            return out
+        finally:
+            trunk.OVERLAP_WGRAD = old
+
+    assert trunk.OVERLAP_WGRAD == 2
+    ref = grads(0)
+    for mode in (2, 1):
+        got = grads(mode)
+        for step, (a, b) in enumerate(zip(ref, got)):
+            for (n, _), u, v in zip(gm.named_parameters(), a, b):
+                assert torch.equal(u, v), (mode, step, n)
+
+
 def test_merged_stride2_data_gradient_equals_the_per_class_launches():
     """The three stride-2 blocks' data gradients: one merged launch (four accumulators per tile)
     against the four per-class launches -- same taps in the same order, so the whole backward pass
