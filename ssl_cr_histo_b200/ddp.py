@@ -135,7 +135,7 @@ class GradAllReducer:
             # a backward pass that runs its weight gradients on a side stream reports gradients from
             # both of its streams: the bucket is complete only when both have caught up
             from . import trunk as _trunk
-            for st in _trunk.ACTIVE_BACKWARD_STREAMS:
+            for st in _trunk.active_backward_streams():
                 self._stream.wait_stream(st)
             with torch.cuda.stream(self._stream):
                 work = dist.all_reduce(self.flat[start:end], op=dist.ReduceOp.SUM, group=self.group,

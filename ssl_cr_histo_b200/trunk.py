@@ -13,6 +13,7 @@ next conv's tensor-core operand) are kept for the backward pass.
 from __future__ import annotations
 
 import os
+import threading
 from typing import List, Optional
 
 import torch
@@ -282,9 +283,28 @@ class ResNet18Trunk(nn.Module):
 # conv: -0.2 ms on average, occasional +3..+20 ms outliers when two persistent 1-CTA/SM kernels
 # contend), =0 keeps the whole pass on one stream.
 _SIDE_STREAMS = {}
-# (main, side) streams of the backward pass that is running, when it uses a side stream: a consumer
-# that is started from inside the pass (ddp.GradAllReducer's bucket all-reduce) must wait for both.
-ACTIVE_BACKWARD_STREAMS = []
+# Per-thread state of the backward pass that is running (nn.DataParallel drives one host thread per
+# GPU, so two passes may be in flight in one process): `before_conv` -- hooks called before every
+# tensor-core launch of the main chain; `streams` -- the (main, side) streams of the pass when it
+# uses a side stream: a consumer that is started from inside the pass (ddp.GradAllReducer's bucket
+# all-reduce) must wait for both.
+_TLS = threading.local()
+
+
+def _before_conv_hooks() -> list:
+    h = getattr(_TLS, "before_conv", None)
+    if h is None:
+        h = _TLS.before_conv = []
+    return h
+
+
+def active_backward_streams() -> list:
+    st = getattr(_TLS, "streams", None)
+    if st is None:
+        st = _TLS.streams = []
+    return st
+
+
 _ov = os.environ.get("B2N_OVERLAP_WGRAD", "2")
 OVERLAP_WGRAD = 0 if _ov in ("", "0") else (2 if _ov == "2" else 1)
 # Stride-2 data gradients: one merged launch over dY for the four output-parity classes (default),
@@ -348,10 +368,6 @@ class _Act:
         self.f32 = torch.empty(shape, device=dev, dtype=torch.float32) if with_f32 else None
 
 
-# (backward pass, B2N_OVERLAP_WGRAD=2: called before every tensor-core launch of the main chain)
-_BEFORE_CONV = []
-
-
 def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, shift=None,
           resid=None, resid_pair=None, mask=None, relu=0, rnd=0, stats=None, out=None,
           out_pair=None, want_out=True, alg=1.0, lo_flag=None, pad_hi_w=None, R_w=None,
@@ -387,8 +403,9 @@ def _conv(x, wp, N, H, W, Cin, Cout, R, stride, pad_lo, pad_hi, *, scale=None, s
         work = (nominal * alg, 0.0, nominal, "dgrad", byt)
     # bnb = (y, BN state, gate_from_y): BatchNorm-backward sums of the result, see b2n.h
     by, bst, bgate = bnb if bnb is not None else (None, None, False)
-    if _BEFORE_CONV:
-        _BEFORE_CONV[-1]()
+    hooks = _before_conv_hooks()       # (backward pass with ordered side-stream weight gradients)
+    if hooks:
+        hooks[-1]()
     call("b2n_conv_fwd", x32, xh, xl, w32, wh, wl, out, oh, ol, N, H, W, Cin, Cout, R, S, stride,
          pad_lo, pad_hi, pad_lo, phw, scale, shift, resid, rh, rl, mask, relu, rnd, stats,
          lo_flag, *placement, gate, by, bst.mean if bst else None, bst.invstd if bst else None,
@@ -635,12 +652,13 @@ class _TrunkFn(torch.autograd.Function):
                 main.wait_event(side_busy[0])
                 side_busy[0] = None
 
-        del _BEFORE_CONV[:]       # (a hook left behind by a pass that raised is dropped here)
-        del ACTIVE_BACKWARD_STREAMS[:]
+        hooks, active = _before_conv_hooks(), active_backward_streams()
+        del hooks[:]              # (a hook left behind by a pass that raised is dropped here)
+        del active[:]
         if ordered:
-            _BEFORE_CONV.append(before_conv)
+            hooks.append(before_conv)
         if side is not None:
-            ACTIVE_BACKWARD_STREAMS.extend((main, side))
+            active.extend((main, side))
 
         def bn_backward(g, y, st, bn, rows, C, reduced=False, gate_from_y=False):
             """g: gradient w.r.t. the BN output, already ReLU-gated by its producer (the gate of
@@ -867,8 +885,8 @@ class _TrunkFn(torch.autograd.Function):
 
         if ordered:
             elementwise_phase()      # weight gradients still held back (nothing left to pair them with)
-            del _BEFORE_CONV[:]
+            del hooks[:]
         if side is not None:
             main.wait_stream(side)   # all weight gradients are complete before anyone reads them
-            del ACTIVE_BACKWARD_STREAMS[:]
+            del active[:]
         return (None, None, None, None) + tuple(grads[id(p)] for p in params)
