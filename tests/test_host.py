@@ -134,6 +134,41 @@ def test_pickled_module_drops_the_packed_weight_cache():
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
 
 
+def test_pack_cache_staleness_rules():
+    """The cache the multi-tensor prefill and the lazy per-conv path share: an entry is fresh for the
+    tensor state it was built from, stale after an in-place write autograd sees, after this
+    package's optimizer / lerp epochs, and after invalidate() (p.data writes, graph capture)."""
+    from ssl_cr_histo_b200 import _lib
+    from ssl_cr_histo_b200.trunk import _PackCache
+    cache, p = _PackCache(), torch.nn.Parameter(torch.ones(4))
+    calls = []
+
+    def maker(w):
+        calls.append(1)
+        return w.clone()
+
+    assert cache.stale("k", p)
+    a = cache.get("k", p, maker)
+    assert not cache.stale("k", p) and cache.get("k", p, maker) is a and len(calls) == 1
+    cache.put("other", p, "packed elsewhere")                    # what the multi-tensor prefill does
+    assert cache.get("other", p, maker) == "packed elsewhere" and len(calls) == 1
+    with torch.no_grad():
+        p.add_(1.0)                                              # bumps p._version
+    assert cache.stale("k", p) and cache.get("k", p, maker) is not a and len(calls) == 2
+    p._b2n_epoch = 7                                             # fused optimizer kernels
+    assert cache.stale("k", p)
+    cache.get("k", p, maker)
+    _lib.WEIGHT_EPOCH += 1                                       # weights.lerp_
+    assert cache.stale("k", p)
+    cache.get("k", p, maker)
+    p.data.mul_(0.5)                                             # invisible to every tag ...
+    assert not cache.stale("k", p)
+    cache.invalidate()                                           # ... hence the explicit invalidation
+    assert cache.stale("k", p) and cache.stale("other", p)
+    b = cache.get("k", p, maker)
+    assert torch.equal(b, p.detach()) and not cache.stale("k", p)
+
+
 def test_no_cpu_fallback():
     m, c = net.TripletNet("resnet18"), net.Classifier(768, 6)
     x = torch.zeros(1, 3, 32, 32)
